@@ -1,0 +1,81 @@
+"""ctypes binding of ``csrc/libbnsgcn.so`` (the C ABI declared in ``include/bnsgcn.h``).
+
+There is deliberately no fallback: if the shared library is missing or does not export a symbol the
+header declares, importing this module raises.  Build it with ``python __graft_entry__.py`` (or
+``__graft_entry__.build()``).
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+from ctypes import POINTER, c_char_p, c_float, c_int, c_int32, c_int64, c_size_t, c_uint64, c_void_p
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "csrc", "libbnsgcn.so")
+
+ABI_VERSION = 1
+P2P_HANDLE_BYTES = 64
+
+# name -> (restype, argtypes); must list every function of include/bnsgcn.h (tests check this)
+SIGNATURES = {
+    "bns_abi_version": (c_int, []),
+    "bns_last_error": (c_char_p, []),
+    "bns_device_info": (c_int, [c_char_p, c_size_t, POINTER(c_int), POINTER(c_int64), POINTER(c_int), POINTER(c_int)]),
+    "bns_graph_create": (c_int, [POINTER(c_void_p), c_int64, c_int64, c_int64, c_void_p, c_void_p, c_int32, c_void_p]),
+    "bns_graph_transpose": (c_int, [c_void_p, POINTER(c_void_p), c_void_p]),
+    "bns_graph_destroy": (c_int, [c_void_p]),
+    "bns_graph_info": (c_int, [c_void_p, POINTER(c_int64), POINTER(c_int64), POINTER(c_int64), POINTER(c_int64),
+                               POINTER(c_int64)]),
+    "bns_graph_copy_csr": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p]),
+    "bns_spmm_workspace_bytes": (c_size_t, [c_void_p, c_int64]),
+    "bns_spmm_sum_f32": (c_int, [c_void_p, c_void_p, c_int64, c_int64, c_void_p, c_int64, c_void_p, c_void_p,
+                                 c_void_p, c_void_p, c_int64, c_int, c_void_p, c_size_t, c_void_p]),
+    "bns_gather_div_f32": (c_int, [c_void_p, c_int64, c_int64, c_void_p, c_int64, c_float, c_void_p, c_int64, c_void_p]),
+    "bns_scatter_add_div_f32": (c_int, [c_void_p, c_int64, c_int64, c_void_p, c_int64, c_float, c_void_p, c_int64,
+                                        c_void_p]),
+    "bns_copy_rows_f32": (c_int, [c_void_p, c_int64, c_void_p, c_int64, c_int64, c_int64, c_void_p]),
+    "bns_sample_workspace_bytes": (c_size_t, [c_int64]),
+    "bns_sample_boundary": (c_int, [c_void_p, c_void_p, c_void_p, c_int32, c_int64, c_int64, c_uint64, c_uint64,
+                                    c_void_p, c_void_p, c_size_t, c_void_p]),
+    "bns_fill_i32": (c_int, [c_void_p, c_int64, c_int32, c_void_p]),
+    "bns_halo_slot_update": (c_int, [c_void_p, c_void_p, c_int64, c_int64, c_int32, c_void_p, c_void_p]),
+    "bns_p2p_create": (c_int, [POINTER(c_void_p), c_int32, c_int32, c_size_t, c_int32]),
+    "bns_p2p_destroy": (c_int, [c_void_p]),
+    "bns_p2p_local": (c_int, [c_void_p, POINTER(c_void_p), POINTER(c_void_p)]),
+    "bns_p2p_export": (c_int, [c_void_p, c_void_p]),
+    "bns_p2p_import": (c_int, [c_void_p, c_int32, c_void_p]),
+    "bns_p2p_set_peer": (c_int, [c_void_p, c_int32, c_void_p, c_void_p]),
+    "bns_p2p_put_rows_f32": (c_int, [c_void_p, c_int32, c_size_t, c_int64, c_void_p, c_int64, c_int64, c_void_p,
+                                     c_int64, c_float, c_int32, c_uint64, c_void_p]),
+    "bns_p2p_wait_flag": (c_int, [c_void_p, c_int32, c_uint64, c_void_p]),
+}
+
+
+class BnsError(RuntimeError):
+    pass
+
+
+def _load() -> ctypes.CDLL:
+    if not os.path.exists(LIB_PATH):
+        raise ImportError(
+            f"{LIB_PATH} is missing: the CUDA extension has not been built. Run `python __graft_entry__.py` "
+            "(nvcc -gencode arch=compute_100a,code=sm_100a). There is no CPU fallback.")
+    lib = ctypes.CDLL(LIB_PATH)
+    for name, (res, args) in SIGNATURES.items():
+        try:
+            fn = getattr(lib, name)
+        except AttributeError as e:
+            raise ImportError(f"{LIB_PATH} does not export {name} (declared in include/bnsgcn.h)") from e
+        fn.restype, fn.argtypes = res, args
+    if lib.bns_abi_version() != ABI_VERSION:
+        raise ImportError(f"{LIB_PATH}: ABI version {lib.bns_abi_version()} != {ABI_VERSION}; rebuild")
+    return lib
+
+
+lib = _load()
+
+
+def check(rc: int, what: str = "") -> None:
+    if rc != 0:
+        msg = lib.bns_last_error()
+        raise BnsError(f"{what or 'libbnsgcn'} failed ({rc}): {msg.decode() if msg else ''}")

@@ -1,0 +1,1046 @@
+// bnsgcn.cu -- sm_100a kernels + the C ABI of include/bnsgcn.h.
+//
+// Hot kernels (all HBM/L2-bound f32 gather / scatter work; no tensor-core shaped math here):
+//   spmm_kernel        K1/K1b/K2  nnz-balanced CSR row-sum, one warp per chunk, 16 B/lane gathers
+//   spmm_fixup_kernel  deterministic combine of rows longer than one chunk
+//   gather / scatter   K3/K5      boundary pack and gradient scatter-add
+//   philox_key / take  K6         counter-based exactly-k sampling (with cub radix sort)
+//   p2p_put_rows       K3+C1      pack straight into the peer's receive slab over NVLink + flag
+//
+// Build: nvcc -gencode arch=compute_100a,code=sm_100a -lineinfo -O3 --shared -Xcompiler -fPIC
+#include "bnsgcn.h"
+
+#include <cuda_runtime.h>
+#include <cub/device/device_radix_sort.cuh>
+#include <cub/device/device_scan.cuh>
+
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <new>
+
+namespace {
+
+thread_local char g_err[512] = "";
+
+int fail(int code, const char *fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+    return code;
+}
+
+#define BNS_CUDA(call)                                                                         \
+    do {                                                                                       \
+        cudaError_t e_ = (call);                                                               \
+        if (e_ != cudaSuccess)                                                                 \
+            return fail(BNS_E_CUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_),    \
+                        __FILE__, __LINE__);                                                   \
+    } while (0)
+
+#define BNS_REQUIRE(cond, ...)                                                                 \
+    do {                                                                                       \
+        if (!(cond)) return fail(BNS_E_INVALID, __VA_ARGS__);                                  \
+    } while (0)
+
+inline cudaStream_t as_stream(void *s) { return reinterpret_cast<cudaStream_t>(s); }
+
+constexpr int kThreads = 256;
+constexpr int kWarps = kThreads / 32;
+constexpr int kDefaultChunk = 1024;
+
+int g_sm_count = 0;
+int sm_count() {
+    if (g_sm_count == 0) {
+        int dev = 0, n = 0;
+        if (cudaGetDevice(&dev) == cudaSuccess &&
+            cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) == cudaSuccess && n > 0)
+            g_sm_count = n;
+        else
+            g_sm_count = 148;
+    }
+    return g_sm_count;
+}
+
+}  // namespace
+
+struct bns_graph {
+    int64_t n_rows = 0, n_cols = 0, nnz = 0;
+    int32_t chunk_nnz = 0;
+    int64_t n_chunks = 0, n_split = 0, n_parts = 0;
+    int64_t *indptr = nullptr;      // [n_rows+1]
+    int32_t *indices = nullptr;     // [nnz]
+    int32_t *chunk_row = nullptr;   // [n_chunks]
+    int64_t *chunk_start = nullptr; // [n_chunks]
+    int32_t *chunk_part = nullptr;  // [n_chunks]  partial-sum slot, -1 when the row is a single chunk
+    int32_t *split_row = nullptr;   // [n_split]
+    int32_t *split_part = nullptr;  // [n_split+1] first partial slot of each split row
+};
+
+// =================================================================================================
+// graph construction
+// =================================================================================================
+namespace {
+
+__global__ void count_chunks_kernel(const int64_t *__restrict__ indptr, int64_t n_rows, int32_t chunk,
+                                    int32_t *__restrict__ n_chunk, int32_t *__restrict__ n_part,
+                                    int32_t *__restrict__ is_split) {
+    int64_t r = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (r >= n_rows) return;
+    int64_t deg = indptr[r + 1] - indptr[r];
+    int32_t c = deg <= chunk ? 1 : (int32_t)((deg + chunk - 1) / chunk);
+    n_chunk[r] = c;
+    n_part[r] = c > 1 ? c : 0;
+    is_split[r] = c > 1 ? 1 : 0;
+}
+
+__global__ void fill_chunks_kernel(const int64_t *__restrict__ indptr, int64_t n_rows, int32_t chunk,
+                                   const int32_t *__restrict__ chunk_off, const int32_t *__restrict__ part_off,
+                                   const int32_t *__restrict__ split_off, int32_t *__restrict__ chunk_row,
+                                   int64_t *__restrict__ chunk_start, int32_t *__restrict__ chunk_part,
+                                   int32_t *__restrict__ split_row, int32_t *__restrict__ split_part) {
+    int64_t r = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (r >= n_rows) return;
+    int32_t c0 = chunk_off[r], c1 = chunk_off[r + 1];
+    int64_t s = indptr[r];
+    bool split = (c1 - c0) > 1;
+    int32_t p0 = part_off[r];
+    for (int32_t c = c0; c < c1; ++c) {
+        chunk_row[c] = (int32_t)r;
+        chunk_start[c] = s + (int64_t)(c - c0) * chunk;
+        chunk_part[c] = split ? p0 + (c - c0) : -1;
+    }
+    if (split) {
+        int32_t i = split_off[r];
+        split_row[i] = (int32_t)r;
+        split_part[i] = p0;
+    }
+}
+
+__global__ void set_last_kernel(int32_t *split_part, int64_t n_split, int32_t n_parts) {
+    if (threadIdx.x == 0 && blockIdx.x == 0) split_part[n_split] = n_parts;
+}
+
+__global__ void expand_rows_kernel(const int64_t *__restrict__ indptr, int64_t n_rows, int32_t *__restrict__ rows) {
+    // one warp per row
+    int64_t w = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
+    int lane = threadIdx.x & 31;
+    if (w >= n_rows) return;
+    for (int64_t k = indptr[w] + lane; k < indptr[w + 1]; k += 32) rows[k] = (int32_t)w;
+}
+
+__global__ void lower_bound_kernel(const int32_t *__restrict__ sorted_keys, int64_t n, int64_t n_cols,
+                                   int64_t *__restrict__ indptr) {
+    int64_t c = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (c > n_cols) return;
+    int64_t lo = 0, hi = n;
+    while (lo < hi) {
+        int64_t mid = (lo + hi) >> 1;
+        if ((int64_t)sorted_keys[mid] < c) lo = mid + 1; else hi = mid;
+    }
+    indptr[c] = lo;
+}
+
+__global__ void check_indices_kernel(const int32_t *__restrict__ idx, int64_t nnz, int64_t n_cols, int *bad) {
+    int64_t k = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (k < nnz && (idx[k] < 0 || idx[k] >= n_cols)) *bad = 1;
+}
+
+int build_chunks(bns_graph *g, cudaStream_t st) {
+    const int64_t n = g->n_rows;
+    int32_t *n_chunk = nullptr, *n_part = nullptr, *is_split = nullptr;
+    int32_t *chunk_off = nullptr, *part_off = nullptr, *split_off = nullptr;
+    void *tmp = nullptr;
+    size_t tmp_bytes = 0;
+    BNS_CUDA(cudaMalloc(&n_chunk, (n + 1) * sizeof(int32_t)));
+    BNS_CUDA(cudaMalloc(&n_part, (n + 1) * sizeof(int32_t)));
+    BNS_CUDA(cudaMalloc(&is_split, (n + 1) * sizeof(int32_t)));
+    BNS_CUDA(cudaMalloc(&chunk_off, (n + 1) * sizeof(int32_t)));
+    BNS_CUDA(cudaMalloc(&part_off, (n + 1) * sizeof(int32_t)));
+    BNS_CUDA(cudaMalloc(&split_off, (n + 1) * sizeof(int32_t)));
+    BNS_CUDA(cudaMemsetAsync(n_chunk, 0, (n + 1) * sizeof(int32_t), st));
+    BNS_CUDA(cudaMemsetAsync(n_part, 0, (n + 1) * sizeof(int32_t), st));
+    BNS_CUDA(cudaMemsetAsync(is_split, 0, (n + 1) * sizeof(int32_t), st));
+    if (n > 0) {
+        count_chunks_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(g->indptr, n, g->chunk_nnz, n_chunk, n_part,
+                                                                        is_split);
+    }
+    BNS_CUDA(cub::DeviceScan::ExclusiveSum(nullptr, tmp_bytes, n_chunk, chunk_off, (int)(n + 1), st));
+    BNS_CUDA(cudaMalloc(&tmp, tmp_bytes ? tmp_bytes : 16));
+    BNS_CUDA(cub::DeviceScan::ExclusiveSum(tmp, tmp_bytes, n_chunk, chunk_off, (int)(n + 1), st));
+    BNS_CUDA(cub::DeviceScan::ExclusiveSum(tmp, tmp_bytes, n_part, part_off, (int)(n + 1), st));
+    BNS_CUDA(cub::DeviceScan::ExclusiveSum(tmp, tmp_bytes, is_split, split_off, (int)(n + 1), st));
+    int32_t totals[3] = {0, 0, 0};
+    BNS_CUDA(cudaMemcpyAsync(&totals[0], chunk_off + n, sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+    BNS_CUDA(cudaMemcpyAsync(&totals[1], part_off + n, sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+    BNS_CUDA(cudaMemcpyAsync(&totals[2], split_off + n, sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+    BNS_CUDA(cudaStreamSynchronize(st));
+    g->n_chunks = totals[0];
+    g->n_parts = totals[1];
+    g->n_split = totals[2];
+    BNS_CUDA(cudaMalloc(&g->chunk_row, (g->n_chunks + 1) * sizeof(int32_t)));
+    BNS_CUDA(cudaMalloc(&g->chunk_start, (g->n_chunks + 1) * sizeof(int64_t)));
+    BNS_CUDA(cudaMalloc(&g->chunk_part, (g->n_chunks + 1) * sizeof(int32_t)));
+    BNS_CUDA(cudaMalloc(&g->split_row, (g->n_split + 1) * sizeof(int32_t)));
+    BNS_CUDA(cudaMalloc(&g->split_part, (g->n_split + 2) * sizeof(int32_t)));
+    if (n > 0) {
+        fill_chunks_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(g->indptr, n, g->chunk_nnz, chunk_off, part_off,
+                                                                       split_off, g->chunk_row, g->chunk_start,
+                                                                       g->chunk_part, g->split_row, g->split_part);
+    }
+    set_last_kernel<<<1, 32, 0, st>>>(g->split_part, g->n_split, (int32_t)g->n_parts);
+    BNS_CUDA(cudaGetLastError());
+    BNS_CUDA(cudaStreamSynchronize(st));
+    cudaFree(n_chunk); cudaFree(n_part); cudaFree(is_split);
+    cudaFree(chunk_off); cudaFree(part_off); cudaFree(split_off); cudaFree(tmp);
+    return BNS_OK;
+}
+
+}  // namespace
+
+extern "C" int bns_abi_version(void) { return BNS_ABI_VERSION; }
+extern "C" const char *bns_last_error(void) { return g_err; }
+
+extern "C" int bns_device_info(char *name, size_t name_len, int *sms, int64_t *l2_bytes, int *cc_major, int *cc_minor) {
+    int dev = 0;
+    BNS_CUDA(cudaGetDevice(&dev));
+    cudaDeviceProp prop;
+    BNS_CUDA(cudaGetDeviceProperties(&prop, dev));
+    if (name && name_len) {
+        strncpy(name, prop.name, name_len - 1);
+        name[name_len - 1] = 0;
+    }
+    if (sms) *sms = prop.multiProcessorCount;
+    if (l2_bytes) *l2_bytes = prop.l2CacheSize;
+    if (cc_major) *cc_major = prop.major;
+    if (cc_minor) *cc_minor = prop.minor;
+    return BNS_OK;
+}
+
+extern "C" int bns_graph_destroy(bns_graph_t *g) {
+    if (!g) return BNS_OK;
+    cudaFree(g->indptr); cudaFree(g->indices); cudaFree(g->chunk_row); cudaFree(g->chunk_start);
+    cudaFree(g->chunk_part); cudaFree(g->split_row); cudaFree(g->split_part);
+    delete g;
+    return BNS_OK;
+}
+
+extern "C" int bns_graph_create(bns_graph_t **out, int64_t n_rows, int64_t n_cols, int64_t nnz,
+                                const int64_t *indptr, const int32_t *indices, int32_t chunk_nnz, void *stream) {
+    BNS_REQUIRE(out != nullptr, "bns_graph_create: out is NULL");
+    BNS_REQUIRE(n_rows >= 0 && n_cols >= 0 && nnz >= 0, "bns_graph_create: negative size");
+    BNS_REQUIRE(n_rows < INT32_MAX && n_cols < INT32_MAX, "bns_graph_create: more than 2^31-1 rows/cols");
+    BNS_REQUIRE(indptr != nullptr, "bns_graph_create: indptr is NULL");
+    BNS_REQUIRE(nnz == 0 || indices != nullptr, "bns_graph_create: indices is NULL");
+    BNS_REQUIRE(chunk_nnz >= 0, "bns_graph_create: negative chunk_nnz");
+    cudaStream_t st = as_stream(stream);
+    bns_graph *g = new (std::nothrow) bns_graph();
+    if (!g) return fail(BNS_E_INVALID, "bns_graph_create: out of host memory");
+    g->n_rows = n_rows; g->n_cols = n_cols; g->nnz = nnz;
+    g->chunk_nnz = chunk_nnz ? ((chunk_nnz + 31) / 32) * 32 : kDefaultChunk;
+    int rc = BNS_OK;
+    do {
+        if (cudaMalloc(&g->indptr, (n_rows + 1) * sizeof(int64_t)) != cudaSuccess ||
+            cudaMalloc(&g->indices, (nnz + 4) * sizeof(int32_t)) != cudaSuccess) {
+            rc = fail(BNS_E_CUDA, "bns_graph_create: cudaMalloc failed: %s", cudaGetErrorString(cudaGetLastError()));
+            break;
+        }
+        if (cudaMemcpyAsync(g->indptr, indptr, (n_rows + 1) * sizeof(int64_t), cudaMemcpyDeviceToDevice, st) != cudaSuccess ||
+            (nnz && cudaMemcpyAsync(g->indices, indices, nnz * sizeof(int32_t), cudaMemcpyDeviceToDevice, st) != cudaSuccess)) {
+            rc = fail(BNS_E_CUDA, "bns_graph_create: copy failed: %s", cudaGetErrorString(cudaGetLastError()));
+            break;
+        }
+        // validate: indptr[0] == 0, indptr[n_rows] == nnz, indices in range
+        int64_t ends[2] = {0, 0};
+        cudaMemcpyAsync(&ends[0], g->indptr, sizeof(int64_t), cudaMemcpyDeviceToHost, st);
+        cudaMemcpyAsync(&ends[1], g->indptr + n_rows, sizeof(int64_t), cudaMemcpyDeviceToHost, st);
+        int *bad = nullptr, hbad = 0;
+        cudaMalloc(&bad, sizeof(int));
+        cudaMemsetAsync(bad, 0, sizeof(int), st);
+        if (nnz) check_indices_kernel<<<(unsigned)((nnz + 255) / 256), 256, 0, st>>>(g->indices, nnz, n_cols, bad);
+        cudaMemcpyAsync(&hbad, bad, sizeof(int), cudaMemcpyDeviceToHost, st);
+        cudaError_t e = cudaStreamSynchronize(st);
+        cudaFree(bad);
+        if (e != cudaSuccess) { rc = fail(BNS_E_CUDA, "bns_graph_create: %s", cudaGetErrorString(e)); break; }
+        if (ends[0] != 0 || ends[1] != nnz) {
+            rc = fail(BNS_E_INVALID, "bns_graph_create: indptr[0]=%lld indptr[n_rows]=%lld but nnz=%lld",
+                      (long long)ends[0], (long long)ends[1], (long long)nnz);
+            break;
+        }
+        if (hbad) { rc = fail(BNS_E_INVALID, "bns_graph_create: a column index is outside [0, n_cols)"); break; }
+        rc = build_chunks(g, st);
+    } while (0);
+    if (rc != BNS_OK) { bns_graph_destroy(g); return rc; }
+    *out = g;
+    return BNS_OK;
+}
+
+extern "C" int bns_graph_transpose(const bns_graph_t *g, bns_graph_t **out, void *stream) {
+    BNS_REQUIRE(g && out, "bns_graph_transpose: NULL argument");
+    cudaStream_t st = as_stream(stream);
+    const int64_t nnz = g->nnz;
+    BNS_REQUIRE(nnz < INT32_MAX, "bns_graph_transpose: nnz >= 2^31 not supported by the sort");
+    int32_t *rows = nullptr, *keys_out = nullptr, *vals_out = nullptr;
+    int64_t *t_indptr = nullptr;
+    void *tmp = nullptr;
+    size_t tmp_bytes = 0;
+    BNS_CUDA(cudaMalloc(&rows, (nnz + 1) * sizeof(int32_t)));
+    BNS_CUDA(cudaMalloc(&keys_out, (nnz + 1) * sizeof(int32_t)));
+    BNS_CUDA(cudaMalloc(&vals_out, (nnz + 1) * sizeof(int32_t)));
+    BNS_CUDA(cudaMalloc(&t_indptr, (g->n_cols + 1) * sizeof(int64_t)));
+    if (g->n_rows > 0) {
+        int64_t threads = g->n_rows * 32;
+        expand_rows_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, st>>>(g->indptr, g->n_rows, rows);
+    }
+    int end_bit = 1;
+    while (end_bit < 32 && ((int64_t)1 << end_bit) < g->n_cols) ++end_bit;
+    BNS_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, g->indices, keys_out, rows, vals_out, (int)nnz, 0,
+                                             end_bit, st));
+    BNS_CUDA(cudaMalloc(&tmp, tmp_bytes ? tmp_bytes : 16));
+    BNS_CUDA(cub::DeviceRadixSort::SortPairs(tmp, tmp_bytes, g->indices, keys_out, rows, vals_out, (int)nnz, 0,
+                                             end_bit, st));
+    lower_bound_kernel<<<(unsigned)((g->n_cols + 1 + 255) / 256), 256, 0, st>>>(keys_out, nnz, g->n_cols, t_indptr);
+    BNS_CUDA(cudaGetLastError());
+    BNS_CUDA(cudaStreamSynchronize(st));
+    int rc = bns_graph_create(out, g->n_cols, g->n_rows, nnz, t_indptr, vals_out, g->chunk_nnz, stream);
+    cudaFree(rows); cudaFree(keys_out); cudaFree(vals_out); cudaFree(t_indptr); cudaFree(tmp);
+    return rc;
+}
+
+extern "C" int bns_graph_info(const bns_graph_t *g, int64_t *n_rows, int64_t *n_cols, int64_t *nnz,
+                              int64_t *n_chunks, int64_t *n_split_rows) {
+    BNS_REQUIRE(g, "bns_graph_info: NULL graph");
+    if (n_rows) *n_rows = g->n_rows;
+    if (n_cols) *n_cols = g->n_cols;
+    if (nnz) *nnz = g->nnz;
+    if (n_chunks) *n_chunks = g->n_chunks;
+    if (n_split_rows) *n_split_rows = g->n_split;
+    return BNS_OK;
+}
+
+extern "C" int bns_graph_copy_csr(const bns_graph_t *g, int64_t *indptr_out, int32_t *indices_out, void *stream) {
+    BNS_REQUIRE(g, "bns_graph_copy_csr: NULL graph");
+    cudaStream_t st = as_stream(stream);
+    if (indptr_out)
+        BNS_CUDA(cudaMemcpyAsync(indptr_out, g->indptr, (g->n_rows + 1) * sizeof(int64_t), cudaMemcpyDeviceToDevice, st));
+    if (indices_out && g->nnz)
+        BNS_CUDA(cudaMemcpyAsync(indices_out, g->indices, g->nnz * sizeof(int32_t), cudaMemcpyDeviceToDevice, st));
+    return BNS_OK;
+}
+
+// =================================================================================================
+// SpMM
+// =================================================================================================
+namespace {
+
+struct SpmmArgs {
+    const int64_t *indptr;
+    const int32_t *indices;
+    const int32_t *chunk_row;
+    const int64_t *chunk_start;
+    const int32_t *chunk_part;
+    const int32_t *split_row;
+    const int32_t *split_part;
+    int64_t n_chunks, n_split;
+    int32_t chunk_nnz;
+    const float *X;
+    int64_t ldx;
+    float *Y;
+    int64_t ldy;
+    int32_t F;
+    const float *row_scale;
+    const float *col_scale;
+    const int32_t *row_map;
+    const int32_t *col_map;
+    int32_t n_direct;
+    int32_t accumulate;
+    float *ws;
+    int64_t ldws;
+};
+
+template <int W> struct Vec;
+template <> struct Vec<4> {
+    float4 v;
+    __device__ __forceinline__ void zero() { v = make_float4(0.f, 0.f, 0.f, 0.f); }
+    __device__ __forceinline__ void load_ro(const float *p) { v = __ldg(reinterpret_cast<const float4 *>(p)); }
+    __device__ __forceinline__ void load(const float *p) { v = *reinterpret_cast<const float4 *>(p); }
+    __device__ __forceinline__ void store(float *p) const { *reinterpret_cast<float4 *>(p) = v; }
+    __device__ __forceinline__ void add(const Vec &o) { v.x += o.v.x; v.y += o.v.y; v.z += o.v.z; v.w += o.v.w; }
+    __device__ __forceinline__ void fma(const Vec &o, float s) {
+        v.x = fmaf(o.v.x, s, v.x); v.y = fmaf(o.v.y, s, v.y); v.z = fmaf(o.v.z, s, v.z); v.w = fmaf(o.v.w, s, v.w);
+    }
+    __device__ __forceinline__ void scale(float s) { v.x *= s; v.y *= s; v.z *= s; v.w *= s; }
+};
+template <> struct Vec<1> {
+    float v;
+    __device__ __forceinline__ void zero() { v = 0.f; }
+    __device__ __forceinline__ void load_ro(const float *p) { v = __ldg(p); }
+    __device__ __forceinline__ void load(const float *p) { v = *p; }
+    __device__ __forceinline__ void store(float *p) const { *p = v; }
+    __device__ __forceinline__ void add(const Vec &o) { v += o.v; }
+    __device__ __forceinline__ void fma(const Vec &o, float s) { v = fmaf(o.v, s, v); }
+    __device__ __forceinline__ void scale(float s) { v *= s; }
+};
+
+__device__ __forceinline__ int32_t ld_stream_i32(const int32_t *p) {
+    int32_t r;
+    asm volatile("ld.global.nc.L1::no_allocate.s32 %0, [%1];" : "=r"(r) : "l"(p));
+    return r;
+}
+
+// One warp per chunk of <= chunk_nnz entries of one row.  Lane l owns columns
+//   f0 + (l + 32 t) * W .. + W   for t < NV   (W = 4: one 16-byte vector, W = 1: scalar path)
+// so a warp reads each gathered row as NV fully coalesced 512-byte (W=4) requests.
+// Column ids of 32 entries are fetched with one coalesced load, mapped (col_map: sampled halo ->
+// slab row, -1 = skip), compacted through shared memory and then consumed UNROLL at a time so that
+// UNROLL*NV independent 16-byte gathers are in flight per lane.
+template <int W, int NV, bool MAP, bool CSCALE, bool GUARD>
+__global__ void __launch_bounds__(kThreads) spmm_kernel(SpmmArgs a) {
+    constexpr int UNROLL = (NV <= 2) ? 8 / NV : 2;
+    __shared__ int32_t s_col[kWarps][32];
+    __shared__ float s_sc[kWarps][32];
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    const int f0 = blockIdx.y * (32 * W * NV);
+    const int64_t warps_total = (int64_t)gridDim.x * kWarps;
+    int fcol[NV];
+    bool fok[NV];
+#pragma unroll
+    for (int t = 0; t < NV; ++t) {
+        fcol[t] = f0 + (lane + 32 * t) * W;
+        fok[t] = !GUARD || fcol[t] < a.F;
+    }
+    for (int64_t c = (int64_t)blockIdx.x * kWarps + w; c < a.n_chunks; c += warps_total) {
+        const int32_t row = a.chunk_row[c];
+        int32_t orow = row;
+        if (a.row_map) {
+            orow = a.row_map[row];
+            if (orow < 0) continue;
+        }
+        const int64_t s = a.chunk_start[c];
+        int64_t e = a.indptr[row + 1];
+        if (e > s + a.chunk_nnz) e = s + a.chunk_nnz;
+        Vec<W> acc[NV];
+#pragma unroll
+        for (int t = 0; t < NV; ++t) acc[t].zero();
+        for (int64_t k0 = s; k0 < e; k0 += 32) {
+            const int64_t k = k0 + lane;
+            int32_t col = -1;
+            float sc = 1.f;
+            if (k < e) {
+                col = ld_stream_i32(a.indices + k);
+                if (CSCALE) sc = __ldg(a.col_scale + col);
+                if (MAP) {
+                    if (col >= a.n_direct) col = __ldg(a.col_map + (col - a.n_direct));
+                }
+            }
+            int cnt;
+            if (MAP) {
+                const unsigned m = __ballot_sync(0xffffffffu, col >= 0);
+                cnt = __popc(m);
+                if (col >= 0) {
+                    const int pos = __popc(m & ((1u << lane) - 1u));
+                    s_col[w][pos] = col;
+                    if (CSCALE) s_sc[w][pos] = sc;
+                }
+            } else {
+                const int64_t rem = e - k0;
+                cnt = rem < 32 ? (int)rem : 32;
+                s_col[w][lane] = col;
+                if (CSCALE) s_sc[w][lane] = sc;
+            }
+            __syncwarp();
+            int j = 0;
+            for (; j + UNROLL <= cnt; j += UNROLL) {
+                Vec<W> v[UNROLL][NV];
+#pragma unroll
+                for (int u = 0; u < UNROLL; ++u) {
+                    const float *xr = a.X + (int64_t)s_col[w][j + u] * a.ldx;
+#pragma unroll
+                    for (int t = 0; t < NV; ++t) {
+                        if (fok[t]) v[u][t].load_ro(xr + fcol[t]); else v[u][t].zero();
+                    }
+                }
+#pragma unroll
+                for (int u = 0; u < UNROLL; ++u) {
+                    const float cs = CSCALE ? s_sc[w][j + u] : 1.f;
+#pragma unroll
+                    for (int t = 0; t < NV; ++t) {
+                        if (CSCALE) acc[t].fma(v[u][t], cs); else acc[t].add(v[u][t]);
+                    }
+                }
+            }
+            for (; j < cnt; ++j) {
+                const float *xr = a.X + (int64_t)s_col[w][j] * a.ldx;
+                const float cs = CSCALE ? s_sc[w][j] : 1.f;
+#pragma unroll
+                for (int t = 0; t < NV; ++t) {
+                    if (fok[t]) {
+                        Vec<W> v;
+                        v.load_ro(xr + fcol[t]);
+                        if (CSCALE) acc[t].fma(v, cs); else acc[t].add(v);
+                    }
+                }
+            }
+            __syncwarp();
+        }
+        const int32_t part = a.chunk_part[c];
+        if (part >= 0) {   // the row spans several chunks: park the raw partial sum, combined later
+            float *wr = a.ws + (int64_t)part * a.ldws;
+#pragma unroll
+            for (int t = 0; t < NV; ++t)
+                if (fok[t]) acc[t].store(wr + fcol[t]);
+        } else {
+            const float rs = a.row_scale ? a.row_scale[row] : 1.f;
+            float *yr = a.Y + (int64_t)orow * a.ldy;
+#pragma unroll
+            for (int t = 0; t < NV; ++t) {
+                if (!fok[t]) continue;
+                if (a.row_scale) acc[t].scale(rs);
+                if (a.accumulate) {
+                    Vec<W> old;
+                    old.load(yr + fcol[t]);
+                    acc[t].add(old);
+                }
+                acc[t].store(yr + fcol[t]);
+            }
+        }
+    }
+}
+
+// Rows longer than one chunk: add their partial sums in chunk order (deterministic), then finish
+// exactly like the single-chunk epilogue.
+template <int W, int NV, bool GUARD>
+__global__ void __launch_bounds__(kThreads) spmm_fixup_kernel(SpmmArgs a) {
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    const int f0 = blockIdx.y * (32 * W * NV);
+    const int64_t i = (int64_t)blockIdx.x * kWarps + w;
+    if (i >= a.n_split) return;
+    const int32_t row = a.split_row[i];
+    int32_t orow = row;
+    if (a.row_map) {
+        orow = a.row_map[row];
+        if (orow < 0) return;
+    }
+    const int32_t p0 = a.split_part[i], p1 = a.split_part[i + 1];
+    const float rs = a.row_scale ? a.row_scale[row] : 1.f;
+    float *yr = a.Y + (int64_t)orow * a.ldy;
+#pragma unroll
+    for (int t = 0; t < NV; ++t) {
+        const int fc = f0 + (lane + 32 * t) * W;
+        if (GUARD && fc >= a.F) continue;
+        Vec<W> acc;
+        acc.zero();
+        for (int32_t p = p0; p < p1; ++p) {
+            Vec<W> v;
+            v.load(a.ws + (int64_t)p * a.ldws + fc);
+            acc.add(v);
+        }
+        if (a.row_scale) acc.scale(rs);
+        if (a.accumulate) {
+            Vec<W> old;
+            old.load(yr + fc);
+            acc.add(old);
+        }
+        acc.store(yr + fc);
+    }
+}
+
+template <int W, int NV, bool MAP, bool CSCALE, bool GUARD>
+int launch_spmm(const SpmmArgs &a, int tiles, cudaStream_t st) {
+    static int blocks_per_sm = 0;
+    if (blocks_per_sm == 0) {
+        int n = 0;
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, spmm_kernel<W, NV, MAP, CSCALE, GUARD>, kThreads, 0) !=
+                cudaSuccess || n < 1)
+            n = 2;
+        blocks_per_sm = n;
+    }
+    int64_t want = (a.n_chunks + kWarps - 1) / kWarps;
+    int64_t cap = (int64_t)sm_count() * blocks_per_sm;
+    unsigned gx = (unsigned)(want < cap ? (want > 0 ? want : 1) : cap);
+    spmm_kernel<W, NV, MAP, CSCALE, GUARD><<<dim3(gx, tiles), kThreads, 0, st>>>(a);
+    if (a.n_split > 0) {
+        unsigned fx = (unsigned)((a.n_split + kWarps - 1) / kWarps);
+        spmm_fixup_kernel<W, NV, GUARD><<<dim3(fx, tiles), kThreads, 0, st>>>(a);
+    }
+    return BNS_OK;
+}
+
+template <int W, int NV, bool GUARD>
+int dispatch_flags(const SpmmArgs &a, int tiles, cudaStream_t st) {
+    const bool map = a.col_map != nullptr, cs = a.col_scale != nullptr;
+    if (map && cs) return launch_spmm<W, NV, true, true, GUARD>(a, tiles, st);
+    if (map) return launch_spmm<W, NV, true, false, GUARD>(a, tiles, st);
+    if (cs) return launch_spmm<W, NV, false, true, GUARD>(a, tiles, st);
+    return launch_spmm<W, NV, false, false, GUARD>(a, tiles, st);
+}
+
+inline int64_t ws_ld(int64_t F) { return (F + 3) / 4 * 4; }
+
+}  // namespace
+
+extern "C" size_t bns_spmm_workspace_bytes(const bns_graph_t *g, int64_t F) {
+    if (!g || F <= 0) return 0;
+    return (size_t)g->n_parts * (size_t)ws_ld(F) * sizeof(float);
+}
+
+extern "C" int bns_spmm_sum_f32(const bns_graph_t *g, const float *X, int64_t ldx, int64_t F, float *Y, int64_t ldy,
+                                const float *row_scale, const float *col_scale, const int32_t *row_map,
+                                const int32_t *col_map, int64_t n_direct, int accumulate, void *ws, size_t ws_bytes,
+                                void *stream) {
+    BNS_REQUIRE(g, "bns_spmm_sum_f32: NULL graph");
+    BNS_REQUIRE(F > 0 && F < (1 << 24), "bns_spmm_sum_f32: bad feature width %lld", (long long)F);
+    BNS_REQUIRE(X && Y, "bns_spmm_sum_f32: NULL matrix");
+    BNS_REQUIRE(ldx >= F && ldy >= F, "bns_spmm_sum_f32: leading dimension smaller than F");
+    if (g->n_rows == 0) return BNS_OK;
+    const size_t need = bns_spmm_workspace_bytes(g, F);
+    if (need > 0 && (ws == nullptr || ws_bytes < need))
+        return fail(BNS_E_WORKSPACE, "bns_spmm_sum_f32: workspace %zu bytes < %zu needed", ws_bytes, need);
+    if (col_map == nullptr) n_direct = g->n_cols;
+    BNS_REQUIRE(n_direct >= 0 && n_direct <= g->n_cols, "bns_spmm_sum_f32: n_direct out of range");
+    SpmmArgs a;
+    a.indptr = g->indptr; a.indices = g->indices;
+    a.chunk_row = g->chunk_row; a.chunk_start = g->chunk_start; a.chunk_part = g->chunk_part;
+    a.split_row = g->split_row; a.split_part = g->split_part;
+    a.n_chunks = g->n_chunks; a.n_split = g->n_split; a.chunk_nnz = g->chunk_nnz;
+    a.X = X; a.ldx = ldx; a.Y = Y; a.ldy = ldy; a.F = (int32_t)F;
+    a.row_scale = row_scale; a.col_scale = col_scale; a.row_map = row_map; a.col_map = col_map;
+    a.n_direct = (int32_t)n_direct; a.accumulate = accumulate ? 1 : 0;
+    a.ws = reinterpret_cast<float *>(ws); a.ldws = ws_ld(F);
+    cudaStream_t st = as_stream(stream);
+    const bool vec = (F % 4 == 0) && (ldx % 4 == 0) && (ldy % 4 == 0) &&
+                     ((reinterpret_cast<uintptr_t>(X) | reinterpret_cast<uintptr_t>(Y)) % 16 == 0);
+    if (vec) {
+        if (F <= 128) {
+            if (F == 128) dispatch_flags<4, 1, false>(a, 1, st); else dispatch_flags<4, 1, true>(a, 1, st);
+        } else {
+            const int tiles = (int)((F + 255) / 256);
+            if (F % 256 == 0) dispatch_flags<4, 2, false>(a, tiles, st); else dispatch_flags<4, 2, true>(a, tiles, st);
+        }
+    } else {
+        const int tiles = (int)((F + 255) / 256);
+        dispatch_flags<1, 8, true>(a, tiles, st);
+    }
+    BNS_CUDA(cudaGetLastError());
+    return BNS_OK;
+}
+
+// =================================================================================================
+// boundary pack / scatter / copy
+// =================================================================================================
+namespace {
+
+// one warp per row, 16-byte lanes when aligned
+template <bool VEC, bool SCATTER>
+__global__ void __launch_bounds__(kThreads) rows_kernel(const float *__restrict__ src, int64_t lds, float *dst,
+                                                        int64_t ldd, const int64_t *__restrict__ idx, int64_t k,
+                                                        int32_t F, float div) {
+    const int lane = threadIdx.x & 31;
+    const int64_t warps_total = (int64_t)gridDim.x * kWarps;
+    for (int64_t i = (int64_t)blockIdx.x * kWarps + (threadIdx.x >> 5); i < k; i += warps_total) {
+        const int64_t r = idx ? idx[i] : i;
+        const float *s = SCATTER ? src + i * lds : src + r * lds;
+        float *d = SCATTER ? dst + r * ldd : dst + i * ldd;
+        if (VEC) {
+            for (int f = lane * 4; f < F; f += 128) {
+                float4 v = *reinterpret_cast<const float4 *>(s + f);
+                v.x = __fdiv_rn(v.x, div); v.y = __fdiv_rn(v.y, div); v.z = __fdiv_rn(v.z, div); v.w = __fdiv_rn(v.w, div);
+                if (SCATTER) {
+                    float4 o = *reinterpret_cast<float4 *>(d + f);
+                    v.x += o.x; v.y += o.y; v.z += o.z; v.w += o.w;
+                }
+                *reinterpret_cast<float4 *>(d + f) = v;
+            }
+        } else {
+            for (int f = lane; f < F; f += 32) {
+                float v = __fdiv_rn(s[f], div);
+                if (SCATTER) v += d[f];
+                d[f] = v;
+            }
+        }
+    }
+}
+
+inline bool vec_ok(const void *a, const void *b, int64_t F, int64_t lda, int64_t ldb) {
+    return F % 4 == 0 && lda % 4 == 0 && ldb % 4 == 0 &&
+           ((reinterpret_cast<uintptr_t>(a) | reinterpret_cast<uintptr_t>(b)) % 16 == 0);
+}
+
+inline unsigned rows_grid(int64_t k) {
+    int64_t want = (k + kWarps - 1) / kWarps;
+    int64_t cap = (int64_t)sm_count() * 8;
+    return (unsigned)(want < cap ? (want > 0 ? want : 1) : cap);
+}
+
+}  // namespace
+
+extern "C" int bns_gather_div_f32(const float *H, int64_t ldh, int64_t F, const int64_t *idx, int64_t k, float div,
+                                  float *out, int64_t ldo, void *stream) {
+    BNS_REQUIRE(k >= 0 && F > 0, "bns_gather_div_f32: bad size");
+    if (k == 0) return BNS_OK;
+    BNS_REQUIRE(H && out && idx, "bns_gather_div_f32: NULL pointer");
+    BNS_REQUIRE(ldh >= F && ldo >= F, "bns_gather_div_f32: leading dimension smaller than F");
+    BNS_REQUIRE(div != 0.f, "bns_gather_div_f32: division by zero");
+    cudaStream_t st = as_stream(stream);
+    if (vec_ok(H, out, F, ldh, ldo))
+        rows_kernel<true, false><<<rows_grid(k), kThreads, 0, st>>>(H, ldh, out, ldo, idx, k, (int32_t)F, div);
+    else
+        rows_kernel<false, false><<<rows_grid(k), kThreads, 0, st>>>(H, ldh, out, ldo, idx, k, (int32_t)F, div);
+    BNS_CUDA(cudaGetLastError());
+    return BNS_OK;
+}
+
+extern "C" int bns_scatter_add_div_f32(float *G, int64_t ldg, int64_t F, const int64_t *idx, int64_t k, float div,
+                                       const float *src, int64_t lds, void *stream) {
+    BNS_REQUIRE(k >= 0 && F > 0, "bns_scatter_add_div_f32: bad size");
+    if (k == 0) return BNS_OK;
+    BNS_REQUIRE(G && src && idx, "bns_scatter_add_div_f32: NULL pointer");
+    BNS_REQUIRE(ldg >= F && lds >= F, "bns_scatter_add_div_f32: leading dimension smaller than F");
+    BNS_REQUIRE(div != 0.f, "bns_scatter_add_div_f32: division by zero");
+    cudaStream_t st = as_stream(stream);
+    if (vec_ok(G, src, F, ldg, lds))
+        rows_kernel<true, true><<<rows_grid(k), kThreads, 0, st>>>(src, lds, G, ldg, idx, k, (int32_t)F, div);
+    else
+        rows_kernel<false, true><<<rows_grid(k), kThreads, 0, st>>>(src, lds, G, ldg, idx, k, (int32_t)F, div);
+    BNS_CUDA(cudaGetLastError());
+    return BNS_OK;
+}
+
+extern "C" int bns_copy_rows_f32(const float *src, int64_t lds, float *dst, int64_t ldd, int64_t n_rows, int64_t F,
+                                 void *stream) {
+    BNS_REQUIRE(n_rows >= 0 && F > 0, "bns_copy_rows_f32: bad size");
+    if (n_rows == 0) return BNS_OK;
+    BNS_REQUIRE(src && dst, "bns_copy_rows_f32: NULL pointer");
+    BNS_REQUIRE(lds >= F && ldd >= F, "bns_copy_rows_f32: leading dimension smaller than F");
+    BNS_CUDA(cudaMemcpy2DAsync(dst, ldd * sizeof(float), src, lds * sizeof(float), F * sizeof(float), n_rows,
+                               cudaMemcpyDeviceToDevice, as_stream(stream)));
+    return BNS_OK;
+}
+
+// =================================================================================================
+// sampler
+// =================================================================================================
+namespace {
+
+__device__ __forceinline__ void philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t k0,
+                                              uint32_t k1, uint32_t out[4]) {
+    constexpr uint32_t M0 = 0xD2511F53u, M1 = 0xCD9E8D57u, W0 = 0x9E3779B9u, W1 = 0xBB67AE85u;
+#pragma unroll
+    for (int r = 0; r < 10; ++r) {
+        const uint32_t hi0 = __umulhi(M0, c0), lo0 = M0 * c0;
+        const uint32_t hi1 = __umulhi(M1, c2), lo1 = M1 * c2;
+        const uint32_t n0 = hi1 ^ c1 ^ k0, n1 = lo1, n2 = hi0 ^ c3 ^ k1, n3 = lo0;
+        c0 = n0; c1 = n1; c2 = n2; c3 = n3;
+        k0 += W0; k1 += W1;
+    }
+    out[0] = c0; out[1] = c1; out[2] = c2; out[3] = c3;
+}
+
+__global__ void sample_keys_kernel(const int64_t *__restrict__ seg_begin, int32_t n_seg, int64_t B, uint64_t seed,
+                                   uint64_t offset, uint64_t *__restrict__ keys, int32_t *__restrict__ vals) {
+    const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (i >= B) return;
+    int32_t lo = 0, hi = n_seg;   // segment s with seg_begin[s] <= i < seg_begin[s+1]
+    while (hi - lo > 1) {
+        const int32_t mid = (lo + hi) >> 1;
+        if (seg_begin[mid] <= i) lo = mid; else hi = mid;
+    }
+    uint32_t r[4];
+    philox4x32_10((uint32_t)i, (uint32_t)((uint64_t)i >> 32), (uint32_t)offset, (uint32_t)(offset >> 32),
+                  (uint32_t)seed, (uint32_t)(seed >> 32), r);
+    const uint64_t r56 = ((uint64_t)r[0] << 24) | (uint64_t)(r[1] >> 8);
+    keys[i] = ((uint64_t)lo << 56) | r56;
+    vals[i] = (int32_t)i;
+}
+
+__global__ void sample_take_kernel(const int64_t *__restrict__ boundary_cat, const int64_t *__restrict__ seg_begin,
+                                   const int64_t *__restrict__ out_begin, int32_t n_seg, int64_t K,
+                                   const int32_t *__restrict__ sorted_vals, int64_t *__restrict__ selected) {
+    const int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (t >= K) return;
+    int32_t lo = 0, hi = n_seg;
+    while (hi - lo > 1) {
+        const int32_t mid = (lo + hi) >> 1;
+        if (out_begin[mid] <= t) lo = mid; else hi = mid;
+    }
+    const int64_t j = t - out_begin[lo];
+    selected[t] = boundary_cat[sorted_vals[seg_begin[lo] + j]];
+}
+
+struct SampleLayout {
+    size_t keys_in, keys_out, vals_in, vals_out, tmp, tmp_bytes, total;
+};
+
+inline size_t align256(size_t x) { return (x + 255) / 256 * 256; }
+
+SampleLayout sample_layout(int64_t B) {
+    SampleLayout l;
+    size_t n = (size_t)(B > 0 ? B : 1);
+    l.keys_in = 0;
+    l.keys_out = l.keys_in + align256(n * 8);
+    l.vals_in = l.keys_out + align256(n * 8);
+    l.vals_out = l.vals_in + align256(n * 4);
+    l.tmp = l.vals_out + align256(n * 4);
+    size_t tb = 0;
+    cub::DeviceRadixSort::SortPairs(nullptr, tb, (const uint64_t *)nullptr, (uint64_t *)nullptr,
+                                    (const int32_t *)nullptr, (int32_t *)nullptr, (int)n, 0, 64, (cudaStream_t)0);
+    l.tmp_bytes = align256(tb ? tb : 16);
+    l.total = l.tmp + l.tmp_bytes;
+    return l;
+}
+
+}  // namespace
+
+extern "C" size_t bns_sample_workspace_bytes(int64_t B) { return sample_layout(B).total; }
+
+extern "C" int bns_sample_boundary(const int64_t *boundary_cat, const int64_t *seg_begin, const int64_t *out_begin,
+                                   int32_t n_seg, int64_t B, int64_t K_total, uint64_t seed, uint64_t offset,
+                                   int64_t *selected, void *ws, size_t ws_bytes, void *stream) {
+    BNS_REQUIRE(n_seg >= 0 && n_seg <= 255, "bns_sample_boundary: n_seg must be in [0, 255]");
+    BNS_REQUIRE(B >= 0 && K_total >= 0 && K_total <= B, "bns_sample_boundary: need 0 <= K_total <= B");
+    BNS_REQUIRE(B < INT32_MAX, "bns_sample_boundary: B >= 2^31");
+    if (K_total == 0 || n_seg == 0) return BNS_OK;
+    BNS_REQUIRE(boundary_cat && seg_begin && out_begin && selected, "bns_sample_boundary: NULL pointer");
+    const SampleLayout l = sample_layout(B);
+    if (!ws || ws_bytes < l.total)
+        return fail(BNS_E_WORKSPACE, "bns_sample_boundary: workspace %zu bytes < %zu needed", ws_bytes, l.total);
+    char *base = reinterpret_cast<char *>(ws);
+    uint64_t *keys_in = reinterpret_cast<uint64_t *>(base + l.keys_in);
+    uint64_t *keys_out = reinterpret_cast<uint64_t *>(base + l.keys_out);
+    int32_t *vals_in = reinterpret_cast<int32_t *>(base + l.vals_in);
+    int32_t *vals_out = reinterpret_cast<int32_t *>(base + l.vals_out);
+    cudaStream_t st = as_stream(stream);
+    sample_keys_kernel<<<(unsigned)((B + 255) / 256), 256, 0, st>>>(seg_begin, n_seg, B, seed, offset, keys_in, vals_in);
+    size_t tb = l.tmp_bytes;
+    BNS_CUDA(cub::DeviceRadixSort::SortPairs(base + l.tmp, tb, keys_in, keys_out, vals_in, vals_out, (int)B, 0, 64, st));
+    sample_take_kernel<<<(unsigned)((K_total + 255) / 256), 256, 0, st>>>(boundary_cat, seg_begin, out_begin, n_seg,
+                                                                         K_total, vals_out, selected);
+    BNS_CUDA(cudaGetLastError());
+    return BNS_OK;
+}
+
+// =================================================================================================
+// halo slot map
+// =================================================================================================
+namespace {
+
+__global__ void fill_i32_kernel(int32_t *dst, int64_t n, int32_t v) {
+    int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (i < n) dst[i] = v;
+}
+
+__global__ void halo_slot_kernel(const int64_t *__restrict__ pos, const int64_t *__restrict__ one_hops, int64_t r,
+                                 int64_t n_in, int32_t slab_offset, int32_t *__restrict__ slot) {
+    int64_t k = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (k >= r) return;
+    const int64_t local = pos[one_hops[k]];
+    if (local >= n_in) slot[local - n_in] = slab_offset + (int32_t)k;
+}
+
+}  // namespace
+
+extern "C" int bns_fill_i32(int32_t *dst, int64_t n, int32_t value, void *stream) {
+    BNS_REQUIRE(n >= 0, "bns_fill_i32: negative size");
+    if (n == 0) return BNS_OK;
+    BNS_REQUIRE(dst, "bns_fill_i32: NULL pointer");
+    fill_i32_kernel<<<(unsigned)((n + 255) / 256), 256, 0, as_stream(stream)>>>(dst, n, value);
+    BNS_CUDA(cudaGetLastError());
+    return BNS_OK;
+}
+
+extern "C" int bns_halo_slot_update(const int64_t *pos, const int64_t *one_hops, int64_t r, int64_t n_in,
+                                    int32_t slab_offset, int32_t *slot, void *stream) {
+    BNS_REQUIRE(r >= 0, "bns_halo_slot_update: negative size");
+    if (r == 0) return BNS_OK;
+    BNS_REQUIRE(pos && one_hops && slot, "bns_halo_slot_update: NULL pointer");
+    halo_slot_kernel<<<(unsigned)((r + 255) / 256), 256, 0, as_stream(stream)>>>(pos, one_hops, r, n_in, slab_offset, slot);
+    BNS_CUDA(cudaGetLastError());
+    return BNS_OK;
+}
+
+// =================================================================================================
+// peer-mapped exchange
+// =================================================================================================
+struct bns_p2p {
+    int32_t rank = 0, world = 0, n_flags = 0;
+    size_t slab_bytes = 0;
+    char *slab = nullptr;                 // this rank's receive slab
+    unsigned long long *flags = nullptr;  // this rank's flag block
+    char **peer_slab = nullptr;           // [world] mapped pointers (self = own)
+    unsigned long long **peer_flags = nullptr;
+    bool *imported = nullptr;             // opened with cudaIpcOpenMemHandle (must be closed)
+};
+
+namespace {
+
+__device__ __forceinline__ void st_release_sys(unsigned long long *p, unsigned long long v) {
+    asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long long *p) {
+    unsigned long long v;
+    asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+
+// Each warp moves whole rows  H[idx[i]] / div  into the peer's slab (16-byte stores over NVLink).
+// The last CTA to finish (device-scope ticket) publishes the flag with a system-scope release.
+template <bool VEC>
+__global__ void __launch_bounds__(kThreads) p2p_put_rows_kernel(const float *__restrict__ H, int64_t ldh, int32_t F,
+                                                               const int64_t *__restrict__ idx, int64_t k, float div,
+                                                               float *remote, int64_t ldr, unsigned long long *flag,
+                                                               unsigned long long flag_value, unsigned int *ticket) {
+    const int lane = threadIdx.x & 31;
+    const int64_t warps_total = (int64_t)gridDim.x * kWarps;
+    for (int64_t i = (int64_t)blockIdx.x * kWarps + (threadIdx.x >> 5); i < k; i += warps_total) {
+        const int64_t r = idx ? idx[i] : i;
+        const float *s = H + r * ldh;
+        float *d = remote + i * ldr;
+        if (VEC) {
+            for (int f = lane * 4; f < F; f += 128) {
+                float4 v = *reinterpret_cast<const float4 *>(s + f);
+                v.x = __fdiv_rn(v.x, div); v.y = __fdiv_rn(v.y, div); v.z = __fdiv_rn(v.z, div); v.w = __fdiv_rn(v.w, div);
+                *reinterpret_cast<float4 *>(d + f) = v;
+            }
+        } else {
+            for (int f = lane; f < F; f += 32) d[f] = __fdiv_rn(s[f], div);
+        }
+    }
+    __threadfence_system();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        const unsigned int done = atomicAdd(ticket, 1u);
+        if (done == gridDim.x - 1) {
+            *ticket = 0;               // re-arm for the next launch on this stream
+            __threadfence_system();
+            st_release_sys(flag, flag_value);
+        }
+    }
+}
+
+__global__ void p2p_wait_kernel(const unsigned long long *flag, unsigned long long value) {
+    if (threadIdx.x == 0) {
+        while (ld_acquire_sys(flag) < value) __nanosleep(64);
+    }
+}
+
+}  // namespace
+
+extern "C" int bns_p2p_create(bns_p2p_t **out, int32_t rank, int32_t world, size_t slab_bytes, int32_t n_flags) {
+    BNS_REQUIRE(out, "bns_p2p_create: out is NULL");
+    BNS_REQUIRE(world >= 1 && rank >= 0 && rank < world, "bns_p2p_create: bad rank/world");
+    BNS_REQUIRE(n_flags >= 1, "bns_p2p_create: n_flags must be >= 1");
+    bns_p2p *p = new (std::nothrow) bns_p2p();
+    if (!p) return fail(BNS_E_INVALID, "bns_p2p_create: out of host memory");
+    p->rank = rank; p->world = world; p->n_flags = n_flags;
+    p->slab_bytes = slab_bytes ? align256(slab_bytes) : 256;
+    p->peer_slab = new char *[world]();
+    p->peer_flags = new unsigned long long *[world]();
+    p->imported = new bool[world]();
+    // flags block: n_flags u64 + one u32 ticket per peer (for the put kernel), zero-initialised
+    const size_t flag_bytes = align256((size_t)n_flags * 8) + align256((size_t)world * 4);
+    if (cudaMalloc(&p->slab, p->slab_bytes) != cudaSuccess || cudaMalloc(&p->flags, flag_bytes) != cudaSuccess) {
+        int rc = fail(BNS_E_CUDA, "bns_p2p_create: cudaMalloc failed: %s", cudaGetErrorString(cudaGetLastError()));
+        bns_p2p_destroy(p);
+        return rc;
+    }
+    cudaMemset(p->slab, 0, p->slab_bytes);
+    cudaMemset(p->flags, 0, flag_bytes);
+    cudaDeviceSynchronize();
+    p->peer_slab[rank] = p->slab;
+    p->peer_flags[rank] = p->flags;
+    *out = p;
+    return BNS_OK;
+}
+
+extern "C" int bns_p2p_destroy(bns_p2p_t *p) {
+    if (!p) return BNS_OK;
+    for (int i = 0; i < p->world; ++i) {
+        if (p->imported && p->imported[i]) {
+            cudaIpcCloseMemHandle(p->peer_slab[i]);
+            cudaIpcCloseMemHandle(p->peer_flags[i]);
+        }
+    }
+    cudaFree(p->slab); cudaFree(p->flags);
+    delete[] p->peer_slab; delete[] p->peer_flags; delete[] p->imported;
+    delete p;
+    return BNS_OK;
+}
+
+extern "C" int bns_p2p_local(const bns_p2p_t *p, void **slab, void **flags) {
+    BNS_REQUIRE(p, "bns_p2p_local: NULL handle");
+    if (slab) *slab = p->slab;
+    if (flags) *flags = p->flags;
+    return BNS_OK;
+}
+
+extern "C" int bns_p2p_export(const bns_p2p_t *p, void *handle_out) {
+    BNS_REQUIRE(p && handle_out, "bns_p2p_export: NULL argument");
+    static_assert(sizeof(cudaIpcMemHandle_t) <= BNS_P2P_HANDLE_BYTES, "handle size");
+    cudaIpcMemHandle_t h;
+    BNS_CUDA(cudaIpcGetMemHandle(&h, p->slab));
+    memcpy(handle_out, &h, sizeof(h));
+    BNS_CUDA(cudaIpcGetMemHandle(&h, p->flags));
+    memcpy(reinterpret_cast<char *>(handle_out) + BNS_P2P_HANDLE_BYTES, &h, sizeof(h));
+    return BNS_OK;
+}
+
+extern "C" int bns_p2p_import(bns_p2p_t *p, int32_t peer, const void *handle) {
+    BNS_REQUIRE(p && handle, "bns_p2p_import: NULL argument");
+    BNS_REQUIRE(peer >= 0 && peer < p->world && peer != p->rank, "bns_p2p_import: bad peer %d", peer);
+    cudaIpcMemHandle_t h;
+    void *ptr = nullptr;
+    memcpy(&h, handle, sizeof(h));
+    BNS_CUDA(cudaIpcOpenMemHandle(&ptr, h, cudaIpcMemLazyEnablePeerAccess));
+    p->peer_slab[peer] = reinterpret_cast<char *>(ptr);
+    memcpy(&h, reinterpret_cast<const char *>(handle) + BNS_P2P_HANDLE_BYTES, sizeof(h));
+    BNS_CUDA(cudaIpcOpenMemHandle(&ptr, h, cudaIpcMemLazyEnablePeerAccess));
+    p->peer_flags[peer] = reinterpret_cast<unsigned long long *>(ptr);
+    p->imported[peer] = true;
+    return BNS_OK;
+}
+
+extern "C" int bns_p2p_set_peer(bns_p2p_t *p, int32_t peer, void *slab, void *flags) {
+    BNS_REQUIRE(p && slab && flags, "bns_p2p_set_peer: NULL argument");
+    BNS_REQUIRE(peer >= 0 && peer < p->world && peer != p->rank, "bns_p2p_set_peer: bad peer %d", peer);
+    p->peer_slab[peer] = reinterpret_cast<char *>(slab);
+    p->peer_flags[peer] = reinterpret_cast<unsigned long long *>(flags);
+    return BNS_OK;
+}
+
+extern "C" int bns_p2p_put_rows_f32(bns_p2p_t *p, int32_t peer, size_t remote_off, int64_t ld_remote, const float *H,
+                                    int64_t ldh, int64_t F, const int64_t *idx, int64_t k, float div,
+                                    int32_t flag_index, uint64_t flag_value, void *stream) {
+    BNS_REQUIRE(p, "bns_p2p_put_rows_f32: NULL handle");
+    BNS_REQUIRE(peer >= 0 && peer < p->world && peer != p->rank, "bns_p2p_put_rows_f32: bad peer %d", peer);
+    BNS_REQUIRE(p->peer_slab[peer] && p->peer_flags[peer], "bns_p2p_put_rows_f32: peer %d not connected", peer);
+    BNS_REQUIRE(flag_index >= 0 && flag_index < p->n_flags, "bns_p2p_put_rows_f32: bad flag index");
+    BNS_REQUIRE(k >= 0 && F > 0 && ldh >= F && ld_remote >= F, "bns_p2p_put_rows_f32: bad shape");
+    BNS_REQUIRE(div != 0.f, "bns_p2p_put_rows_f32: division by zero");
+    BNS_REQUIRE(remote_off % 16 == 0 && remote_off + (size_t)k * ld_remote * 4 <= p->slab_bytes,
+                "bns_p2p_put_rows_f32: remote range outside the slab");
+    BNS_REQUIRE(k == 0 || H, "bns_p2p_put_rows_f32: NULL source");
+    float *remote = reinterpret_cast<float *>(p->peer_slab[peer] + remote_off);
+    unsigned long long *flag = p->peer_flags[peer] + flag_index;
+    // ticket counters live behind the flags of THIS rank's block, one per destination peer
+    unsigned int *ticket = reinterpret_cast<unsigned int *>(reinterpret_cast<char *>(p->flags) +
+                                                            align256((size_t)p->n_flags * 8)) + peer;
+    cudaStream_t st = as_stream(stream);
+    const unsigned grid = rows_grid(k);
+    if (vec_ok(H, remote, F, ldh, ld_remote))
+        p2p_put_rows_kernel<true><<<grid, kThreads, 0, st>>>(H, ldh, (int32_t)F, idx, k, div, remote, ld_remote, flag,
+                                                             flag_value, ticket);
+    else
+        p2p_put_rows_kernel<false><<<grid, kThreads, 0, st>>>(H, ldh, (int32_t)F, idx, k, div, remote, ld_remote, flag,
+                                                              flag_value, ticket);
+    BNS_CUDA(cudaGetLastError());
+    return BNS_OK;
+}
+
+extern "C" int bns_p2p_wait_flag(bns_p2p_t *p, int32_t flag_index, uint64_t flag_value, void *stream) {
+    BNS_REQUIRE(p, "bns_p2p_wait_flag: NULL handle");
+    BNS_REQUIRE(flag_index >= 0 && flag_index < p->n_flags, "bns_p2p_wait_flag: bad flag index");
+    p2p_wait_kernel<<<1, 32, 0, as_stream(stream)>>>(p->flags + flag_index, flag_value);
+    BNS_CUDA(cudaGetLastError());
+    return BNS_OK;
+}

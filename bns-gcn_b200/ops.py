@@ -1,0 +1,242 @@
+"""torch-facing wrappers over the C ABI (``include/bnsgcn.h``): device memory and streams come from
+PyTorch, every kernel comes from ``libbnsgcn.so``.  Nothing here computes on the CPU.
+
+* ``DeviceGraph``      a static CSR matrix in HBM (``bns_graph_t``) + its transpose
+* ``spmm``             ``bns_spmm_sum_f32``
+* ``AggregateSum``     autograd Function: the DGL ``update_all(copy_u, sum)`` of module/layer.py:35-37, 88-90
+                       with the degree / norm scalings of :34, :38, :91 fused in
+* ``gather_div`` / ``scatter_add_div`` / ``sample_boundary`` / ``halo_slot_update``
+"""
+from __future__ import annotations
+
+import ctypes
+from typing import Dict, Optional
+
+import torch
+
+from . import _lib
+from ._lib import check, lib
+
+
+def _stream_ptr() -> int:
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _ptr(t: Optional[torch.Tensor]) -> Optional[int]:
+    return None if t is None else t.data_ptr()
+
+
+def _req(t: torch.Tensor, dtype, name: str) -> torch.Tensor:
+    if not t.is_cuda:
+        raise _lib.BnsError(f"{name} must be a CUDA tensor (there is no CPU path)")
+    if t.dtype != dtype:
+        raise _lib.BnsError(f"{name} must be {dtype}, got {t.dtype}")
+    return t
+
+
+def device_info() -> dict:
+    name = ctypes.create_string_buffer(256)
+    sms, l2, maj, mnr = ctypes.c_int(), ctypes.c_int64(), ctypes.c_int(), ctypes.c_int()
+    check(lib.bns_device_info(name, 256, ctypes.byref(sms), ctypes.byref(l2), ctypes.byref(maj), ctypes.byref(mnr)),
+          "bns_device_info")
+    return {"name": name.value.decode(), "sm_count": sms.value, "l2_bytes": l2.value, "cc": (maj.value, mnr.value)}
+
+
+class DeviceGraph:
+    """A static sparse 0/1 matrix ``[n_rows, n_cols]`` in CSR, resident on the GPU.
+
+    Row ``r`` lists the columns whose feature rows are summed into output row ``r``.
+    """
+
+    def __init__(self, handle: int, device: torch.device):
+        self._h = ctypes.c_void_p(handle)
+        self.device = device
+        nr, nc, nnz, nch, nsp = (ctypes.c_int64() for _ in range(5))
+        check(lib.bns_graph_info(self._h, ctypes.byref(nr), ctypes.byref(nc), ctypes.byref(nnz), ctypes.byref(nch),
+                                 ctypes.byref(nsp)), "bns_graph_info")
+        self.n_rows, self.n_cols, self.nnz = nr.value, nc.value, nnz.value
+        self.n_chunks, self.n_split_rows = nch.value, nsp.value
+        self._t: Optional["DeviceGraph"] = None
+        self._ws: Dict[int, torch.Tensor] = {}
+
+    @classmethod
+    def from_csr(cls, indptr: torch.Tensor, indices: torch.Tensor, n_cols: int, chunk_nnz: int = 0) -> "DeviceGraph":
+        _req(indptr, torch.int64, "indptr")
+        _req(indices, torch.int32, "indices")
+        indptr, indices = indptr.contiguous(), indices.contiguous()
+        out = ctypes.c_void_p()
+        with torch.cuda.device(indptr.device):
+            check(lib.bns_graph_create(ctypes.byref(out), indptr.numel() - 1, n_cols, indices.numel(),
+                                       indptr.data_ptr(), indices.data_ptr() if indices.numel() else None,
+                                       chunk_nnz, _stream_ptr()), "bns_graph_create")
+        return cls(out.value, indptr.device)
+
+    def transpose(self) -> "DeviceGraph":
+        if self._t is None:
+            out = ctypes.c_void_p()
+            with torch.cuda.device(self.device):
+                check(lib.bns_graph_transpose(self._h, ctypes.byref(out), _stream_ptr()), "bns_graph_transpose")
+            self._t = DeviceGraph(out.value, self.device)
+            self._t._t = self
+        return self._t
+
+    def csr(self):
+        """Copies of the library-owned CSR (for tests)."""
+        indptr = torch.empty(self.n_rows + 1, dtype=torch.int64, device=self.device)
+        indices = torch.empty(self.nnz, dtype=torch.int32, device=self.device)
+        with torch.cuda.device(self.device):
+            check(lib.bns_graph_copy_csr(self._h, indptr.data_ptr(), indices.data_ptr() if self.nnz else None,
+                                         _stream_ptr()), "bns_graph_copy_csr")
+        return indptr, indices
+
+    def workspace(self, F: int) -> Optional[torch.Tensor]:
+        need = lib.bns_spmm_workspace_bytes(self._h, F)
+        if need == 0:
+            return None
+        ws = self._ws.get(F)
+        if ws is None or ws.numel() < need:
+            ws = torch.empty(need, dtype=torch.uint8, device=self.device)
+            self._ws[F] = ws
+        return ws
+
+    def __del__(self):
+        h, self._h = getattr(self, "_h", None), None
+        if h:
+            try:
+                lib.bns_graph_destroy(h)
+            except Exception:   # interpreter shutdown
+                pass
+
+
+def spmm(g: DeviceGraph, x: torch.Tensor, out: Optional[torch.Tensor] = None, *, n_out_rows: Optional[int] = None,
+         row_scale: Optional[torch.Tensor] = None, col_scale: Optional[torch.Tensor] = None,
+         row_map: Optional[torch.Tensor] = None, col_map: Optional[torch.Tensor] = None, n_direct: int = 0,
+         accumulate: bool = False) -> torch.Tensor:
+    """``bns_spmm_sum_f32``: ``out[orow(r)] (+)= row_scale[r] * sum_k col_scale[c_k] * x[xrow(c_k)]``."""
+    _req(x, torch.float32, "x")
+    if x.dim() != 2 or x.stride(1) != 1:
+        raise _lib.BnsError("x must be a row-major 2-D tensor")
+    F = x.shape[1]
+    if out is None:
+        if accumulate:
+            raise _lib.BnsError("accumulate=True needs an output tensor")
+        rows = g.n_rows if n_out_rows is None else n_out_rows
+        out = torch.empty(rows, F, dtype=torch.float32, device=x.device)
+    _req(out, torch.float32, "out")
+    if out.dim() != 2 or out.stride(1) != 1 or out.shape[1] != F:
+        raise _lib.BnsError("out must be row-major [*, F]")
+    for t, n, nm in ((row_scale, torch.float32, "row_scale"), (col_scale, torch.float32, "col_scale"),
+                     (row_map, torch.int32, "row_map"), (col_map, torch.int32, "col_map")):
+        if t is not None:
+            _req(t, n, nm)
+    ws = g.workspace(F)
+    with torch.cuda.device(x.device):
+        check(lib.bns_spmm_sum_f32(g._h, x.data_ptr(), x.stride(0), F, out.data_ptr(), out.stride(0),
+                                   _ptr(row_scale), _ptr(col_scale), _ptr(row_map), _ptr(col_map), n_direct,
+                                   1 if accumulate else 0, _ptr(ws), 0 if ws is None else ws.numel(), _stream_ptr()),
+              "bns_spmm_sum_f32")
+    return out
+
+
+class AggregateSum(torch.autograd.Function):
+    """``Y = rs * (A @ (cs * X))`` on a static ``DeviceGraph`` ``A [n_dst, n_src]`` and its transpose in backward.
+
+    The full-graph (single partition / evaluation) form of module/layer.py:35-38, 88-91: ``rs`` is ``1/in_deg``
+    (GraphSAGE) or ``1/sqrt(in_deg)`` (GCN), ``cs`` is ``1/sqrt(out_deg)`` (GCN) or ``None``.
+    """
+
+    @staticmethod
+    def forward(ctx, x, g: DeviceGraph, row_scale, col_scale):
+        ctx.g, ctx.rs, ctx.cs = g, row_scale, col_scale
+        return spmm(g, x.contiguous(), row_scale=row_scale, col_scale=col_scale)
+
+    @staticmethod
+    def backward(ctx, dy):
+        gt = ctx.g.transpose()
+        dx = spmm(gt, dy.contiguous(), row_scale=ctx.cs, col_scale=ctx.rs)
+        return dx, None, None, None
+
+
+def gather_div(h: torch.Tensor, idx: torch.Tensor, div: float, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """``out[i] = h[idx[i]] / div`` (helper/feature_buffer.py:117)."""
+    _req(h, torch.float32, "h")
+    _req(idx, torch.int64, "idx")
+    k, F = idx.numel(), h.shape[1]
+    if out is None:
+        out = torch.empty(k, F, dtype=torch.float32, device=h.device)
+    with torch.cuda.device(h.device):
+        check(lib.bns_gather_div_f32(h.data_ptr(), h.stride(0), F, idx.data_ptr(), k, float(div), out.data_ptr(),
+                                     out.stride(0), _stream_ptr()), "bns_gather_div_f32")
+    return out
+
+
+def scatter_add_div(g: torch.Tensor, idx: torch.Tensor, src: torch.Tensor, div: float) -> torch.Tensor:
+    """``g[idx[i]] += src[i] / div`` in place (helper/feature_buffer.py:129)."""
+    _req(g, torch.float32, "g")
+    _req(src, torch.float32, "src")
+    _req(idx, torch.int64, "idx")
+    with torch.cuda.device(g.device):
+        check(lib.bns_scatter_add_div_f32(g.data_ptr(), g.stride(0), g.shape[1], idx.data_ptr(), idx.numel(),
+                                          float(div), src.data_ptr(), src.stride(0), _stream_ptr()),
+              "bns_scatter_add_div_f32")
+    return g
+
+
+def copy_rows(src: torch.Tensor, dst: torch.Tensor, n_rows: int) -> None:
+    with torch.cuda.device(src.device):
+        check(lib.bns_copy_rows_f32(src.data_ptr(), src.stride(0), dst.data_ptr(), dst.stride(0), n_rows,
+                                    src.shape[1], _stream_ptr()), "bns_copy_rows_f32")
+
+
+class BoundarySampler:
+    """All peers' boundary samples in one call (``bns_sample_boundary``; replaces train.py:225-236)."""
+
+    def __init__(self, boundary, send_size, device):
+        segs = [(j, b) for j, b in enumerate(boundary) if b is not None]
+        self.peers = [j for j, _ in segs]
+        self.sizes = [int(send_size[j]) for j in self.peers]
+        lens = [int(b.numel()) for _, b in segs]
+        self.B, self.K = sum(lens), sum(self.sizes)
+        self.device = device
+        if segs:
+            self.cat = torch.cat([b.to(device=device, dtype=torch.int64) for _, b in segs]).contiguous()
+        else:
+            self.cat = torch.empty(0, dtype=torch.int64, device=device)
+        self.seg_begin = torch.tensor([0] + list(torch.tensor(lens).cumsum(0).tolist()) if lens else [0],
+                                      dtype=torch.int64, device=device)
+        self.out_begin_host = [0]
+        for s in self.sizes:
+            self.out_begin_host.append(self.out_begin_host[-1] + s)
+        self.out_begin = torch.tensor(self.out_begin_host, dtype=torch.int64, device=device)
+        self.ws = torch.empty(max(lib.bns_sample_workspace_bytes(self.B), 16), dtype=torch.uint8, device=device)
+        self.world = len(boundary)
+
+    def sample(self, seed: int, offset: int):
+        """Returns ``(selected_cat, [per-peer views or None])``."""
+        sel = torch.empty(self.K, dtype=torch.int64, device=self.device)
+        if self.K:
+            with torch.cuda.device(self.device):
+                check(lib.bns_sample_boundary(self.cat.data_ptr(), self.seg_begin.data_ptr(), self.out_begin.data_ptr(),
+                                              len(self.peers), self.B, self.K, seed & (2**64 - 1), offset & (2**64 - 1),
+                                              sel.data_ptr(), self.ws.data_ptr(), self.ws.numel(), _stream_ptr()),
+                      "bns_sample_boundary")
+        views = [None] * self.world
+        for i, j in enumerate(self.peers):
+            views[j] = sel[self.out_begin_host[i]:self.out_begin_host[i + 1]]
+        return sel, views
+
+
+def fill_i32(t: torch.Tensor, value: int) -> None:
+    _req(t, torch.int32, "t")
+    with torch.cuda.device(t.device):
+        check(lib.bns_fill_i32(t.data_ptr(), t.numel(), value, _stream_ptr()), "bns_fill_i32")
+
+
+def halo_slot_update(pos: torch.Tensor, one_hops: torch.Tensor, n_in: int, slab_offset: int, slot: torch.Tensor) -> None:
+    """``slot[pos[one_hops[k]] - n_in] = slab_offset + k`` (replaces train.py:268-275)."""
+    _req(pos, torch.int64, "pos")
+    _req(one_hops, torch.int64, "one_hops")
+    _req(slot, torch.int32, "slot")
+    with torch.cuda.device(slot.device):
+        check(lib.bns_halo_slot_update(pos.data_ptr(), one_hops.data_ptr(), one_hops.numel(), n_in, slab_offset,
+                                       slot.data_ptr(), _stream_ptr()), "bns_halo_slot_update")

@@ -1,0 +1,176 @@
+/*
+ * bnsgcn.h -- C ABI of libbnsgcn.so: the B200 (sm_100a) replacement for the device work the
+ * BNS-GCN hot path reaches through DGL / ATen / numpy.
+ *
+ * The reference (GATECH-EIC/BNS-GCN, 100 % Python) has no FFI layer of its own: its "operator API"
+ * is the set of Python call sites cited beside each entry point below (paths relative to the
+ * reference root).  INTEGRATION.md shows the ctypes stub a maintainer would add at each of them.
+ *
+ * Conventions
+ *   - plain C symbols, plain pointers and sizes; no torch / C++ types cross this boundary;
+ *   - every pointer marked "device" is a CUDA device pointer owned by the caller (PyTorch owns the
+ *     tensors; the library never frees or reallocates caller memory);
+ *   - `stream` is a cudaStream_t passed as void*; all work is enqueued on it, nothing synchronises
+ *     the host except bns_graph_create / bns_graph_transpose (setup) and where stated;
+ *   - return value: 0 = ok, negative = error (BNS_E_*); bns_last_error() gives the message of the
+ *     calling thread's most recent failure;
+ *   - after *_create the library allocates nothing: scratch space is passed in (`ws`, sized by the
+ *     matching *_workspace_bytes query);
+ *   - thread-compatible: distinct handles may be used from distinct threads concurrently.
+ *   - feature matrices are row-major f32; graph ids int32 on device (train.py:71-73 uses int32
+ *     graphs), row offsets int64, exchanged index lists int64 (train.py:233-234, utils.py:171).
+ */
+#ifndef BNSGCN_H_
+#define BNSGCN_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define BNS_OK            0
+#define BNS_E_INVALID    (-1)   /* bad argument (null pointer, negative size, misaligned leading dim) */
+#define BNS_E_CUDA       (-2)   /* a CUDA runtime call failed; message holds cudaGetErrorString */
+#define BNS_E_WORKSPACE  (-3)   /* workspace too small */
+#define BNS_E_UNSUPPORTED (-4)
+
+#define BNS_ABI_VERSION 1
+
+typedef struct bns_graph bns_graph_t;   /* opaque: a static CSR matrix resident in HBM */
+typedef struct bns_p2p   bns_p2p_t;     /* opaque: peer-mapped exchange slabs of one rank */
+
+int         bns_abi_version(void);
+const char *bns_last_error(void);
+/* Name, SM count, L2 bytes of the current device (for bench.py's grid / roofline bookkeeping). */
+int         bns_device_info(char *name, size_t name_len, int *sm_count, int64_t *l2_bytes, int *cc_major, int *cc_minor);
+
+/* ------------------------------------------------------------------------------------------------
+ * Static graphs.  Replaces the per-epoch dgl.heterograph rebuild of train.py:256-281
+ * (construct_graph) and DGL's lazy COO->CSR/CSC conversion: a graph is built ONCE, per-epoch
+ * sampling only changes the small `col_map` / `row_map` arrays given to bns_spmm_sum_f32.
+ *
+ * bns_graph_create copies a device CSR (row r's entries are indices[indptr[r] .. indptr[r+1])) and
+ * precomputes the nnz-balanced work decomposition (rows are cut into chunks of <= chunk_nnz
+ * entries; rows longer than a chunk are combined by a deterministic second pass).
+ *   n_rows, n_cols : matrix shape; every index must lie in [0, n_cols)
+ *   chunk_nnz      : 0 = library default
+ * ----------------------------------------------------------------------------------------------*/
+int bns_graph_create(bns_graph_t **out, int64_t n_rows, int64_t n_cols, int64_t nnz,
+                     const int64_t *indptr /*device [n_rows+1]*/, const int32_t *indices /*device [nnz]*/,
+                     int32_t chunk_nnz, void *stream);
+/* CSR of the reversed graph (what autograd needs for K1b): out[c] lists the rows r with
+ * (r, c) in g, ascending.  Built once, on the device (radix sort). */
+int bns_graph_transpose(const bns_graph_t *g, bns_graph_t **out, void *stream);
+int bns_graph_destroy(bns_graph_t *g);
+int bns_graph_info(const bns_graph_t *g, int64_t *n_rows, int64_t *n_cols, int64_t *nnz,
+                   int64_t *n_chunks, int64_t *n_split_rows);
+/* Copy the library-owned CSR into caller buffers (device [n_rows+1] / [nnz]); for tests and tools. */
+int bns_graph_copy_csr(const bns_graph_t *g, int64_t *indptr_out, int32_t *indices_out, void *stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * K1 / K1b / K2: the aggregation.  Replaces
+ *     graph['_E'].update_all(fn.copy_u('h','m'), fn.sum('m','h'))        module/layer.py:35-37, 88-90
+ *     ... / degs, feat / out_norm, ... / in_norm                         module/layer.py:34, 38, 91
+ * and their autograd transposes, with
+ *     Y[orow(r), :] = (accumulate ? Y[orow(r), :] : 0)
+ *                     + row_scale[r] * sum_{k in row r, xrow(c_k) >= 0} col_scale[c_k] * X[xrow(c_k), :]
+ *   xrow(c) = c                       if c <  n_direct
+ *           = col_map[c - n_direct]   otherwise (-1 = entry skipped: an unsampled halo node)
+ *   orow(r) = r  if row_map == NULL, else row_map[r]  (-1 = row skipped)
+ * row_scale / col_scale / row_map / col_map may be NULL (= 1 / identity; col_map == NULL means
+ * n_direct = n_cols).  All f32; summation order inside a row is the CSR order (deterministic).
+ *   X  [*, F] with leading dimension ldx (floats); Y [*, F] with ldy.
+ * The 16-byte vector path needs F % 4 == 0, ldx % 4 == 0, ldy % 4 == 0 and 16-byte aligned X, Y;
+ * anything else takes the scalar path (same results).
+ * ws: scratch of at least bns_spmm_workspace_bytes(g, F) bytes (0 when no row is split).
+ * ----------------------------------------------------------------------------------------------*/
+size_t bns_spmm_workspace_bytes(const bns_graph_t *g, int64_t F);
+int bns_spmm_sum_f32(const bns_graph_t *g,
+                     const float *X, int64_t ldx, int64_t F,
+                     float *Y, int64_t ldy,
+                     const float *row_scale /*device [n_rows] or NULL*/,
+                     const float *col_scale /*device [n_cols] or NULL*/,
+                     const int32_t *row_map /*device [n_rows] or NULL*/,
+                     const int32_t *col_map /*device [n_cols - n_direct] or NULL*/, int64_t n_direct,
+                     int accumulate, void *ws, size_t ws_bytes, void *stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * K3 / K4 / K5: boundary pack / concat / scatter.  helper/feature_buffer.py:
+ *   :117  send_cpu[right].copy_(send_gpu[self._selected[right]] / self._ratio[right])
+ *   :85-91 __feat_concat  (cat([feat, recv_0, ...]))
+ *   :129  send_gpu[self._selected[idx]] += recv / self._ratio[idx]
+ * out[i, :] = H[idx[i], :] / div        (true division, as the reference)
+ * G[idx[i], :] += src[i, :] / div       (idx must not repeat inside one call; calls on one stream
+ *                                         are ordered, which is how the reference orders peers)
+ * ----------------------------------------------------------------------------------------------*/
+int bns_gather_div_f32(const float *H, int64_t ldh, int64_t F, const int64_t *idx /*device [k]*/, int64_t k,
+                       float div, float *out, int64_t ldo, void *stream);
+int bns_scatter_add_div_f32(float *G, int64_t ldg, int64_t F, const int64_t *idx /*device [k]*/, int64_t k,
+                            float div, const float *src, int64_t lds, void *stream);
+/* dst[r, :F] = src[r, :F] for r < n_rows (the "inner" block of the concat buffer). */
+int bns_copy_rows_f32(const float *src, int64_t lds, float *dst, int64_t ldd, int64_t n_rows, int64_t F, void *stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * K6: boundary-node sampling.  Replaces train.py:225-236 (select_node):
+ *     idx = np.random.choice(b.shape[0], send_size[i], replace=False);  selected = boundary[i][idx]
+ * i.e. a uniformly random ORDERED k-subset per peer.  All peers are drawn by one call:
+ *   boundary_cat : the sorted boundary lists of the n_seg peers, concatenated (device, int64 [B])
+ *   seg_begin    : device int64 [n_seg+1], boundary list s is boundary_cat[seg_begin[s] .. seg_begin[s+1])
+ *   out_begin    : device int64 [n_seg+1], prefix sums of the sample sizes k_s (k_s <= b_s)
+ *   selected     : device int64 [K_total], peer s's sample is selected[out_begin[s] .. out_begin[s+1])
+ * Element i of boundary_cat gets the key  (s << 56) | r56(i),  r56 = the top 56 bits of
+ * Philox4x32-10(counter = (i_lo, i_hi, offset_lo, offset_hi), key = (seed_lo, seed_hi)) words 0,1;
+ * a stable radix sort orders each segment by key and the first k_s entries are the sample.
+ * Counter-based => reproducible: the oracle replays it bit for bit (oracle/philox.py).
+ * ----------------------------------------------------------------------------------------------*/
+size_t bns_sample_workspace_bytes(int64_t B);
+int bns_sample_boundary(const int64_t *boundary_cat, const int64_t *seg_begin, const int64_t *out_begin,
+                        int32_t n_seg, int64_t B, int64_t K_total, uint64_t seed, uint64_t offset,
+                        int64_t *selected, void *ws, size_t ws_bytes, void *stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * K7: per-epoch graph "rebuild".  Replaces train.py:256-281 (construct_graph) and 245-253
+ * (construct_out_norm): instead of building a new heterograph, record where each sampled halo node's
+ * row lives in the receive slab:
+ *     slot[pos[one_hops[k]] - n_in] = slab_offset + k        k = 0 .. r-1
+ * (`pos` = get_pos() of train.py:90-104: owner-local id -> my local node id, -1 if not my halo).
+ * Call bns_fill_i32(slot, n_halo, -1) first, then once per peer.
+ * ----------------------------------------------------------------------------------------------*/
+int bns_fill_i32(int32_t *dst, int64_t n, int32_t value, void *stream);
+int bns_halo_slot_update(const int64_t *pos /*device [part size of the peer]*/, const int64_t *one_hops /*device [r]*/,
+                         int64_t r, int64_t n_in, int32_t slab_offset, int32_t *slot /*device [n_halo]*/, void *stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * C1/C2 fused with K3/K5: the boundary exchange over peer-mapped memory (NVLink 5 / NVSwitch).
+ * Replaces Buffer.__gloo_all_to_all / __mpi_all_to_all (helper/feature_buffer.py:101-153): the pack
+ * kernel of rank a stores  H[selected_b] / ratio_b  straight into rank b's receive slab, then raises a
+ * flag in b's memory; b's stream waits on the flag.  No staging buffer, no host round trip.
+ * One bns_p2p_t per rank; slabs are cudaMalloc'd by the library so that they can be exported with
+ * cudaIpcGetMemHandle (processes) or shared by pointer (ranks that are threads of one process).
+ * ----------------------------------------------------------------------------------------------*/
+#define BNS_P2P_HANDLE_BYTES 64
+int bns_p2p_create(bns_p2p_t **out, int32_t rank, int32_t world, size_t slab_bytes, int32_t n_flags);
+int bns_p2p_destroy(bns_p2p_t *p);
+/* base of this rank's slab / flag block (device pointers, valid in this process) */
+int bns_p2p_local(const bns_p2p_t *p, void **slab, void **flags);
+/* IPC export / import (multi-process).  handle_out: BNS_P2P_HANDLE_BYTES bytes for the slab followed by
+ * BNS_P2P_HANDLE_BYTES bytes for the flags. */
+int bns_p2p_export(const bns_p2p_t *p, void *handle_out /*2*BNS_P2P_HANDLE_BYTES*/);
+int bns_p2p_import(bns_p2p_t *p, int32_t peer, const void *handle /*2*BNS_P2P_HANDLE_BYTES*/);
+/* In-process peers (threads): register the peer's pointers directly. */
+int bns_p2p_set_peer(bns_p2p_t *p, int32_t peer, void *slab, void *flags);
+/* remote_rows[i, :F] (in peer's slab at byte offset remote_off, leading dim ld_remote floats)
+ *     = H[idx[i], :F] / div   for i < k   (idx == NULL: rows i of H, used for the gradient return trip);
+ * then, after a system-scope fence, peer.flags[flag_index] = flag_value (release). */
+int bns_p2p_put_rows_f32(bns_p2p_t *p, int32_t peer, size_t remote_off, int64_t ld_remote,
+                         const float *H, int64_t ldh, int64_t F, const int64_t *idx, int64_t k, float div,
+                         int32_t flag_index, uint64_t flag_value, void *stream);
+/* Enqueue a wait on `stream` until this rank's flags[flag_index] >= flag_value (acquire). */
+int bns_p2p_wait_flag(bns_p2p_t *p, int32_t flag_index, uint64_t flag_value, void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* BNSGCN_H_ */
