@@ -591,9 +591,10 @@ extern "C" int bns_spmm_sum_f32(const bns_graph_t *g, const float *X, int64_t ld
                                 void *stream) {
     BNS_REQUIRE(g, "bns_spmm_sum_f32: NULL graph");
     BNS_REQUIRE(F > 0 && F < (1 << 24), "bns_spmm_sum_f32: bad feature width %lld", (long long)F);
-    BNS_REQUIRE(X && Y, "bns_spmm_sum_f32: NULL matrix");
+    if (g->n_rows == 0) return BNS_OK;      // nothing to write (Y may legitimately be NULL)
+    BNS_REQUIRE(Y, "bns_spmm_sum_f32: NULL output matrix");
+    BNS_REQUIRE(X || g->nnz == 0, "bns_spmm_sum_f32: NULL input matrix");
     BNS_REQUIRE(ldx >= F && ldy >= F, "bns_spmm_sum_f32: leading dimension smaller than F");
-    if (g->n_rows == 0) return BNS_OK;
     const size_t need = bns_spmm_workspace_bytes(g, F);
     if (need > 0 && (ws == nullptr || ws_bytes < need))
         return fail(BNS_E_WORKSPACE, "bns_spmm_sum_f32: workspace %zu bytes < %zu needed", ws_bytes, need);

@@ -1,0 +1,95 @@
+"""Graph handles passed to the layers in place of DGL graphs.
+
+``PartitionGraph`` is what ``train.construct_graph`` returns: the reference rebuilds a bipartite ``_U -> _V``
+``dgl.heterograph`` every epoch (train.py:256-281); here the structure is static -- ``a_in`` (inner -> inner) and
+``a_out`` (halo -> inner), each with its transpose, all built once -- and an epoch only rewrites ``slot``:
+``slot[h]`` = row of halo node ``h`` in this epoch's receive slab (U-numbering minus ``n_in``), or -1 when the
+owner did not sample it.  Callers see the same surface the layers use: ``num_nodes('_V')``.
+
+``FullGraphHandle`` is the homogeneous graph of the evaluation branch (module/layer.py:39-45, 93-102).
+"""
+from __future__ import annotations
+
+from typing import Dict, Optional
+
+import torch
+
+from . import ops
+
+
+class PartitionGraph:
+    def __init__(self, n_in: int, n_halo: int, a_in: ops.DeviceGraph, a_out: Optional[ops.DeviceGraph], device):
+        self.n_in, self.n_halo = n_in, n_halo
+        self.a_in, self.a_out = a_in, a_out
+        self.a_in_t = a_in.transpose()
+        self.a_out_t = a_out.transpose() if a_out is not None else None
+        self.device = device
+        self.slot = torch.full((max(n_halo, 1),), -1, dtype=torch.int32, device=device)
+        self.n_u = n_in
+        self._recip: Dict[int, torch.Tensor] = {}
+
+    def num_nodes(self, ntype: str = '_V') -> int:
+        return self.n_in if ntype == '_V' else self.n_u
+
+    def num_edges(self) -> int:
+        return self.a_in.nnz + (self.a_out.nnz if self.a_out is not None else 0)
+
+    def recip(self, t: torch.Tensor) -> torch.Tensor:
+        """``1 / t`` as f32, cached per source tensor (degree / norm vectors are static)."""
+        key = (t.data_ptr(), t.numel(), t.dtype)
+        r = self._recip.get(key)
+        if r is None:
+            r = (1.0 / t.to(torch.float32)).contiguous()
+            self._recip[key] = r
+        return r
+
+
+class FullGraphHandle:
+    def __init__(self, a: ops.DeviceGraph, in_deg: torch.Tensor, out_deg: torch.Tensor):
+        self.a = a
+        self._in, self._out = in_deg, out_deg
+
+    def num_nodes(self, ntype: str = '_V') -> int:
+        return self.a.n_rows
+
+    def in_degrees(self):
+        return self._in
+
+    def out_degrees(self):
+        return self._out
+
+
+class PartitionAggregate(torch.autograd.Function):
+    """K1 + K2 (+ K1b in backward) on a ``PartitionGraph``:
+
+        Y = rs * ( A_in (cs_in * H_U[:n_in])  +  A_out[:, sampled] (cs_halo * H_U[n_in:]) )
+
+    The inner-edge pass only needs the local rows, so it is issued first; the halo pass waits for the exchange
+    (``ready`` event recorded by ``Buffer.update(..., overlap=True)``) -- that is the comm/compute overlap.
+    """
+
+    @staticmethod
+    def forward(ctx, h_u, g: PartitionGraph, rs, cs_in, cs_halo, ready):
+        ctx.g, ctx.rs, ctx.cs_in, ctx.cs_halo = g, rs, cs_in, cs_halo
+        ctx.n_u = h_u.shape[0]
+        h_u = h_u.contiguous()
+        y = ops.spmm(g.a_in, h_u, row_scale=rs, col_scale=cs_in)
+        if ready is not None:
+            torch.cuda.current_stream(h_u.device).wait_event(ready)
+        if g.a_out is not None and ctx.n_u > g.n_in:
+            ops.spmm(g.a_out, h_u[g.n_in:], y, row_scale=rs, col_scale=cs_halo, col_map=g.slot, n_direct=0,
+                     accumulate=True)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        g = ctx.g
+        dy = dy.contiguous()
+        du = torch.empty(ctx.n_u, dy.shape[1], dtype=torch.float32, device=dy.device)
+        if ctx.n_u > g.n_in:
+            tail = du[g.n_in:]
+            tail.zero_()
+            if g.a_out_t is not None:
+                ops.spmm(g.a_out_t, dy, tail, row_scale=ctx.cs_halo, col_scale=ctx.rs, row_map=g.slot)
+        ops.spmm(g.a_in_t, dy, du[:g.n_in], row_scale=ctx.cs_in, col_scale=ctx.rs)
+        return du, None, None, None, None, None

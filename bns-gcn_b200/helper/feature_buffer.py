@@ -1,0 +1,281 @@
+"""``Buffer``: the sampled boundary-feature exchange (reference: helper/feature_buffer.py).
+
+Same surface -- ``init_buffer(num_in, ratio, f_send_shape, f_recv_shape, layer_size, use_pp, backend)``,
+``set_selected(selected)``, ``update(layer, feat) -> [n_U, F]`` whose gradient does the reverse exchange and the
+``/ratio`` scatter-add (``__grad_hook``, :169-174) -- but nothing leaves the device:
+
+* ``backend='nccl'`` (staged): pack kernel (K3, ``bns_gather_div_f32``) -> one grouped NCCL send/recv on a side
+  stream straight into the tail rows of the concat buffer -> scatter-add kernel (K5) in backward.  Replaces the
+  pinned-host gloo ring of :101-129.
+* ``backend='p2p'``: the pack kernel of the sender stores ``H[selected]/ratio`` directly into the receiver's concat
+  buffer through a peer-mapped pointer (NVLink 5 / NVSwitch) and raises a flag there (``bns_p2p_put_rows_f32`` /
+  ``bns_p2p_wait_flag``): K3 + C1 fused, no staging copy, no NCCL launch.
+
+The exchange runs on ``self._comm_stream``; with ``update(..., overlap=True)`` the caller's stream does not wait
+for it -- the aggregation op waits on ``h_u._bns_ready`` right before it touches the halo rows, so the transfer
+hides behind the inner-edge SpMM.  ``Comm(s)`` is measured with CUDA events on that stream.
+"""
+from __future__ import annotations
+
+import ctypes
+import struct
+from typing import List, Optional
+
+import torch
+
+from .. import ops
+from .._lib import P2P_HANDLE_BYTES, check, lib
+from . import context as ctx
+from .timer.timer import comm_timer
+
+
+class _DevArray:
+    """Zero-copy torch view of library-owned device memory (``__cuda_array_interface__``)."""
+
+    def __init__(self, ptr: int, shape, typestr="<f4"):
+        self.__cuda_array_interface__ = {"shape": tuple(shape), "typestr": typestr, "data": (ptr, False),
+                                         "version": 2, "strides": None}
+
+
+class Buffer(object):
+
+    def __init__(self):
+        super(Buffer, self).__init__()
+        self._num_in = None
+        self._selected: List[Optional[torch.Tensor]] = []
+        self._n_layers = 0
+        self._layer_size = []
+        self._ratio = []
+        self._recv_shape, self._send_shape = [], []
+        self._backend = None
+        self._pl, self._pr = [], []
+        self._comm_stream = None
+        self._send_buf, self._b_recv = None, None
+        self._p2p = None
+        self._seq = {}
+
+    # helper/feature_buffer.py:23-33
+    def __init_pl_pr(self):
+        self._pl, self._pr = [], []
+        tot = self._num_in
+        for j, s in enumerate(self._recv_shape):
+            if j == self._rank:
+                self._pl.append(None)
+                self._pr.append(None)
+            else:
+                self._pl.append(tot)
+                tot += s
+                self._pr.append(tot)
+        self._n_u = tot
+
+    def init_buffer(self, num_in, ratio, f_send_shape, f_recv_shape, layer_size, use_pp=False, backend='nccl',
+                    device=None):
+        if use_pp is False:
+            raise NotImplementedError            # helper/feature_buffer.py:36-37
+        c = ctx.comm()
+        self._rank, self._size = c.rank, c.size
+        self._num_in = num_in
+        self._n_layers = len(layer_size)
+        self._layer_size = layer_size
+        self._recv_shape = [int(s) for s in f_recv_shape]
+        self._send_shape = [int(s) for s in f_send_shape]
+        self._ratio = ratio
+        if backend in ('nccl', 'staged'):
+            backend = 'nccl'
+        elif backend != 'p2p':
+            raise NotImplementedError(f"backend {backend!r}: this build moves boundary rows GPU-to-GPU "
+                                      "('nccl' or 'p2p'); the reference's host-staged gloo/mpi paths are what it replaces")
+        self._backend = backend
+        self.__init_pl_pr()
+        if self._size == 1:
+            return
+        self._device = torch.device(device if device is not None else torch.cuda.current_device())
+        if self._device.type != 'cuda':
+            raise RuntimeError("Buffer needs a CUDA device: there is no CPU exchange path")
+        width = self._layer_size[1]              # the reference sizes every slab with layer_size[1] (:54-55)
+        self._width = width
+        self._comm_stream = torch.cuda.Stream(self._device)
+        self._send_begin, tot = [], 0
+        for j in range(self._size):
+            self._send_begin.append(tot)
+            tot += 0 if j == self._rank else self._send_shape[j]
+        self._send_total = tot
+        if backend == 'nccl':
+            self._send_buf = [None if j == self._rank else
+                              torch.zeros(self._send_shape[j], width, device=self._device) for j in range(self._size)]
+            self._b_recv = [None if j == self._rank else
+                            torch.zeros(self._send_shape[j], width, device=self._device) for j in range(self._size)]
+        else:
+            self.__init_p2p(c, width)
+
+    # ---- p2p slabs -------------------------------------------------------------------------------
+    def __init_p2p(self, c, width):
+        n_comm_layers = max(self._n_layers - 1, 1)
+        fwd_rows, bwd_rows = self._n_u, max(self._send_total, 1)
+        row_bytes = width * 4
+        self._fwd_off = [l * (fwd_rows + bwd_rows) * row_bytes for l in range(n_comm_layers)]
+        self._bwd_off = [o + fwd_rows * row_bytes for o in self._fwd_off]
+        slab_bytes = n_comm_layers * (fwd_rows + bwd_rows) * row_bytes
+        n_flags = n_comm_layers * 2 * self._size
+        h = ctypes.c_void_p()
+        with torch.cuda.device(self._device):
+            check(lib.bns_p2p_create(ctypes.byref(h), self._rank, self._size, slab_bytes, n_flags), "bns_p2p_create")
+        self._p2p = h
+        slab, flags = ctypes.c_void_p(), ctypes.c_void_p()
+        check(lib.bns_p2p_local(h, ctypes.byref(slab), ctypes.byref(flags)), "bns_p2p_local")
+        self._slab_ptr = slab.value
+        # publish: where peers must write inside MY slab (row offsets of their segment) + how to map my memory
+        my = {"fwd_off": self._fwd_off, "bwd_off": self._bwd_off, "pl": self._pl, "send_begin": self._send_begin}
+        if c.kind == "thread":
+            my["ptrs"] = (slab.value, flags.value)
+        else:
+            hb = ctypes.create_string_buffer(2 * P2P_HANDLE_BYTES)
+            check(lib.bns_p2p_export(h, hb), "bns_p2p_export")
+            my["handle"] = hb.raw
+        import pickle
+        table = [pickle.loads(b) for b in c.all_gather_bytes(pickle.dumps(my))]
+        self._peer_layout = table
+        for j in range(self._size):
+            if j == self._rank:
+                continue
+            if c.kind == "thread":
+                check(lib.bns_p2p_set_peer(h, j, table[j]["ptrs"][0], table[j]["ptrs"][1]), "bns_p2p_set_peer")
+            else:
+                with torch.cuda.device(self._device):
+                    check(lib.bns_p2p_import(h, j, table[j]["handle"]), "bns_p2p_import")
+        c.barrier()
+
+    def _flag(self, layer, backward, src):
+        return ((layer - 1) * 2 + (1 if backward else 0)) * self._size + src
+
+    def _slab_view(self, byte_off, rows):
+        return torch.as_tensor(_DevArray(self._slab_ptr + byte_off, (rows, self._width)), device=self._device)
+
+    def set_selected(self, selected):
+        self._selected = selected
+
+    # ---- forward ---------------------------------------------------------------------------------
+    def update(self, layer, feat, overlap=False):
+        """``[feat ; recv_0 ; recv_1 ...]`` with the boundary rows of the peers (helper/feature_buffer.py:93-99)."""
+        if self._size == 1:
+            return feat
+        res = _BoundaryExchange.apply(feat, self, layer, overlap)
+        if overlap:
+            res._bns_ready = self._last_ready
+        return res
+
+    def _forward(self, layer, feat, overlap):
+        F = feat.shape[1]
+        if F > self._width:
+            raise RuntimeError(f"layer width {F} > slab width {self._width} (the reference sizes slabs with layer_size[1])")
+        feat = feat.contiguous()
+        main, cs = torch.cuda.current_stream(self._device), self._comm_stream
+        ready = torch.cuda.Event()
+        if self._backend == 'nccl':
+            h_u = torch.empty(self._n_u, F, device=self._device)
+        else:
+            h_u = self._slab_view(self._fwd_off[layer - 1], self._n_u)[:, :F] if F == self._width else None
+            if h_u is None:
+                raise RuntimeError("p2p transport needs equal hidden widths")
+        ops.copy_rows(feat, h_u, self._num_in)                         # K4: the only copy of the concat
+        start = torch.cuda.Event()
+        start.record(main)
+        cs.wait_event(start)
+        with torch.cuda.stream(cs):
+            with comm_timer.timer(f'forward_{layer}', stream=cs):
+                if self._backend == 'nccl':
+                    send = [None] * self._size
+                    recv = [None] * self._size
+                    for j in range(self._size):
+                        if j == self._rank:
+                            continue
+                        send[j] = self._send_buf[j][:, :F] if F == self._width else \
+                            torch.empty(self._send_shape[j], F, device=self._device)
+                        ops.gather_div(feat, self._selected[j], self._ratio[j], out=send[j])      # K3
+                        recv[j] = h_u[self._pl[j]:self._pr[j]]
+                    ctx.comm().alltoall(send, recv, tag=16 + layer)                               # C1/C2
+                else:
+                    seq = self._seq[(layer, 0)] = self._seq.get((layer, 0), 0) + 1
+                    for i in range(1, self._size):
+                        j = (self._rank + i) % self._size
+                        lay = self._peer_layout[j]
+                        off = lay["fwd_off"][layer - 1] + lay["pl"][self._rank] * self._width * 4
+                        check(lib.bns_p2p_put_rows_f32(self._p2p, j, off, self._width, feat.data_ptr(), feat.stride(0),
+                                                       F, ops._ptr(self._selected[j]), self._send_shape[j],
+                                                       float(self._ratio[j]), self._flag(layer, False, self._rank), seq,
+                                                       cs.cuda_stream), "bns_p2p_put_rows_f32")
+                    for i in range(1, self._size):
+                        j = (self._rank - i + self._size) % self._size
+                        check(lib.bns_p2p_wait_flag(self._p2p, self._flag(layer, False, j), seq, cs.cuda_stream),
+                              "bns_p2p_wait_flag")
+            ready.record(cs)
+        feat.record_stream(cs)
+        h_u.record_stream(cs)
+        if not overlap:
+            main.wait_event(ready)
+        self._last_ready = ready
+        return h_u
+
+    # ---- backward (the grad hook) -------------------------------------------------------------------
+    def _backward(self, layer, grad):
+        F = grad.shape[1]
+        if not grad.is_contiguous():
+            grad = grad.contiguous()
+        main, cs = torch.cuda.current_stream(self._device), self._comm_stream
+        start, done = torch.cuda.Event(), torch.cuda.Event()
+        start.record(main)
+        cs.wait_event(start)
+        with torch.cuda.stream(cs):
+            with comm_timer.timer(f'backward_{layer}', stream=cs):
+                if self._backend == 'nccl':
+                    send = [None if j == self._rank else grad[self._pl[j]:self._pr[j]] for j in range(self._size)]
+                    recv = [None if j == self._rank else
+                            (self._b_recv[j][:, :F] if F == self._width else
+                             torch.empty(self._send_shape[j], F, device=self._device)) for j in range(self._size)]
+                    ctx.comm().alltoall(send, recv, tag=64 + layer)
+                else:
+                    seq = self._seq[(layer, 1)] = self._seq.get((layer, 1), 0) + 1
+                    for i in range(1, self._size):
+                        j = (self._rank + i) % self._size
+                        lay = self._peer_layout[j]
+                        off = lay["bwd_off"][layer - 1] + lay["send_begin"][self._rank] * self._width * 4
+                        src = grad[self._pl[j]:self._pr[j]]
+                        check(lib.bns_p2p_put_rows_f32(self._p2p, j, off, self._width, src.data_ptr(), grad.stride(0), F,
+                                                       None, self._recv_shape[j], 1.0,
+                                                       self._flag(layer, True, self._rank), seq, cs.cuda_stream),
+                              "bns_p2p_put_rows_f32")
+                    recv = [None] * self._size
+                    bwd = self._slab_view(self._bwd_off[layer - 1], max(self._send_total, 1))
+                    for i in range(1, self._size):
+                        j = (self._rank - i + self._size) % self._size
+                        check(lib.bns_p2p_wait_flag(self._p2p, self._flag(layer, True, j), seq, cs.cuda_stream),
+                              "bns_p2p_wait_flag")
+                        recv[j] = bwd[self._send_begin[j]:self._send_begin[j] + self._send_shape[j], :F]
+            done.record(cs)
+        grad.record_stream(cs)
+        main.wait_event(done)
+        inner = grad[:self._num_in]
+        for i in range(1, self._size):               # the reference's order: idx = left, i = 1 .. P-1 (:111-129)
+            left = (self._rank - i + self._size) % self._size
+            ops.scatter_add_div(inner, self._selected[left], recv[left], self._ratio[left])      # K5
+        return inner
+
+    def __del__(self):
+        h, self._p2p = getattr(self, "_p2p", None), None
+        if h:
+            try:
+                lib.bns_p2p_destroy(h)
+            except Exception:
+                pass
+
+
+class _BoundaryExchange(torch.autograd.Function):
+
+    @staticmethod
+    def forward(ctx_, feat, buf: Buffer, layer: int, overlap: bool):
+        ctx_.buf, ctx_.layer = buf, layer
+        return buf._forward(layer, feat, overlap)
+
+    @staticmethod
+    def backward(ctx_, grad):
+        return ctx_.buf._backward(ctx_.layer, grad), None, None, None

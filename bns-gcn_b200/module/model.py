@@ -1,0 +1,79 @@
+"""``GCN`` / ``GraphSAGE`` layer stacks with the reference's constructor and ``forward`` signatures
+(module/model.py:7-93).  ``GAT`` and ``--norm batch`` are SURVEY.md §8(f) "next" rows."""
+from torch import nn
+
+from ..helper import context as ctx
+from .layer import GCNLayer, GraphSAGELayer
+
+
+class GNNBase(nn.Module):
+
+    def __init__(self, layer_size, activation, use_pp=False, dropout=0.5, norm='layer', n_linear=0):
+        super(GNNBase, self).__init__()
+        self.n_layers = len(layer_size) - 1
+        self.layers = nn.ModuleList()
+        self.activation = activation
+        self.use_pp = use_pp
+        self.n_linear = n_linear
+        if norm is None:
+            self.use_norm = False
+        else:
+            self.use_norm = True
+            self.norm = nn.ModuleList()
+        self.dropout = nn.Dropout(p=dropout)
+
+    def _build(self, layer_cls, layer_size, use_pp, norm, train_size):
+        for i in range(self.n_layers):
+            if i < self.n_layers - self.n_linear:
+                self.layers.append(layer_cls(layer_size[i], layer_size[i + 1], use_pp=use_pp))
+            else:
+                self.layers.append(nn.Linear(layer_size[i], layer_size[i + 1]))
+            if i < self.n_layers - 1 and self.use_norm:
+                if norm == 'layer':
+                    self.norm.append(nn.LayerNorm(layer_size[i + 1], elementwise_affine=True))
+                elif norm == 'batch':
+                    from .sync_bn import SyncBatchNorm
+                    self.norm.append(SyncBatchNorm(layer_size[i + 1], train_size))
+            use_pp = False                                   # model.py:40, 75: only layer 0 is precomputed
+
+    def _forward(self, g, feat, *norms):
+        h = feat
+        for i in range(self.n_layers):
+            h = self.dropout(h)
+            if i < self.n_layers - self.n_linear:
+                if self.training and (i > 0 or not self.use_pp):
+                    h = ctx.buffer.update(i, h, overlap=True)          # model.py:47-48, 82-83
+                h = self.layers[i](g, h, *norms)
+            else:
+                h = self.layers[i](h)
+            if i < self.n_layers - 1:
+                if self.use_norm:
+                    h = self.norm[i](h)
+                h = self.activation(h)
+        return h
+
+
+class GCN(GNNBase):
+
+    def __init__(self, layer_size, activation, use_pp, dropout=0.5, norm='layer', train_size=None, n_linear=0):
+        super(GCN, self).__init__(layer_size, activation, use_pp, dropout, norm, n_linear)
+        self._build(GCNLayer, layer_size, use_pp, norm, train_size)
+
+    def forward(self, g, feat, in_norm=None, out_norm=None):
+        return self._forward(g, feat, in_norm, out_norm)
+
+
+class GraphSAGE(GNNBase):
+
+    def __init__(self, layer_size, activation, use_pp, dropout=0.5, norm='layer', train_size=None, n_linear=0):
+        super(GraphSAGE, self).__init__(layer_size, activation, use_pp, dropout, norm, n_linear)
+        self._build(GraphSAGELayer, layer_size, use_pp, norm, train_size)
+
+    def forward(self, g, feat, in_norm=None):
+        return self._forward(g, feat, in_norm)
+
+
+class GAT(GNNBase):
+
+    def __init__(self, *a, **k):
+        raise NotImplementedError("GAT (dgl.nn.GATConv, module/model.py:96-132) is a SURVEY.md §8(f) 'next' row")

@@ -1,0 +1,371 @@
+"""The training driver: same function names and call order as the reference's train.py, on the DGL-free
+partition contract and the CUDA path.
+
+``run(graph, node_dict, gpb, args)`` is the reference entry point (train.py:300-456).  It is split into
+``setup(...) -> TrainState`` and ``train_epoch(state, epoch)`` so that bench.py / tests can time or inspect single
+epochs; ``run`` is the loop around them with the reference's log line.
+"""
+from __future__ import annotations
+
+import dataclasses
+import time
+from typing import List, Optional
+
+import numpy as np
+import torch
+import torch.nn.functional as F
+
+from . import ops
+from .data.partition import NID, LocalGraph
+from .graph import FullGraphHandle, PartitionGraph
+from .helper import context as ctx
+from .helper.timer.timer import comm_timer
+from .helper.utils import (TransferTag, data_transfer, get_boundary, get_layer_size, merge_feature, minus_one_tensor,
+                           nonzero_idx, print_memory)
+from .module.model import GAT, GCN, GraphSAGE
+
+
+def _rank_size():
+    c = ctx.comm()
+    return c.rank, c.size
+
+
+def calc_acc(logits, labels):
+    """train.py:13-19 (micro-F1 for multi-label without sklearn's host round trip)."""
+    if labels.dim() == 1:
+        return (logits.argmax(dim=1) == labels).sum().item() / labels.shape[0]
+    pred = logits > 0
+    tp = (pred & (labels > 0)).sum().item()
+    fp = (pred & ~(labels > 0)).sum().item()
+    fn = (~pred & (labels > 0)).sum().item()
+    return 2 * tp / max(2 * tp + fp + fn, 1)
+
+
+def move_to_cuda(graph, in_graph, out_graph, node_dict, boundary, device=None):
+    """train.py:64-74.  ``in_graph`` / ``out_graph`` are already device-resident ``DeviceGraph`` s."""
+    rank, size = _rank_size()
+    dev = torch.device(device if device is not None else torch.cuda.current_device())
+    for i in range(size):
+        if i != rank:
+            boundary[i] = boundary[i].to(dev)
+    for key in node_dict.keys():
+        node_dict[key] = node_dict[key].to(dev)
+    return graph, in_graph, out_graph, node_dict, boundary
+
+
+def get_in_out_graph(graph: LocalGraph, node_dict, device=None, chunk_nnz: int = 0):
+    """train.py:77-87.  ``in_graph``: edges between inner nodes; ``out_graph``: edges halo -> inner (stored with
+    halo-local column ids ``src - n_in``).  Both become static CSR matrices in HBM, int32 ids (train.py:71-73)."""
+    dev = torch.device(device if device is not None else torch.cuda.current_device())
+    n_in = graph.n_in
+    indptr, idx = graph.indptr.to(dev), graph.indices.to(dev)
+    inner = idx < n_in
+    rows = torch.repeat_interleave(torch.arange(n_in, device=dev), indptr[1:] - indptr[:-1])
+
+    def csr_of(mask, shift):
+        cnt = torch.bincount(rows[mask], minlength=n_in)
+        ip = torch.zeros(n_in + 1, dtype=torch.int64, device=dev)
+        ip[1:] = torch.cumsum(cnt, 0)
+        return ip, (idx[mask] - shift).to(torch.int32)
+
+    ip_in, ix_in = csr_of(inner, 0)
+    in_graph = ops.DeviceGraph.from_csr(ip_in, ix_in, n_in, chunk_nnz)
+    out_graph = None
+    if graph.n_halo > 0:
+        ip_out, ix_out = csr_of(~inner, n_in)
+        out_graph = ops.DeviceGraph.from_csr(ip_out, ix_out, graph.n_halo, chunk_nnz)
+    return in_graph, out_graph
+
+
+def get_pos(node_dict, gpb):
+    """train.py:90-104: ``pos[i][owner-local id] = my local id`` of that node, -1 if it is not one of my halo nodes."""
+    rank, size = _rank_size()
+    dev = node_dict['part_id'].device
+    pos = []
+    for i in range(size):
+        if i == rank:
+            pos.append(None)
+            continue
+        start, end = int(gpb.ranges[i]), int(gpb.ranges[i + 1])
+        p = minus_one_tensor(end - start, dev)
+        in_idx = nonzero_idx(node_dict['part_id'] == i)
+        p[node_dict[NID][in_idx] - start] = in_idx
+        pos.append(p)
+    return pos
+
+
+def get_send_size(boundary, prob):
+    """train.py:107-119.  An empty boundary makes the reference divide by zero; here it sends nothing at ratio 1."""
+    rank, size = _rank_size()
+    res, ratio = [], []
+    for i, b in enumerate(boundary):
+        if i == rank:
+            res.append(0)
+            ratio.append(0)
+            continue
+        s = int(prob * b.shape[0])
+        res.append(s)
+        ratio.append(s / b.shape[0] if b.shape[0] else 1.0)
+    return res, ratio
+
+
+def get_recv_size(node_dict, prob):
+    """train.py:122-131."""
+    rank, size = _rank_size()
+    counts = torch.bincount(node_dict['part_id'], minlength=size).tolist()
+    return [0 if i == rank else int(prob * counts[i]) for i in range(size)]
+
+
+def _halo_counts(node_dict):
+    rank, size = _rank_size()
+    counts = torch.bincount(node_dict['part_id'], minlength=size).tolist()
+    return [None if i == rank else counts[i] for i in range(size)]
+
+
+def collect_out_degree(node_dict, boundary):
+    """train.py:148-167: out-degrees of my halo nodes, fetched from their owners -> ``[inner | halo]`` vector."""
+    rank, size = _rank_size()
+    out_deg = node_dict['out_deg']
+    if size == 1:
+        return out_deg
+    send_info = [None if i == rank else out_deg[b] for i, b in enumerate(boundary)]
+    recv_shape = [None if c is None else torch.Size([c]) for c in _halo_counts(node_dict)]
+    recv_out_deg = data_transfer(send_info, recv_shape, tag=TransferTag.DEG, dtype=torch.long)
+    return merge_feature(out_deg, recv_out_deg)
+
+
+def select_node(boundary, send_size, sampler: Optional[ops.BoundarySampler] = None, seed: int = 0, epoch: int = 0):
+    """train.py:225-236 (K6).  The reference draws ``np.random.choice(b, k, replace=False)`` per peer on the host
+    and copies the ids to the GPU; here one Philox kernel draws all peers' samples on the device."""
+    if sampler is None:
+        dev = next(b for b in boundary if b is not None).device
+        sampler = ops.BoundarySampler(boundary, send_size, dev)
+    return sampler.sample(seed, epoch)[1]
+
+
+def construct_graph(part: PartitionGraph, graph, pos, one_hops):
+    """train.py:256-281 (K7).  Instead of a new heterograph: refresh the slot map of the static graph.
+    U-numbering = ``[inner | sampled halo of peer 0 | peer 1 ...]`` in the order of the received ``one_hops``."""
+    rank, size = _rank_size()
+    tot = part.n_in
+    if part.n_halo:
+        ops.fill_i32(part.slot, -1)
+    for i in range(size):
+        if i == rank:
+            continue
+        u = one_hops[i]
+        if u is None or u.shape[0] == 0:
+            continue
+        ops.halo_slot_update(pos[i], u, part.n_in, tot - part.n_in, part.slot)
+        tot += u.shape[0]
+    part.n_u = tot
+    return part
+
+
+def order_graph(part, graph, gpb, node_dict, pos):
+    """train.py:134-145: the full-halo graph (every halo node present, sorted by owner-local id)."""
+    rank, size = _rank_size()
+    one_hops = []
+    for i in range(size):
+        if i == rank:
+            one_hops.append(None)
+            continue
+        nodes = node_dict[NID][node_dict['part_id'] == i] - int(gpb.ranges[i])
+        one_hops.append(torch.sort(nodes)[0])
+    return construct_graph(part, graph, pos, one_hops)
+
+
+def construct_out_norm(num, norm, pos, one_hops):
+    """train.py:245-253 rebuilds a U-ordered ``out_norm`` per epoch; the slot map makes that unnecessary --
+    ``GCNLayer`` takes the static ``[inner | halo]`` vector, so this returns it unchanged."""
+    return norm
+
+
+def precompute(part: PartitionGraph, graph, node_dict, boundary, model, gpb, pos, out_deg_all=None):
+    """train.py:170-211: the one-time layer-0 aggregation over ALL boundary nodes (sampling rate 1)."""
+    rank, size = _rank_size()
+    g = order_graph(part, graph, gpb, node_dict, pos)
+    feat = node_dict['feat']
+    if size > 1:
+        send_info = [None if i == rank else feat[b] for i, b in enumerate(boundary)]
+        recv_shape = [None if c is None else torch.Size([c, feat.shape[1]]) for c in _halo_counts(node_dict)]
+        recv_feat = data_transfer(send_info, recv_shape, tag=TransferTag.FEAT, dtype=torch.float)
+    else:
+        recv_feat = [None]
+    h_u = merge_feature(feat, recv_feat)
+    n_feat = feat.shape[1]
+    pad = (-n_feat) % 4                       # 16-byte vector path of the SpMM (602 -> 604 columns)
+    if pad:
+        h_u = F.pad(h_u, (0, pad))
+    from .graph import PartitionAggregate
+    with torch.no_grad():
+        if model == 'gcn':
+            in_norm = torch.sqrt(node_dict['in_deg'].float())
+            out_norm = torch.sqrt(out_deg_all.float())
+            cs = 1.0 / out_norm
+            h = PartitionAggregate.apply(h_u, g, 1.0 / in_norm, cs[:g.n_in].contiguous(), cs[g.n_in:].contiguous(), None)
+            return h[:, :n_feat].contiguous()
+        elif model == 'graphsage':
+            # fn.mean divides by the number of messages = the full in-degree (every in-edge is present here)
+            mean = PartitionAggregate.apply(h_u, g, 1.0 / node_dict['in_deg'].float(), None, None, None)
+            return torch.cat([feat, mean[:, :n_feat]], dim=1)
+        elif model == 'gat':
+            return h_u[:, :n_feat]
+        raise Exception
+
+
+def create_model(layer_size, args):
+    """train.py:214-222."""
+    if args.model == 'gcn':
+        return GCN(layer_size, F.relu, norm=args.norm, use_pp=args.use_pp, dropout=args.dropout,
+                   train_size=args.n_train, n_linear=args.n_linear)
+    elif args.model == 'graphsage':
+        return GraphSAGE(layer_size, F.relu, norm=args.norm, use_pp=args.use_pp, dropout=args.dropout,
+                         train_size=args.n_train, n_linear=args.n_linear)
+    elif args.model == 'gat':
+        return GAT(layer_size, F.relu, use_pp=True, heads=args.heads, norm=args.norm, dropout=args.dropout)
+    raise NotImplementedError(args.model)
+
+
+def reduce_hook(param, name, n_train):
+    """train.py:239-242."""
+    def fn(grad):
+        ctx.reducer.reduce(param, name, grad, n_train)
+    return fn
+
+
+@dataclasses.dataclass
+class TrainState:
+    args: object
+    part: PartitionGraph
+    model: torch.nn.Module
+    optimizer: torch.optim.Optimizer
+    loss_fcn: torch.nn.Module
+    feat: torch.Tensor
+    labels: torch.Tensor
+    train_mask: torch.Tensor
+    in_norm: torch.Tensor
+    out_norm: Optional[torch.Tensor]
+    boundary: list
+    pos: list
+    send_size: list
+    recv_size: list
+    ratio: list
+    sampler: Optional[ops.BoundarySampler]
+    part_train: int
+    selected: Optional[list] = None
+    one_hops: Optional[list] = None
+    last_logits: Optional[torch.Tensor] = None
+
+
+def setup(graph: LocalGraph, node_dict, gpb, args, device=None) -> TrainState:
+    """Everything ``run`` does before its epoch loop (train.py:300-383)."""
+    rank, size = _rank_size()
+    dev = torch.device(device if device is not None else torch.cuda.current_device())
+    node_dict = dict(node_dict)
+    in_graph, out_graph = get_in_out_graph(graph, node_dict, dev, getattr(args, 'chunk_nnz', 0))
+    part = PartitionGraph(graph.n_in, graph.n_halo, in_graph, out_graph, dev)
+    boundary = get_boundary({k: v.to(dev) for k, v in node_dict.items() if k in ('part_id', NID)}, gpb)
+    layer_size = get_layer_size(args.n_feat, args.n_hidden, args.n_class, args.n_layers)
+    _, _, _, node_dict, boundary = move_to_cuda(graph, in_graph, out_graph, node_dict, boundary, dev)
+    print(f'Process {rank} has {graph.num_nodes()} nodes, {graph.num_edges()} edges '
+          f'{in_graph.n_rows} inner nodes, and {in_graph.nnz} inner edges.')
+    seed_lock = getattr(ctx.comm(), 'fabric', None)
+    lock = seed_lock._lock if seed_lock is not None else None
+    if lock is not None:
+        lock.acquire()
+    try:
+        torch.manual_seed(args.seed)                                        # train.py:331-333
+        model = create_model(layer_size, args)
+    finally:
+        if lock is not None:
+            lock.release()
+    model.to(dev)
+    ctx.reducer.init(model)
+    for name, param in model.named_parameters():
+        param.register_hook(reduce_hook(param, name, args.n_train))         # train.py:337-338
+    labels = node_dict['label']
+    part_train = int(node_dict['train_mask'].int().sum().item())
+    pos = get_pos(node_dict, gpb)
+    send_size, ratio = get_send_size(boundary, args.sampling_rate)
+    recv_size = get_recv_size(node_dict, args.sampling_rate)
+    ctx.buffer.init_buffer(in_graph.n_rows, ratio, send_size, recv_size,
+                           layer_size[:args.n_layers - args.n_linear], use_pp=args.use_pp, backend=args.backend,
+                           device=dev)
+    out_deg_all = collect_out_degree(node_dict, boundary)                   # train.py:350
+    if args.use_pp:
+        node_dict['feat'] = precompute(part, graph, node_dict, boundary, args.model, gpb, pos, out_deg_all)
+    if getattr(args, 'multilabel', False) or args.dataset == 'yelp':
+        loss_fcn = torch.nn.BCEWithLogitsLoss(reduction='sum')              # train.py:358-361
+    else:
+        loss_fcn = torch.nn.CrossEntropyLoss(reduction='sum')
+    optimizer = torch.optim.Adam(model.parameters(), lr=args.lr, weight_decay=args.weight_decay)
+    out_norm = None
+    if args.model == 'gcn':
+        in_norm = torch.sqrt(node_dict['in_deg'].float())                   # train.py:377-378
+        out_norm = torch.sqrt(out_deg_all.float())
+    else:
+        in_norm = node_dict['in_deg']                                       # train.py:380
+    sampler = ops.BoundarySampler(boundary, send_size, dev) if size > 1 else None
+    return TrainState(args, part, model, optimizer, loss_fcn, node_dict['feat'], labels, node_dict['train_mask'],
+                      in_norm, out_norm, boundary, pos, send_size, recv_size, ratio, sampler, part_train)
+
+
+def train_epoch(st: TrainState, epoch: int, selected: Optional[list] = None) -> torch.Tensor:
+    """One pass of the epoch body (train.py:388-413).  Returns the local sum-reduced loss (device scalar).
+    ``selected`` injects the sampled sets (parity runs); by default they come from the Philox sampler."""
+    rank, size = _rank_size()
+    args = st.args
+    if size > 1:
+        if selected is None:
+            selected = st.sampler.sample(getattr(args, 'sampler_seed', 0), epoch)[1]            # K6
+        recv_shape = [torch.Size([s]) for s in st.recv_size]
+        one_hops = data_transfer(selected, recv_shape, tag=TransferTag.NODE, dtype=torch.long)  # C3
+        ctx.buffer.set_selected(selected)
+    else:
+        selected, one_hops = [None], [None]
+    st.selected, st.one_hops = selected, one_hops
+    g = construct_graph(st.part, None, st.pos, one_hops)                                        # K7
+    st.model.train()
+    if args.model == 'gcn':
+        logits = st.model(g, st.feat, st.in_norm, st.out_norm)
+    elif args.model == 'graphsage':
+        logits = st.model(g, st.feat, st.in_norm)
+    else:
+        raise NotImplementedError
+    loss = st.loss_fcn(logits[st.train_mask], st.labels[st.train_mask])
+    st.optimizer.zero_grad(set_to_none=True)
+    loss.backward()
+    ctx.reducer.synchronize()
+    st.optimizer.step()
+    st.last_logits = logits
+    return loss.detach()
+
+
+def run(graph, node_dict, gpb, args, device=None):
+    """train.py:300-456 without the evaluation / checkpoint branch (not on the throughput path, README.md:110)."""
+    rank, size = _rank_size()
+    st = setup(graph, node_dict, gpb, args, device)
+    dev = st.feat.device
+    train_dur, comm_dur, reduce_dur = [], [], []
+    torch.cuda.reset_peak_memory_stats(dev)
+    print(f'Process {rank} start training')
+    loss = None
+    for epoch in range(args.n_epochs):
+        torch.cuda.synchronize(dev)
+        t0 = time.time()
+        loss = train_epoch(st, epoch)
+        torch.cuda.synchronize(dev)
+        if epoch >= 5:                                                      # train.py:415-418
+            train_dur.append(time.time() - t0)
+            comm_dur.append(comm_timer.tot_time())
+            reduce_dur.append(ctx.reducer.last_reduce_seconds())
+        if (epoch + 1) % args.log_every == 0:
+            print("Process {:03d} | Epoch {:05d} | Time(s) {:.4f} | Comm(s) {:.4f} | Reduce(s) {:.4f} | Loss {:.4f}".format(
+                rank, epoch, np.mean(train_dur) if train_dur else float('nan'),
+                np.mean(comm_dur) if comm_dur else float('nan'),
+                np.mean(reduce_dur) if reduce_dur else float('nan'), loss.item() / max(st.part_train, 1)))
+        comm_timer.clear()
+    print_memory("memory stats")
+    return st, {"time": train_dur, "comm": comm_dur, "reduce": reduce_dur,
+                "loss": None if loss is None else loss.item()}

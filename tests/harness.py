@@ -1,0 +1,140 @@
+"""Parity harness shared by ``tests/``, ``__graft_entry__.smoke()`` and ``bench.py``: run the same seeded
+configuration through the CUDA path (P in-process ranks on one GPU) and through the CPU oracle, and compare.
+TEST INFRASTRUCTURE: lives under tests/ because it imports ``oracle``; nothing under bns-gcn_b200/ does."""
+from __future__ import annotations
+
+import argparse
+from typing import Dict, List, Optional
+
+import numpy as np
+import torch
+
+
+def make_args(**kw) -> argparse.Namespace:
+    d = dict(dataset="tiny", model="graphsage", n_layers=3, n_hidden=16, sampling_rate=1.0, use_pp=True, dropout=0.0,
+             norm="layer", lr=1e-2, weight_decay=0.0, seed=0, n_linear=0, backend="nccl", sampler_seed=0,
+             n_epochs=3, log_every=10, heads=1, n_partitions=1, inductive=False, partition_method="random",
+             eval=False, chunk_nnz=0)
+    d.update(kw)
+    return argparse.Namespace(**d)
+
+
+def _relerr(a: torch.Tensor, b: torch.Tensor) -> float:
+    a, b = a.detach().double().cpu(), b.detach().double().cpu()
+    return ((a - b).norm() / b.norm().clamp(min=1e-30)).item()
+
+
+def run_product(parts, args, device, n_epochs, selected_per_epoch=None, capture=True):
+    """Train ``n_epochs`` on the CUDA path with one in-process rank per partition.  Returns per-rank dicts."""
+    from bns_gcn_b200 import train
+    from bns_gcn_b200.helper.comm import run_threads
+
+    def fn(comm, r):
+        p = parts[r]
+        a = argparse.Namespace(**vars(args))
+        a.n_feat, a.n_class, a.n_train = p.meta["n_feat"], p.meta["n_class"], p.meta["n_train"]
+        st = train.setup(p.graph, p.node_dict, p.gpb, a, device)
+        outs: Dict[str, torch.Tensor] = {}
+        hooks = []
+        if capture:
+            for i, layer in enumerate(st.model.layers):
+                hooks.append(layer.register_forward_hook(
+                    lambda m, inp, out, i=i: outs.__setitem__(f"layer{i}", out.detach().clone())))
+        losses, sel_log, hops_log = [], [], []
+        for e in range(n_epochs):
+            inj = None
+            if selected_per_epoch is not None:
+                inj = [None if s is None else s.to(device) for s in selected_per_epoch[e][r]]
+            loss = train.train_epoch(st, e, selected=inj)
+            losses.append(loss.item())
+            sel_log.append([None if s is None else s.cpu().clone() for s in st.selected])
+            hops_log.append([None if s is None else s.cpu().clone() for s in st.one_hops])
+        torch.cuda.synchronize()
+        for h in hooks:
+            h.remove()
+        return {"loss": losses, "selected": sel_log, "one_hops": hops_log,
+                "layers": {k: v.cpu() for k, v in outs.items()},
+                "logits": st.last_logits.detach().cpu(),
+                "grads": [p_.grad.detach().cpu().clone() for p_ in st.model.parameters()],
+                "params": [p_.detach().cpu().clone() for p_ in st.model.parameters()],
+                "boundary": [None if b is None else b.cpu() for b in st.boundary],
+                "send_size": st.send_size, "feat0": st.feat.detach().cpu()}
+
+    return run_threads(len(parts), fn, device=device)
+
+
+def run_oracle(parts, args, n_epochs, selected_per_epoch):
+    """The same run on the CPU oracle (P threads, injected index sets)."""
+    from oracle import bns_oracle as O
+
+    def fn(comm, r):
+        p = parts[r]
+        rk = O.OracleRank(O.RankInput.from_partition(p), comm, model=args.model, n_layers=args.n_layers,
+                          n_hidden=args.n_hidden, sampling_rate=args.sampling_rate, use_pp=args.use_pp,
+                          dropout=args.dropout, norm=args.norm, lr=args.lr, weight_decay=args.weight_decay,
+                          seed=args.seed, n_linear=args.n_linear, multilabel=(args.dataset == "yelp"))
+        losses = []
+        for e in range(n_epochs):
+            sel = None if selected_per_epoch is None else selected_per_epoch[e][r]
+            losses.append(rk.epoch(selected=sel, trace=True))
+        return {"loss": losses, "layers": {k: v for k, v in rk.trace.items() if k.startswith("layer")},
+                "logits": rk.trace["logits"], "grads": [q.grad.detach().clone() for q in rk.net.parameters()],
+                "params": [q.detach().clone() for q in rk.net.parameters()],
+                "boundary": rk.boundary, "send_size": rk.send_size, "one_hops": rk.one_hops, "feat0": rk.feat}
+
+    return O.run_threads(len(parts), fn)
+
+
+def run_parity_case(shape="tiny", n_parts=2, model="graphsage", sampling_rate=0.5, n_epochs=2, device="cuda:0",
+                    backend="nccl", n_layers=3, n_hidden=16, partition_method="random", graph_seed=0,
+                    sampler_seed=0, chunk_nnz=0) -> dict:
+    """Product vs oracle on one seeded configuration.  Returns the worst relative error over layer outputs, logits,
+    reduced gradients and updated weights, plus the exactness checks on index sets."""
+    from bns_gcn_b200.data import make_graph, partition_graph
+    from oracle import philox
+
+    fg = make_graph(shape, seed=graph_seed)
+    parts = partition_graph(fg, n_parts, partition_method, seed=graph_seed)
+    args = make_args(dataset=shape, model=model, sampling_rate=sampling_rate, backend=backend, n_layers=n_layers,
+                     n_hidden=n_hidden, n_partitions=n_parts, sampler_seed=sampler_seed, chunk_nnz=chunk_nnz)
+    prod = run_product(parts, args, device, n_epochs)
+    selected = [[prod[r]["selected"][e] for r in range(n_parts)] for e in range(n_epochs)]
+    orc = run_oracle(parts, args, n_epochs, selected if n_parts > 1 else None)
+    worst, detail = 0.0, {}
+    for r in range(n_parts):
+        for k in list(prod[r]["layers"].keys()) + ["logits", "feat0"]:
+            a = prod[r]["layers"][k] if k.startswith("layer") else prod[r][k]
+            b = orc[r]["layers"][k] if k.startswith("layer") else orc[r][k]
+            e = _relerr(a, b)
+            detail[f"r{r}/{k}"] = e
+            worst = max(worst, e)
+        for i, (a, b) in enumerate(zip(prod[r]["grads"], orc[r]["grads"])):
+            e = _relerr(a, b)
+            detail[f"r{r}/grad{i}"] = e
+            worst = max(worst, e)
+        for i, (a, b) in enumerate(zip(prod[r]["params"], orc[r]["params"])):
+            e = _relerr(a, b)
+            detail[f"r{r}/param{i}"] = e
+            worst = max(worst, e)
+    # exactness of the integer side
+    index_ok = True
+    for r in range(n_parts):
+        for j in range(n_parts):
+            if j == r:
+                continue
+            index_ok &= torch.equal(prod[r]["boundary"][j], orc[r]["boundary"][j])            # boundary sets
+            index_ok &= prod[r]["send_size"][j] == orc[r]["send_size"][j]
+            for e in range(n_epochs):
+                # what j received from r is exactly what r selected for j, in order
+                index_ok &= torch.equal(prod[j]["one_hops"][e][r], prod[r]["selected"][e][j])
+        # Philox replay of this rank's draws
+        peers = [j for j in range(n_parts) if j != r]
+        for e in range(n_epochs if n_parts > 1 else 0):
+            ref = philox.sample_boundary([prod[r]["boundary"][j].numpy() for j in peers],
+                                         [prod[r]["send_size"][j] for j in peers], sampler_seed, e)
+            for i, j in enumerate(peers):
+                index_ok &= torch.equal(prod[r]["selected"][e][j], torch.from_numpy(ref[i]))
+    loss_p = [sum(prod[r]["loss"][e] for r in range(n_parts)) for e in range(n_epochs)]
+    loss_o = [sum(orc[r]["loss"][e] for r in range(n_parts)) for e in range(n_epochs)]
+    return {"max_rel_err": worst, "detail": detail, "index_sets_equal": bool(index_ok), "loss": loss_p,
+            "loss_oracle": loss_o}
