@@ -73,6 +73,8 @@ class Buffer(object):
         if use_pp is False:
             raise NotImplementedError            # helper/feature_buffer.py:36-37
         c = ctx.comm()
+        # captured now: backward runs on autograd's device thread, where thread-local lookups would miss
+        self._comm, self._timer = c, comm_timer._get()
         self._rank, self._size = c.rank, c.size
         self._num_in = num_in
         self._n_layers = len(layer_size)
@@ -182,7 +184,7 @@ class Buffer(object):
         start.record(main)
         cs.wait_event(start)
         with torch.cuda.stream(cs):
-            with comm_timer.timer(f'forward_{layer}', stream=cs):
+            with self._timer.timer(f'forward_{layer}', stream=cs):
                 if self._backend == 'nccl':
                     send = [None] * self._size
                     recv = [None] * self._size
@@ -193,7 +195,7 @@ class Buffer(object):
                             torch.empty(self._send_shape[j], F, device=self._device)
                         ops.gather_div(feat, self._selected[j], self._ratio[j], out=send[j])      # K3
                         recv[j] = h_u[self._pl[j]:self._pr[j]]
-                    ctx.comm().alltoall(send, recv, tag=16 + layer)                               # C1/C2
+                    self._comm.alltoall(send, recv, tag=16 + layer)                               # C1/C2
                 else:
                     seq = self._seq[(layer, 0)] = self._seq.get((layer, 0), 0) + 1
                     for i in range(1, self._size):
@@ -226,13 +228,13 @@ class Buffer(object):
         start.record(main)
         cs.wait_event(start)
         with torch.cuda.stream(cs):
-            with comm_timer.timer(f'backward_{layer}', stream=cs):
+            with self._timer.timer(f'backward_{layer}', stream=cs):
                 if self._backend == 'nccl':
                     send = [None if j == self._rank else grad[self._pl[j]:self._pr[j]] for j in range(self._size)]
                     recv = [None if j == self._rank else
                             (self._b_recv[j][:, :F] if F == self._width else
                              torch.empty(self._send_shape[j], F, device=self._device)) for j in range(self._size)]
-                    ctx.comm().alltoall(send, recv, tag=64 + layer)
+                    self._comm.alltoall(send, recv, tag=64 + layer)
                 else:
                     seq = self._seq[(layer, 1)] = self._seq.get((layer, 1), 0) + 1
                     for i in range(1, self._size):

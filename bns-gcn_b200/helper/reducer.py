@@ -34,6 +34,7 @@ class Reducer(object):
             off += p.numel()
         if dev.type == 'cuda':
             self._stream = torch.cuda.Stream(device=dev)
+        self._comm = ctx.comm()
 
     def reduce(self, param, name, data, n_train):
         off, n = self._slices[name]
@@ -43,7 +44,7 @@ class Reducer(object):
     def synchronize(self):
         if not self._pending:
             return
-        c = ctx.comm()
+        c = self._comm
         if c.size > 1:
             if self._stream is not None:
                 cur = torch.cuda.current_stream(self._flat.device)

@@ -228,9 +228,11 @@ def create_model(layer_size, args):
 
 
 def reduce_hook(param, name, n_train):
-    """train.py:239-242."""
+    """train.py:239-242.  The rank's reducer is bound here: the hook fires on autograd's device thread."""
+    red = ctx.reducer._get()
+
     def fn(grad):
-        ctx.reducer.reduce(param, name, grad, n_train)
+        red.reduce(param, name, grad, n_train)
     return fn
 
 
