@@ -46,6 +46,7 @@ class ThreadFabric:
         self._bar = threading.Barrier(size)
         self._slots: List = [None] * size
         self.shared: Dict = {}
+        self.failed = False          # set when any rank raised: blocked peers give up instead of hanging
 
     def box(self, src: int, dst: int, tag: int) -> "queue.Queue":
         with self._lock:
@@ -63,13 +64,23 @@ class ThreadComm:
 
     def _put(self, t: torch.Tensor, dst: int, tag: int):
         ev = None
+        t = t.detach().clone()      # the sender may reuse its buffer as soon as this returns (NCCL semantics)
         if t.is_cuda:
             ev = torch.cuda.Event()
             ev.record(torch.cuda.current_stream(t.device))
         self.fabric.box(self.rank, dst, tag).put((t, ev))
 
     def _get(self, out: torch.Tensor, src: int, tag: int):
-        t, ev = self.fabric.box(src, self.rank, tag).get(timeout=600)
+        box, waited = self.fabric.box(src, self.rank, tag), 0.0
+        while True:
+            try:
+                t, ev = box.get(timeout=0.5)
+                break
+            except queue.Empty:
+                waited += 0.5
+                if self.fabric.failed or waited > 120:
+                    raise RuntimeError(f"rank {self.rank}: no message from rank {src} (tag {tag}); "
+                                       f"{'a peer failed' if self.fabric.failed else 'timeout'}")
         if ev is not None:
             torch.cuda.current_stream(out.device).wait_event(ev)
         out.copy_(t.view_as(out))
@@ -182,15 +193,19 @@ def run_threads(n_ranks: int, fn, *args, device: Optional[str] = None):
         try:
             c = fabric.comm(r)
             ctx.set_comm(c)
-            if device is not None and str(device).startswith("cuda"):
-                torch.cuda.set_device(device)
-                with torch.cuda.stream(torch.cuda.Stream(device)):
+            # autograd normally runs every CUDA backward of the process on ONE device thread; ranks that wait
+            # for each other's messages inside backward would starve each other there -> run it on this thread
+            with torch.autograd.set_multithreading_enabled(False):
+                if device is not None and str(device).startswith("cuda"):
+                    torch.cuda.set_device(device)
+                    with torch.cuda.stream(torch.cuda.Stream(device)):
+                        out[r] = fn(c, r, *args)
+                        torch.cuda.current_stream().synchronize()
+                else:
                     out[r] = fn(c, r, *args)
-                    torch.cuda.current_stream().synchronize()
-            else:
-                out[r] = fn(c, r, *args)
         except BaseException as e:      # noqa: BLE001
             err[r] = e
+            fabric.failed = True
             fabric._bar.abort()
         finally:
             ctx.reset()
