@@ -318,6 +318,7 @@ def train_epoch(st: TrainState, epoch: int, selected: Optional[list] = None) -> 
     ``selected`` injects the sampled sets (parity runs); by default they come from the Philox sampler."""
     rank, size = _rank_size()
     args = st.args
+    comm_timer.clear()                      # train.py:425 (interval names are per epoch)
     if size > 1:
         if selected is None:
             selected = st.sampler.sample(getattr(args, 'sampler_seed', 0), epoch)[1]            # K6
@@ -367,7 +368,6 @@ def run(graph, node_dict, gpb, args, device=None):
                 rank, epoch, np.mean(train_dur) if train_dur else float('nan'),
                 np.mean(comm_dur) if comm_dur else float('nan'),
                 np.mean(reduce_dur) if reduce_dur else float('nan'), loss.item() / max(st.part_train, 1)))
-        comm_timer.clear()
     print_memory("memory stats")
     return st, {"time": train_dur, "comm": comm_dur, "reduce": reduce_dur,
                 "loss": None if loss is None else loss.item()}
