@@ -870,6 +870,7 @@ struct bns_p2p {
     unsigned long long *flags = nullptr;  // this rank's flag block
     char **peer_slab = nullptr;           // [world] mapped pointers (self = own)
     unsigned long long **peer_flags = nullptr;
+    size_t *peer_slab_bytes = nullptr;    // [world] size of each peer's slab (bounds checks on puts)
     bool *imported = nullptr;             // opened with cudaIpcOpenMemHandle (must be closed)
 };
 
@@ -919,9 +920,23 @@ __global__ void __launch_bounds__(kThreads) p2p_put_rows_kernel(const float *__r
     }
 }
 
-__global__ void p2p_wait_kernel(const unsigned long long *flag, unsigned long long value) {
+__device__ __forceinline__ unsigned long long global_ns() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+    return t;
+}
+
+// Bounded spin: a peer that never signals (it failed, or the schedule is wrong) must not hang the GPU.
+__global__ void p2p_wait_kernel(const unsigned long long *flag, unsigned long long value, unsigned long long timeout_ns) {
     if (threadIdx.x == 0) {
-        while (ld_acquire_sys(flag) < value) __nanosleep(64);
+        const unsigned long long t0 = global_ns();
+        while (ld_acquire_sys(flag) < value) {
+            __nanosleep(64);
+            if (global_ns() - t0 > timeout_ns) {
+                printf("bns_p2p_wait_flag: timed out waiting for flag value %llu (have %llu)\n", value, ld_acquire_sys(flag));
+                __trap();
+            }
+        }
     }
 }
 
@@ -937,6 +952,7 @@ extern "C" int bns_p2p_create(bns_p2p_t **out, int32_t rank, int32_t world, size
     p->slab_bytes = slab_bytes ? align256(slab_bytes) : 256;
     p->peer_slab = new char *[world]();
     p->peer_flags = new unsigned long long *[world]();
+    p->peer_slab_bytes = new size_t[world]();
     p->imported = new bool[world]();
     // flags block: n_flags u64 + one u32 ticket per peer (for the put kernel), zero-initialised
     const size_t flag_bytes = align256((size_t)n_flags * 8) + align256((size_t)world * 4);
@@ -950,6 +966,7 @@ extern "C" int bns_p2p_create(bns_p2p_t **out, int32_t rank, int32_t world, size
     cudaDeviceSynchronize();
     p->peer_slab[rank] = p->slab;
     p->peer_flags[rank] = p->flags;
+    p->peer_slab_bytes[rank] = p->slab_bytes;
     *out = p;
     return BNS_OK;
 }
@@ -963,15 +980,16 @@ extern "C" int bns_p2p_destroy(bns_p2p_t *p) {
         }
     }
     cudaFree(p->slab); cudaFree(p->flags);
-    delete[] p->peer_slab; delete[] p->peer_flags; delete[] p->imported;
+    delete[] p->peer_slab; delete[] p->peer_flags; delete[] p->peer_slab_bytes; delete[] p->imported;
     delete p;
     return BNS_OK;
 }
 
-extern "C" int bns_p2p_local(const bns_p2p_t *p, void **slab, void **flags) {
+extern "C" int bns_p2p_local(const bns_p2p_t *p, void **slab, void **flags, size_t *slab_bytes) {
     BNS_REQUIRE(p, "bns_p2p_local: NULL handle");
     if (slab) *slab = p->slab;
     if (flags) *flags = p->flags;
+    if (slab_bytes) *slab_bytes = p->slab_bytes;
     return BNS_OK;
 }
 
@@ -986,7 +1004,7 @@ extern "C" int bns_p2p_export(const bns_p2p_t *p, void *handle_out) {
     return BNS_OK;
 }
 
-extern "C" int bns_p2p_import(bns_p2p_t *p, int32_t peer, const void *handle) {
+extern "C" int bns_p2p_import(bns_p2p_t *p, int32_t peer, const void *handle, size_t peer_slab_bytes) {
     BNS_REQUIRE(p && handle, "bns_p2p_import: NULL argument");
     BNS_REQUIRE(peer >= 0 && peer < p->world && peer != p->rank, "bns_p2p_import: bad peer %d", peer);
     cudaIpcMemHandle_t h;
@@ -997,15 +1015,17 @@ extern "C" int bns_p2p_import(bns_p2p_t *p, int32_t peer, const void *handle) {
     memcpy(&h, reinterpret_cast<const char *>(handle) + BNS_P2P_HANDLE_BYTES, sizeof(h));
     BNS_CUDA(cudaIpcOpenMemHandle(&ptr, h, cudaIpcMemLazyEnablePeerAccess));
     p->peer_flags[peer] = reinterpret_cast<unsigned long long *>(ptr);
+    p->peer_slab_bytes[peer] = peer_slab_bytes;
     p->imported[peer] = true;
     return BNS_OK;
 }
 
-extern "C" int bns_p2p_set_peer(bns_p2p_t *p, int32_t peer, void *slab, void *flags) {
+extern "C" int bns_p2p_set_peer(bns_p2p_t *p, int32_t peer, void *slab, void *flags, size_t peer_slab_bytes) {
     BNS_REQUIRE(p && slab && flags, "bns_p2p_set_peer: NULL argument");
     BNS_REQUIRE(peer >= 0 && peer < p->world && peer != p->rank, "bns_p2p_set_peer: bad peer %d", peer);
     p->peer_slab[peer] = reinterpret_cast<char *>(slab);
     p->peer_flags[peer] = reinterpret_cast<unsigned long long *>(flags);
+    p->peer_slab_bytes[peer] = peer_slab_bytes;
     return BNS_OK;
 }
 
@@ -1018,8 +1038,9 @@ extern "C" int bns_p2p_put_rows_f32(bns_p2p_t *p, int32_t peer, size_t remote_of
     BNS_REQUIRE(flag_index >= 0 && flag_index < p->n_flags, "bns_p2p_put_rows_f32: bad flag index");
     BNS_REQUIRE(k >= 0 && F > 0 && ldh >= F && ld_remote >= F, "bns_p2p_put_rows_f32: bad shape");
     BNS_REQUIRE(div != 0.f, "bns_p2p_put_rows_f32: division by zero");
-    BNS_REQUIRE(remote_off % 16 == 0 && remote_off + (size_t)k * ld_remote * 4 <= p->slab_bytes,
-                "bns_p2p_put_rows_f32: remote range outside the slab");
+    BNS_REQUIRE(remote_off % 16 == 0 && remote_off + (size_t)k * ld_remote * 4 <= p->peer_slab_bytes[peer],
+                "bns_p2p_put_rows_f32: remote range [%zu, +%lld rows) outside peer %d's slab (%zu bytes)", remote_off,
+                (long long)k, peer, p->peer_slab_bytes[peer]);
     BNS_REQUIRE(k == 0 || H, "bns_p2p_put_rows_f32: NULL source");
     float *remote = reinterpret_cast<float *>(p->peer_slab[peer] + remote_off);
     unsigned long long *flag = p->peer_flags[peer] + flag_index;
@@ -1041,7 +1062,7 @@ extern "C" int bns_p2p_put_rows_f32(bns_p2p_t *p, int32_t peer, size_t remote_of
 extern "C" int bns_p2p_wait_flag(bns_p2p_t *p, int32_t flag_index, uint64_t flag_value, void *stream) {
     BNS_REQUIRE(p, "bns_p2p_wait_flag: NULL handle");
     BNS_REQUIRE(flag_index >= 0 && flag_index < p->n_flags, "bns_p2p_wait_flag: bad flag index");
-    p2p_wait_kernel<<<1, 32, 0, as_stream(stream)>>>(p->flags + flag_index, flag_value);
+    p2p_wait_kernel<<<1, 32, 0, as_stream(stream)>>>(p->flags + flag_index, flag_value, 20ull * 1000000000ull);
     BNS_CUDA(cudaGetLastError());
     return BNS_OK;
 }

@@ -123,11 +123,12 @@ class Buffer(object):
         with torch.cuda.device(self._device):
             check(lib.bns_p2p_create(ctypes.byref(h), self._rank, self._size, slab_bytes, n_flags), "bns_p2p_create")
         self._p2p = h
-        slab, flags = ctypes.c_void_p(), ctypes.c_void_p()
-        check(lib.bns_p2p_local(h, ctypes.byref(slab), ctypes.byref(flags)), "bns_p2p_local")
+        slab, flags, nbytes = ctypes.c_void_p(), ctypes.c_void_p(), ctypes.c_size_t()
+        check(lib.bns_p2p_local(h, ctypes.byref(slab), ctypes.byref(flags), ctypes.byref(nbytes)), "bns_p2p_local")
         self._slab_ptr = slab.value
         # publish: where peers must write inside MY slab (row offsets of their segment) + how to map my memory
-        my = {"fwd_off": self._fwd_off, "bwd_off": self._bwd_off, "pl": self._pl, "send_begin": self._send_begin}
+        my = {"fwd_off": self._fwd_off, "bwd_off": self._bwd_off, "pl": self._pl, "send_begin": self._send_begin,
+              "slab_bytes": nbytes.value}
         if c.kind == "thread":
             my["ptrs"] = (slab.value, flags.value)
         else:
@@ -141,10 +142,11 @@ class Buffer(object):
             if j == self._rank:
                 continue
             if c.kind == "thread":
-                check(lib.bns_p2p_set_peer(h, j, table[j]["ptrs"][0], table[j]["ptrs"][1]), "bns_p2p_set_peer")
+                check(lib.bns_p2p_set_peer(h, j, table[j]["ptrs"][0], table[j]["ptrs"][1], table[j]["slab_bytes"]),
+                      "bns_p2p_set_peer")
             else:
                 with torch.cuda.device(self._device):
-                    check(lib.bns_p2p_import(h, j, table[j]["handle"]), "bns_p2p_import")
+                    check(lib.bns_p2p_import(h, j, table[j]["handle"], table[j]["slab_bytes"]), "bns_p2p_import")
         c.barrier()
 
     def _flag(self, layer, backward, src):

@@ -154,20 +154,21 @@ int bns_halo_slot_update(const int64_t *pos /*device [part size of the peer]*/, 
 int bns_p2p_create(bns_p2p_t **out, int32_t rank, int32_t world, size_t slab_bytes, int32_t n_flags);
 int bns_p2p_destroy(bns_p2p_t *p);
 /* base of this rank's slab / flag block (device pointers, valid in this process) */
-int bns_p2p_local(const bns_p2p_t *p, void **slab, void **flags);
+int bns_p2p_local(const bns_p2p_t *p, void **slab, void **flags, size_t *slab_bytes);
 /* IPC export / import (multi-process).  handle_out: BNS_P2P_HANDLE_BYTES bytes for the slab followed by
  * BNS_P2P_HANDLE_BYTES bytes for the flags. */
 int bns_p2p_export(const bns_p2p_t *p, void *handle_out /*2*BNS_P2P_HANDLE_BYTES*/);
-int bns_p2p_import(bns_p2p_t *p, int32_t peer, const void *handle /*2*BNS_P2P_HANDLE_BYTES*/);
+int bns_p2p_import(bns_p2p_t *p, int32_t peer, const void *handle /*2*BNS_P2P_HANDLE_BYTES*/, size_t peer_slab_bytes);
 /* In-process peers (threads): register the peer's pointers directly. */
-int bns_p2p_set_peer(bns_p2p_t *p, int32_t peer, void *slab, void *flags);
+int bns_p2p_set_peer(bns_p2p_t *p, int32_t peer, void *slab, void *flags, size_t peer_slab_bytes);
 /* remote_rows[i, :F] (in peer's slab at byte offset remote_off, leading dim ld_remote floats)
  *     = H[idx[i], :F] / div   for i < k   (idx == NULL: rows i of H, used for the gradient return trip);
  * then, after a system-scope fence, peer.flags[flag_index] = flag_value (release). */
 int bns_p2p_put_rows_f32(bns_p2p_t *p, int32_t peer, size_t remote_off, int64_t ld_remote,
                          const float *H, int64_t ldh, int64_t F, const int64_t *idx, int64_t k, float div,
                          int32_t flag_index, uint64_t flag_value, void *stream);
-/* Enqueue a wait on `stream` until this rank's flags[flag_index] >= flag_value (acquire). */
+/* Enqueue a wait on `stream` until this rank's flags[flag_index] >= flag_value (acquire).  The spin is bounded
+ * (20 s): a peer that never signals traps the kernel (a loud CUDA error) instead of hanging the device. */
 int bns_p2p_wait_flag(bns_p2p_t *p, int32_t flag_index, uint64_t flag_value, void *stream);
 
 #ifdef __cplusplus
