@@ -1,0 +1,337 @@
+"""bench.py -- the driver's measurement contract.
+
+  python bench.py [--gpus N] [--steps K] [--warmup W]                (N>1: launched under torchrun, one rank per GPU)
+  python bench.py --impl reference [--gpus N] [--steps K] [--warmup W]
+
+Workload (BASELINE.json metric, configs[1]): 3-layer GraphSAGE (hidden 256, --use-pp, LayerNorm, dropout 0.5,
+lr 0.01, sampling rate 0.1) on the Reddit-shape synthetic power-law graph (232,965 nodes, ~114.6M edges, 602
+features, 41 classes), vertex-partitioned over the N GPUs (random partition).  A "step" is one training epoch:
+boundary sampling -> id exchange -> forward (feature exchange + SpMM + dense) -> loss -> backward (SpMM^T +
+gradient exchange) -> weight-gradient all-reduce -> Adam.  The graph is fixed, so more GPUs = less work per GPU
+("scaling": "strong").  value = epochs/sec of the whole job (max over ranks of the device-timed region).
+
+`--impl reference` times the CPU restatement of the reference (oracle/: torch CPU fp32 + C/OpenMP SpMM, P in-process
+ranks for N>1) on the host cores with the same config; the real reference cannot run here (needs DGL + CUDA 11.3
+wheels).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+import torch  # noqa: E402
+
+WORKLOAD = dict(shape="reddit", model="graphsage", n_layers=3, n_hidden=256, sampling_rate=0.1, dropout=0.5,
+                lr=0.01, norm="layer", partition="random")
+
+
+def load_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        with open(p) as f:
+            d = json.load(f)
+        return float(d["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md recipe)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index: int):
+        self.idx, self.proc, self.lines = gpu_index, None, []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "100", "-i", str(self.idx)], stdout=subprocess.PIPE,
+                                         stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self) -> dict:
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm, mx, reasons = [], [], set()
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1]))
+                mx.append(float(f[2]))
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def make_args(n_parts: int, backend: str, extra: dict):
+    ns = argparse.Namespace(dataset=WORKLOAD["shape"], model=WORKLOAD["model"], n_layers=WORKLOAD["n_layers"],
+                            n_hidden=WORKLOAD["n_hidden"], sampling_rate=WORKLOAD["sampling_rate"], use_pp=True,
+                            dropout=WORKLOAD["dropout"], norm=WORKLOAD["norm"], lr=WORKLOAD["lr"], weight_decay=0.0,
+                            seed=0, n_linear=0, backend=backend, sampler_seed=0, n_epochs=0, log_every=10 ** 9,
+                            heads=1, n_partitions=n_parts, inductive=False, partition_method=WORKLOAD["partition"],
+                            eval=False, chunk_nnz=0)
+    for k, v in extra.items():
+        setattr(ns, k, v)
+    return ns
+
+
+def build_partition(shape: str, n_parts: int, rank: int, device):
+    from bns_gcn_b200.data import make_graph, partition_graph
+    fg = make_graph(shape, seed=0, device=device)
+    stats = {"n_nodes": fg.n_nodes, "n_edges": fg.n_edges, "n_feat": fg.n_feat}
+    part = partition_graph(fg, n_parts, WORKLOAD["partition"], seed=0, ranks=[rank], device=device)[0]
+    del fg
+    return part, stats
+
+
+# =====================================================================================================
+# our arm
+# =====================================================================================================
+def run_ours(a):
+    import torch.distributed as dist
+    from bns_gcn_b200 import ops, train
+    from bns_gcn_b200._lib import lib
+    from bns_gcn_b200.helper import context as ctx
+    from bns_gcn_b200.helper.timer.timer import comm_timer
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world != a.gpus:
+        if world == 1 and a.gpus > 1:
+            raise SystemExit(f"--gpus {a.gpus} needs torchrun (one rank per GPU); WORLD_SIZE is 1")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    K, W = a.steps, max(a.warmup, 3)
+    part, gstats = build_partition(a.shape, world, rank, dev)
+    args = make_args(world, a.backend, {"n_feat": part.meta["n_feat"], "n_class": part.meta["n_class"],
+                                        "n_train": part.meta["n_train"], "dataset": a.shape})
+    st = train.setup(part.graph, part.node_dict, part.gpb, args, dev)
+    torch.cuda.synchronize(dev)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    def max_over_ranks(x: float) -> float:
+        if world == 1:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    epoch = 0
+    for _ in range(W):                                   # untimed warm-up
+        train.train_epoch(st, epoch)
+        epoch += 1
+    # ---------------- timed region: device-resident inputs -------------------------------------------
+    clocks = ClockSampler(local)
+    barrier()
+    if rank == 0:
+        clocks.start()
+    ops.PROFILE = prof = []
+    n0 = lib.bns_launch_count()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    ev0.record(torch.cuda.current_stream(dev))
+    torch.cuda.nvtx.range_push("bns_timed")              # ncu --nvtx --nvtx-include "bns_timed/" lists one step
+    for _ in range(K):
+        train.train_epoch(st, epoch)
+        epoch += 1
+    torch.cuda.nvtx.range_pop()
+    ev1.record(torch.cuda.current_stream(dev))
+    barrier()
+    ops.PROFILE = None
+    n1 = lib.bns_launch_count()
+    clk = clocks.stop() if rank == 0 else None
+    dev_ms = max_over_ranks(ev0.elapsed_time(ev1))
+    comm_last = max_over_ranks(comm_timer.tot_time()) if world > 1 else 0.0     # Comm(s) of the last epoch
+    reduce_last = max_over_ranks(ctx.reducer.last_reduce_seconds()) if world > 1 else 0.0
+    spmm_ms = sum(s.elapsed_time(e) for s, e, *_ in prof)
+    spmm_alg = sum(p[2] for p in prof)
+    spmm_gather = sum(8 * 1 + 4 * p[3] + 4 * p[4] * p[3] for p in prof)
+    # ---------------- e2e: host-resident inputs, H2D + D2H inside the timed region -------------------
+    feat_dev, lab_dev, mask_dev = st.feat, st.labels, st.train_mask
+    feat_pin = feat_dev.cpu().pin_memory()
+    lab_pin, mask_pin = lab_dev.cpu().pin_memory(), mask_dev.cpu().pin_memory()
+    bufs = [(torch.empty_like(feat_dev), torch.empty_like(lab_dev), torch.empty_like(mask_dev)) for _ in range(2)]
+    copy_stream = torch.cuda.Stream(dev)
+    ready = [torch.cuda.Event(), torch.cuda.Event()]
+    consumed = [torch.cuda.Event(), torch.cuda.Event()]
+    h2d = feat_pin.numel() * 4 + lab_pin.numel() * lab_pin.element_size() + mask_pin.numel()
+
+    def prefetch(i):
+        with torch.cuda.stream(copy_stream):
+            copy_stream.wait_event(consumed[i % 2])
+            f, l, m = bufs[i % 2]
+            f.copy_(feat_pin, non_blocking=True)
+            l.copy_(lab_pin, non_blocking=True)
+            m.copy_(mask_pin, non_blocking=True)
+            ready[i % 2].record(copy_stream)
+
+    for i in range(2):
+        consumed[i].record(torch.cuda.current_stream(dev))
+    barrier()
+    t0 = time.perf_counter()
+    prefetch(0)
+    for i in range(K):
+        if i + 1 < K:
+            prefetch(i + 1)                              # next step's inputs stream in behind this step's compute
+        torch.cuda.current_stream(dev).wait_event(ready[i % 2])
+        st.feat, st.labels, st.train_mask = bufs[i % 2]
+        loss = train.train_epoch(st, epoch)
+        consumed[i % 2].record(torch.cuda.current_stream(dev))
+        epoch += 1
+        _ = loss.item()                                  # D2H read of the step's result
+    barrier()
+    e2e_s = max_over_ranks(time.perf_counter() - t0)
+    st.feat, st.labels, st.train_mask = feat_dev, lab_dev, mask_dev
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+    peak, peak_src = load_peaks()
+    n_spmm = max(len(prof), 1)
+    ach = spmm_alg / (spmm_ms * 1e-3) / 1e9 if spmm_ms > 0 else 0.0
+    out = {
+        "metric": "epochs/sec (3-layer GraphSAGE, Reddit-shape graph)", "value": K / (dev_ms * 1e-3),
+        "unit": "epochs/s", "n_gpus": world, "steps": K, "warmup": W, "ms_per_step": dev_ms / K,
+        "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": f"BASELINE configs[1]: Reddit-shape synthetic power-law graph, {gstats['n_nodes']} nodes, "
+                               f"{gstats['n_edges']} edges, {gstats['n_feat']} feat, 41 classes; GraphSAGE 3-layer hidden 256 "
+                               f"--use-pp, sampling-rate 0.1, dropout 0.5, {world} random partition(s); "
+                               "inputs (1.1 GB features / rank-count) exceed L2, no flush needed",
+                   "parallelism": f"partition-parallel x{world}", "exchange": a.backend,
+                   "n_in_rank0": part.graph.n_in, "n_halo_rank0": part.graph.n_halo,
+                   "local_edges_rank0": part.graph.num_edges()},
+        "comm_s_per_epoch": comm_last, "reduce_s_per_epoch": reduce_last,
+        "e2e": {"value": K / e2e_s, "unit": "epochs/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": 4,
+                "note": "features+labels+mask copied from pinned host memory every epoch (prefetched one step ahead on "
+                        "a copy stream), loss read back every epoch"},
+        "gpu_launches": int(n1 - n0),
+        "clocks": clk,
+        "roofline": {"bound": "hbm", "kernel": "spmm_kernel (bns_spmm_sum_f32)", "achieved": ach, "peak": peak,
+                     "unit": "GB/s", "frac": ach / peak, "traffic": None, "peak_source": peak_src,
+                     "launches_timed": len(prof), "avg_launch_ms": spmm_ms / n_spmm,
+                     "share_of_step": spmm_ms / dev_ms if dev_ms else None,
+                     "gather_GBs": spmm_gather / (spmm_ms * 1e-3) / 1e9 if spmm_ms > 0 else 0.0,
+                     "note": "achieved = algorithmic bytes (each distinct operand byte once, SURVEY 8d) / CUDA-event time; "
+                             "gather_GBs counts one 4F-byte row read per edge (what actually crosses L2->SM): that is the "
+                             "binding resource on this degree-492 graph, see DESIGN.md"},
+    }
+    if world == 1 and not a.no_cpu_baseline:
+        out["cpu_baseline"] = cpu_epochs_per_sec(a.shape, 1, steps=1, warmup=1)
+    print(json.dumps(out))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+# =====================================================================================================
+# CPU arm (the oracle as the reference's stand-in)
+# =====================================================================================================
+def cpu_epochs_per_sec(shape: str, n_parts: int, steps: int, warmup: int, budget_s: float = 150.0) -> dict:
+    from bns_gcn_b200.data import make_graph, partition_graph
+    from oracle import bns_oracle as O
+    import numpy as np
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(max(1, cores // n_parts))
+    fg = make_graph(shape, seed=0, device=torch.device("cuda") if torch.cuda.is_available() else None)
+    parts = partition_graph(fg, n_parts, WORKLOAD["partition"], seed=0)
+    del fg
+    times = [[] for _ in range(n_parts)]
+
+    def fn(comm, r):
+        rk = O.OracleRank(O.RankInput.from_partition(parts[r]), comm, model=WORKLOAD["model"],
+                          n_layers=WORKLOAD["n_layers"], n_hidden=WORKLOAD["n_hidden"],
+                          sampling_rate=WORKLOAD["sampling_rate"], use_pp=True, dropout=WORKLOAD["dropout"],
+                          norm=WORKLOAD["norm"], lr=WORKLOAD["lr"], seed=0)
+        rng = np.random.RandomState(1234 + r)
+        t_begin = time.perf_counter()
+        for e in range(warmup + steps):
+            comm.barrier()
+            t0 = time.perf_counter()
+            rk.epoch(rng=rng)
+            comm.barrier()
+            dt = time.perf_counter() - t0
+            if e >= warmup:
+                times[r].append(dt)
+            # stay inside the time budget: a bounded sample of full epochs
+            stop = torch.tensor([1.0 if (time.perf_counter() - t_begin > budget_s and e >= warmup) else 0.0])
+            comm.all_reduce_sum(stop)
+            if float(stop) > 0:
+                break
+        return len(times[r])
+
+    done = O.run_threads(n_parts, fn)[0]
+    per_epoch = [max(times[r][i] for r in range(n_parts)) for i in range(done)]
+    mean = sum(per_epoch) / len(per_epoch)
+    return {"value": 1.0 / mean, "unit": "epochs/s", "cores": cores, "kind": "port",
+            "sample": f"{done} full epoch(s) of the same workload ({n_parts} partition(s) as in-process ranks) after "
+                      f"{warmup} warm-up, oracle/bns_oracle.py + oracle/spmm_ref.c (OpenMP), {cores} host threads",
+            "seconds_per_epoch": mean}
+
+
+def run_reference(a):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    K, W = a.steps, a.warmup
+    res = cpu_epochs_per_sec(a.shape, a.gpus, steps=K, warmup=min(W, 1))
+    out = {"impl": "reference", "metric": "epochs/sec (3-layer GraphSAGE, Reddit-shape graph)", "value": res["value"],
+           "unit": "epochs/s", "n_gpus": a.gpus, "steps": K, "warmup": W, "ms_per_step": 1e3 * res["seconds_per_epoch"],
+           "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+           "config": {"workload": f"BASELINE configs[1] on host cores: Reddit-shape synthetic graph, GraphSAGE 3-layer "
+                                  f"hidden 256 --use-pp, sampling-rate 0.1, dropout 0.5, {a.gpus} random partition(s)",
+                      "parallelism": f"{a.gpus} in-process rank(s), OpenMP SpMM"},
+           "cpu_baseline": res,
+           "e2e": {"value": res["value"], "unit": "epochs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(out))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--shape", default=WORKLOAD["shape"])
+    ap.add_argument("--backend", default="nccl", choices=["nccl", "p2p"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    a = ap.parse_args()
+    if a.impl == "reference":
+        run_reference(a)
+    else:
+        run_ours(a)
+
+
+if __name__ == "__main__":
+    main()

@@ -20,6 +20,7 @@ P2P_HANDLE_BYTES = 64
 SIGNATURES = {
     "bns_abi_version": (c_int, []),
     "bns_last_error": (c_char_p, []),
+    "bns_launch_count": (c_uint64, []),
     "bns_device_info": (c_int, [c_char_p, c_size_t, POINTER(c_int), POINTER(c_int64), POINTER(c_int), POINTER(c_int)]),
     "bns_graph_create": (c_int, [POINTER(c_void_p), c_int64, c_int64, c_int64, c_void_p, c_void_p, c_int32, c_void_p]),
     "bns_graph_transpose": (c_int, [c_void_p, POINTER(c_void_p), c_void_p]),

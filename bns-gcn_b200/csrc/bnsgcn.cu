@@ -17,6 +17,7 @@
 #include <cstdarg>
 #include <cstdio>
 #include <cstring>
+#include <atomic>
 #include <new>
 
 namespace {
@@ -50,6 +51,7 @@ constexpr int kThreads = 256;
 constexpr int kWarps = kThreads / 32;
 constexpr int kDefaultChunk = 1024;
 
+std::atomic<unsigned long long> g_launches{0};   // kernels of this library enqueued so far (bench.py gpu_launches)
 int g_sm_count = 0;
 int sm_count() {
     if (g_sm_count == 0) {
@@ -200,6 +202,7 @@ int build_chunks(bns_graph *g, cudaStream_t st) {
 }  // namespace
 
 extern "C" int bns_abi_version(void) { return BNS_ABI_VERSION; }
+extern "C" uint64_t bns_launch_count(void) { return g_launches.load(); }
 extern "C" const char *bns_last_error(void) { return g_err; }
 
 extern "C" int bns_device_info(char *name, size_t name_len, int *sms, int64_t *l2_bytes, int *cc_major, int *cc_minor) {
@@ -560,6 +563,7 @@ int launch_spmm(const SpmmArgs &a, int tiles, cudaStream_t st) {
     int64_t cap = (int64_t)sm_count() * blocks_per_sm;
     unsigned gx = (unsigned)(want < cap ? (want > 0 ? want : 1) : cap);
     spmm_kernel<W, NV, MAP, CSCALE, GUARD><<<dim3(gx, tiles), kThreads, 0, st>>>(a);
+    g_launches += a.n_split > 0 ? 2 : 1;
     if (a.n_split > 0) {
         unsigned fx = (unsigned)((a.n_split + kWarps - 1) / kWarps);
         spmm_fixup_kernel<W, NV, GUARD><<<dim3(fx, tiles), kThreads, 0, st>>>(a);
@@ -688,6 +692,7 @@ extern "C" int bns_gather_div_f32(const float *H, int64_t ldh, int64_t F, const 
         rows_kernel<true, false><<<rows_grid(k), kThreads, 0, st>>>(H, ldh, out, ldo, idx, k, (int32_t)F, div);
     else
         rows_kernel<false, false><<<rows_grid(k), kThreads, 0, st>>>(H, ldh, out, ldo, idx, k, (int32_t)F, div);
+    ++g_launches;
     BNS_CUDA(cudaGetLastError());
     return BNS_OK;
 }
@@ -704,6 +709,7 @@ extern "C" int bns_scatter_add_div_f32(float *G, int64_t ldg, int64_t F, const i
         rows_kernel<true, true><<<rows_grid(k), kThreads, 0, st>>>(src, lds, G, ldg, idx, k, (int32_t)F, div);
     else
         rows_kernel<false, true><<<rows_grid(k), kThreads, 0, st>>>(src, lds, G, ldg, idx, k, (int32_t)F, div);
+    ++g_launches;
     BNS_CUDA(cudaGetLastError());
     return BNS_OK;
 }
@@ -817,6 +823,7 @@ extern "C" int bns_sample_boundary(const int64_t *boundary_cat, const int64_t *s
     BNS_CUDA(cub::DeviceRadixSort::SortPairs(base + l.tmp, tb, keys_in, keys_out, vals_in, vals_out, (int)B, 0, 64, st));
     sample_take_kernel<<<(unsigned)((K_total + 255) / 256), 256, 0, st>>>(boundary_cat, seg_begin, out_begin, n_seg,
                                                                          K_total, vals_out, selected);
+    g_launches += 2;
     BNS_CUDA(cudaGetLastError());
     return BNS_OK;
 }
@@ -846,6 +853,7 @@ extern "C" int bns_fill_i32(int32_t *dst, int64_t n, int32_t value, void *stream
     if (n == 0) return BNS_OK;
     BNS_REQUIRE(dst, "bns_fill_i32: NULL pointer");
     fill_i32_kernel<<<(unsigned)((n + 255) / 256), 256, 0, as_stream(stream)>>>(dst, n, value);
+    ++g_launches;
     BNS_CUDA(cudaGetLastError());
     return BNS_OK;
 }
@@ -856,6 +864,7 @@ extern "C" int bns_halo_slot_update(const int64_t *pos, const int64_t *one_hops,
     if (r == 0) return BNS_OK;
     BNS_REQUIRE(pos && one_hops && slot, "bns_halo_slot_update: NULL pointer");
     halo_slot_kernel<<<(unsigned)((r + 255) / 256), 256, 0, as_stream(stream)>>>(pos, one_hops, r, n_in, slab_offset, slot);
+    ++g_launches;
     BNS_CUDA(cudaGetLastError());
     return BNS_OK;
 }
@@ -1055,6 +1064,7 @@ extern "C" int bns_p2p_put_rows_f32(bns_p2p_t *p, int32_t peer, size_t remote_of
     else
         p2p_put_rows_kernel<false><<<grid, kThreads, 0, st>>>(H, ldh, (int32_t)F, idx, k, div, remote, ld_remote, flag,
                                                               flag_value, ticket);
+    ++g_launches;
     BNS_CUDA(cudaGetLastError());
     return BNS_OK;
 }
@@ -1063,6 +1073,7 @@ extern "C" int bns_p2p_wait_flag(bns_p2p_t *p, int32_t flag_index, uint64_t flag
     BNS_REQUIRE(p, "bns_p2p_wait_flag: NULL handle");
     BNS_REQUIRE(flag_index >= 0 && flag_index < p->n_flags, "bns_p2p_wait_flag: bad flag index");
     p2p_wait_kernel<<<1, 32, 0, as_stream(stream)>>>(p->flags + flag_index, flag_value, 20ull * 1000000000ull);
+    ++g_launches;
     BNS_CUDA(cudaGetLastError());
     return BNS_OK;
 }

@@ -18,6 +18,10 @@ from . import _lib
 from ._lib import check, lib
 
 
+# bench.py sets this to a list to collect (start_event, end_event, algorithmic_bytes, nnz, F) per SpMM launch
+PROFILE = None
+
+
 def _stream_ptr() -> int:
     return torch.cuda.current_stream().cuda_stream
 
@@ -130,11 +134,20 @@ def spmm(g: DeviceGraph, x: torch.Tensor, out: Optional[torch.Tensor] = None, *,
         if t is not None:
             _req(t, n, nm)
     ws = g.workspace(F)
+    prof = PROFILE
+    if prof is not None:
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        ev0.record(torch.cuda.current_stream(x.device))
     with torch.cuda.device(x.device):
         check(lib.bns_spmm_sum_f32(g._h, x.data_ptr(), x.stride(0), F, out.data_ptr(), out.stride(0),
                                    _ptr(row_scale), _ptr(col_scale), _ptr(row_map), _ptr(col_map), n_direct,
                                    1 if accumulate else 0, _ptr(ws), 0 if ws is None else ws.numel(), _stream_ptr()),
               "bns_spmm_sum_f32")
+    if prof is not None:
+        ev1.record(torch.cuda.current_stream(x.device))
+        # every distinct operand byte once -- row offsets, column ids, source rows, output rows
+        alg = 8 * (g.n_rows + 1) + 4 * g.nnz + 4 * F * x.shape[0] + 4 * F * out.shape[0]
+        prof.append((ev0, ev1, alg, g.nnz, F))
     return out
 
 

@@ -43,6 +43,8 @@ typedef struct bns_p2p   bns_p2p_t;     /* opaque: peer-mapped exchange slabs of
 
 int         bns_abi_version(void);
 const char *bns_last_error(void);
+/* Number of kernels of this library enqueued so far by this process (bench.py reports the delta as gpu_launches). */
+uint64_t    bns_launch_count(void);
 /* Name, SM count, L2 bytes of the current device (for bench.py's grid / roofline bookkeeping). */
 int         bns_device_info(char *name, size_t name_len, int *sm_count, int64_t *l2_bytes, int *cc_major, int *cc_minor);
 
