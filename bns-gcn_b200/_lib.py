@@ -30,7 +30,7 @@ SIGNATURES = {
     "bns_graph_copy_csr": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p]),
     "bns_spmm_workspace_bytes": (c_size_t, [c_void_p, c_int64]),
     "bns_spmm_sum_f32": (c_int, [c_void_p, c_void_p, c_int64, c_int64, c_void_p, c_int64, c_void_p, c_void_p,
-                                 c_void_p, c_void_p, c_int64, c_int, c_void_p, c_size_t, c_void_p]),
+                                 c_void_p, c_void_p, c_int64, c_int64, c_int32, c_int, c_void_p, c_size_t, c_void_p]),
     "bns_gather_div_f32": (c_int, [c_void_p, c_int64, c_int64, c_void_p, c_int64, c_float, c_void_p, c_int64, c_void_p]),
     "bns_scatter_add_div_f32": (c_int, [c_void_p, c_int64, c_int64, c_void_p, c_int64, c_float, c_void_p, c_int64,
                                         c_void_p]),

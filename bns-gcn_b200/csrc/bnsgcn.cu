@@ -16,6 +16,7 @@
 
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <atomic>
 #include <new>
@@ -360,6 +361,7 @@ struct SpmmArgs {
     int32_t accumulate;
     float *ws;
     int64_t ldws;
+    int64_t n_tiles;     // column slabs of the kernel's SLAB width covering F
 };
 
 template <int W> struct Vec;
@@ -374,6 +376,10 @@ template <> struct Vec<4> {
         v.x = fmaf(o.v.x, s, v.x); v.y = fmaf(o.v.y, s, v.y); v.z = fmaf(o.v.z, s, v.z); v.w = fmaf(o.v.w, s, v.w);
     }
     __device__ __forceinline__ void scale(float s) { v.x *= s; v.y *= s; v.z *= s; v.w *= s; }
+    __device__ __forceinline__ void add_shfl_xor(int off) {
+        v.x += __shfl_xor_sync(0xffffffffu, v.x, off); v.y += __shfl_xor_sync(0xffffffffu, v.y, off);
+        v.z += __shfl_xor_sync(0xffffffffu, v.z, off); v.w += __shfl_xor_sync(0xffffffffu, v.w, off);
+    }
 };
 template <> struct Vec<1> {
     float v;
@@ -384,6 +390,7 @@ template <> struct Vec<1> {
     __device__ __forceinline__ void add(const Vec &o) { v += o.v; }
     __device__ __forceinline__ void fma(const Vec &o, float s) { v = fmaf(o.v, s, v); }
     __device__ __forceinline__ void scale(float s) { v *= s; }
+    __device__ __forceinline__ void add_shfl_xor(int off) { v += __shfl_xor_sync(0xffffffffu, v, off); }
 };
 
 __device__ __forceinline__ int32_t ld_stream_i32(const int32_t *p) {
@@ -398,22 +405,35 @@ __device__ __forceinline__ int32_t ld_stream_i32(const int32_t *p) {
 // Column ids of 32 entries are fetched with one coalesced load, mapped (col_map: sampled halo ->
 // slab row, -1 = skip), compacted through shared memory and then consumed UNROLL at a time so that
 // UNROLL*NV independent 16-byte gathers are in flight per lane.
-template <int W, int NV, bool MAP, bool CSCALE, bool GUARD>
+//
+// Cache blocking (the ncu capture of round 1 showed why: with the whole F = 256 row per gather the 238 MB
+// source matrix of the Reddit-shape graph misses the 126 MB L2 58 % of the time and the kernel moves 53 GB
+// of DRAM per launch for 0.9 GB of algorithmic bytes).  The feature dimension is cut into column slabs of
+// SLAB = G*W*NV floats chosen so that (source rows x SLAB x 4 B) stays L2-resident; work items are ordered
+// slab-major, so at any moment all resident warps gather from the same slab.  For narrow slabs a warp is
+// split into 32/G row groups of G lanes that walk different entries of the chunk concurrently (every lane
+// still issues 16-byte loads) and are summed with shuffles at the end.
+template <int W, int G, int NV, bool MAP, bool CSCALE, bool GUARD>
 __global__ void __launch_bounds__(kThreads) spmm_kernel(SpmmArgs a) {
-    constexpr int UNROLL = (NV <= 2) ? 8 / NV : 2;
+    constexpr int NG = 32 / G;                               // entries walked concurrently by one warp
+    constexpr int UNROLL = (NV <= 2) ? 8 / NV : 2;           // independent 16-byte gathers in flight per lane
+    constexpr int SLAB = G * W * NV;
     __shared__ int32_t s_col[kWarps][32];
     __shared__ float s_sc[kWarps][32];
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-    const int f0 = blockIdx.y * (32 * W * NV);
+    const int gi = lane / G, gl = lane % G;
     const int64_t warps_total = (int64_t)gridDim.x * kWarps;
-    int fcol[NV];
-    bool fok[NV];
+    const int64_t items = a.n_chunks * a.n_tiles;
+    for (int64_t item = (int64_t)blockIdx.x * kWarps + w; item < items; item += warps_total) {
+        const int64_t c = item % a.n_chunks;
+        const int f0 = (int)(item / a.n_chunks) * SLAB;
+        int fcol[NV];
+        bool fok[NV];
 #pragma unroll
-    for (int t = 0; t < NV; ++t) {
-        fcol[t] = f0 + (lane + 32 * t) * W;
-        fok[t] = !GUARD || fcol[t] < a.F;
-    }
-    for (int64_t c = (int64_t)blockIdx.x * kWarps + w; c < a.n_chunks; c += warps_total) {
+        for (int t = 0; t < NV; ++t) {
+            fcol[t] = f0 + (gl + G * t) * W;
+            fok[t] = !GUARD || fcol[t] < a.F;
+        }
         const int32_t row = a.chunk_row[c];
         int32_t orow = row;
         if (a.row_map) {
@@ -454,11 +474,11 @@ __global__ void __launch_bounds__(kThreads) spmm_kernel(SpmmArgs a) {
             }
             __syncwarp();
             int j = 0;
-            for (; j + UNROLL <= cnt; j += UNROLL) {
+            for (; j + NG * UNROLL <= cnt; j += NG * UNROLL) {       // full steps: no predication
                 Vec<W> v[UNROLL][NV];
 #pragma unroll
                 for (int u = 0; u < UNROLL; ++u) {
-                    const float *xr = a.X + (int64_t)s_col[w][j + u] * a.ldx;
+                    const float *xr = a.X + (int64_t)s_col[w][j + u * NG + gi] * a.ldx;
 #pragma unroll
                     for (int t = 0; t < NV; ++t) {
                         if (fok[t]) v[u][t].load_ro(xr + fcol[t]); else v[u][t].zero();
@@ -466,26 +486,36 @@ __global__ void __launch_bounds__(kThreads) spmm_kernel(SpmmArgs a) {
                 }
 #pragma unroll
                 for (int u = 0; u < UNROLL; ++u) {
-                    const float cs = CSCALE ? s_sc[w][j + u] : 1.f;
+                    const float cs = CSCALE ? s_sc[w][j + u * NG + gi] : 1.f;
 #pragma unroll
                     for (int t = 0; t < NV; ++t) {
                         if (CSCALE) acc[t].fma(v[u][t], cs); else acc[t].add(v[u][t]);
                     }
                 }
             }
-            for (; j < cnt; ++j) {
-                const float *xr = a.X + (int64_t)s_col[w][j] * a.ldx;
-                const float cs = CSCALE ? s_sc[w][j] : 1.f;
+            for (; j < cnt; j += NG) {                               // tail: one entry per row group
+                const int jj = j + gi;
+                if (jj < cnt) {
+                    const float *xr = a.X + (int64_t)s_col[w][jj] * a.ldx;
+                    const float cs = CSCALE ? s_sc[w][jj] : 1.f;
 #pragma unroll
-                for (int t = 0; t < NV; ++t) {
-                    if (fok[t]) {
-                        Vec<W> v;
-                        v.load_ro(xr + fcol[t]);
-                        if (CSCALE) acc[t].fma(v, cs); else acc[t].add(v);
+                    for (int t = 0; t < NV; ++t) {
+                        if (fok[t]) {
+                            Vec<W> v;
+                            v.load_ro(xr + fcol[t]);
+                            if (CSCALE) acc[t].fma(v, cs); else acc[t].add(v);
+                        }
                     }
                 }
             }
             __syncwarp();
+        }
+        if (NG > 1) {            // fold the row groups: afterwards group 0 (lanes < G) holds the chunk's sum
+#pragma unroll
+            for (int t = 0; t < NV; ++t)
+#pragma unroll
+                for (int off = 16; off >= G; off >>= 1) acc[t].add_shfl_xor(off);
+            if (gi != 0) continue;
         }
         const int32_t part = a.chunk_part[c];
         if (part >= 0) {   // the row spans several chunks: park the raw partial sum, combined later
@@ -549,38 +579,81 @@ __global__ void __launch_bounds__(kThreads) spmm_fixup_kernel(SpmmArgs a) {
     }
 }
 
-template <int W, int NV, bool MAP, bool CSCALE, bool GUARD>
-int launch_spmm(const SpmmArgs &a, int tiles, cudaStream_t st) {
+template <int W, int G, int NV, bool MAP, bool CSCALE, bool GUARD>
+int launch_spmm(SpmmArgs a, cudaStream_t st) {
     static int blocks_per_sm = 0;
     if (blocks_per_sm == 0) {
         int n = 0;
-        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, spmm_kernel<W, NV, MAP, CSCALE, GUARD>, kThreads, 0) !=
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, spmm_kernel<W, G, NV, MAP, CSCALE, GUARD>, kThreads, 0) !=
                 cudaSuccess || n < 1)
             n = 2;
         blocks_per_sm = n;
     }
-    int64_t want = (a.n_chunks + kWarps - 1) / kWarps;
+    constexpr int SLAB = G * W * NV;
+    a.n_tiles = (a.F + SLAB - 1) / SLAB;
+    const int64_t items = a.n_chunks * a.n_tiles;
+    int64_t want = (items + kWarps - 1) / kWarps;
     int64_t cap = (int64_t)sm_count() * blocks_per_sm;
     unsigned gx = (unsigned)(want < cap ? (want > 0 ? want : 1) : cap);
-    spmm_kernel<W, NV, MAP, CSCALE, GUARD><<<dim3(gx, tiles), kThreads, 0, st>>>(a);
+    spmm_kernel<W, G, NV, MAP, CSCALE, GUARD><<<gx, kThreads, 0, st>>>(a);
     g_launches += a.n_split > 0 ? 2 : 1;
     if (a.n_split > 0) {
         unsigned fx = (unsigned)((a.n_split + kWarps - 1) / kWarps);
-        spmm_fixup_kernel<W, NV, GUARD><<<dim3(fx, tiles), kThreads, 0, st>>>(a);
+        if (W == 4) {
+            const int tiles = (a.F + 255) / 256;
+            spmm_fixup_kernel<4, 2, true><<<dim3(fx, tiles), kThreads, 0, st>>>(a);
+        } else {
+            const int tiles = (a.F + 255) / 256;
+            spmm_fixup_kernel<1, 8, true><<<dim3(fx, tiles), kThreads, 0, st>>>(a);
+        }
     }
     return BNS_OK;
 }
 
-template <int W, int NV, bool GUARD>
-int dispatch_flags(const SpmmArgs &a, int tiles, cudaStream_t st) {
+template <int W, int G, int NV>
+int dispatch_flags(const SpmmArgs &a, cudaStream_t st) {
     const bool map = a.col_map != nullptr, cs = a.col_scale != nullptr;
-    if (map && cs) return launch_spmm<W, NV, true, true, GUARD>(a, tiles, st);
-    if (map) return launch_spmm<W, NV, true, false, GUARD>(a, tiles, st);
-    if (cs) return launch_spmm<W, NV, false, true, GUARD>(a, tiles, st);
-    return launch_spmm<W, NV, false, false, GUARD>(a, tiles, st);
+    const bool guard = (a.F % (G * W * NV)) != 0;
+    if (guard) {
+        if (map && cs) return launch_spmm<W, G, NV, true, true, true>(a, st);
+        if (map) return launch_spmm<W, G, NV, true, false, true>(a, st);
+        if (cs) return launch_spmm<W, G, NV, false, true, true>(a, st);
+        return launch_spmm<W, G, NV, false, false, true>(a, st);
+    }
+    if (map && cs) return launch_spmm<W, G, NV, true, true, false>(a, st);
+    if (map) return launch_spmm<W, G, NV, true, false, false>(a, st);
+    if (cs) return launch_spmm<W, G, NV, false, true, false>(a, st);
+    return launch_spmm<W, G, NV, false, false, false>(a, st);
 }
 
 inline int64_t ws_ld(int64_t F) { return (F + 3) / 4 * 4; }
+
+int64_t g_l2_bytes = 0;
+int64_t l2_bytes() {
+    if (g_l2_bytes == 0) {
+        int dev = 0, v = 0;
+        if (cudaGetDevice(&dev) == cudaSuccess && cudaDeviceGetAttribute(&v, cudaDevAttrL2CacheSize, dev) == cudaSuccess &&
+            v > 0)
+            g_l2_bytes = v;
+        else
+            g_l2_bytes = 126ll << 20;
+    }
+    return g_l2_bytes;
+}
+
+// Widest column slab (in floats: 256, 128, 64 or 32) whose source slab  x_rows * slab * 4 B  fits the L2 budget.
+int pick_slab(int64_t F, int64_t x_rows, int32_t forced) {
+    if (forced == 256 || forced == 128 || forced == 64 || forced == 32) return forced;
+    const char *env = getenv("BNS_SPMM_SLAB");
+    if (env) {
+        int v = atoi(env);
+        if (v == 256 || v == 128 || v == 64 || v == 32) return v;
+    }
+    const double budget = 0.55 * (double)l2_bytes();      // leave room for the index stream, Y and the other die
+    int slab = 256;
+    while (slab > 32 && (double)x_rows * 4.0 * (double)(slab < F ? slab : F) > budget) slab >>= 1;
+    return slab;
+}
 
 }  // namespace
 
@@ -591,8 +664,8 @@ extern "C" size_t bns_spmm_workspace_bytes(const bns_graph_t *g, int64_t F) {
 
 extern "C" int bns_spmm_sum_f32(const bns_graph_t *g, const float *X, int64_t ldx, int64_t F, float *Y, int64_t ldy,
                                 const float *row_scale, const float *col_scale, const int32_t *row_map,
-                                const int32_t *col_map, int64_t n_direct, int accumulate, void *ws, size_t ws_bytes,
-                                void *stream) {
+                                const int32_t *col_map, int64_t n_direct, int64_t x_rows, int32_t slab_hint,
+                                int accumulate, void *ws, size_t ws_bytes, void *stream) {
     BNS_REQUIRE(g, "bns_spmm_sum_f32: NULL graph");
     BNS_REQUIRE(F > 0 && F < (1 << 24), "bns_spmm_sum_f32: bad feature width %lld", (long long)F);
     if (g->n_rows == 0) return BNS_OK;      // nothing to write (Y may legitimately be NULL)
@@ -604,6 +677,7 @@ extern "C" int bns_spmm_sum_f32(const bns_graph_t *g, const float *X, int64_t ld
         return fail(BNS_E_WORKSPACE, "bns_spmm_sum_f32: workspace %zu bytes < %zu needed", ws_bytes, need);
     if (col_map == nullptr) n_direct = g->n_cols;
     BNS_REQUIRE(n_direct >= 0 && n_direct <= g->n_cols, "bns_spmm_sum_f32: n_direct out of range");
+    if (x_rows <= 0) x_rows = g->n_cols;
     SpmmArgs a;
     a.indptr = g->indptr; a.indices = g->indices;
     a.chunk_row = g->chunk_row; a.chunk_start = g->chunk_start; a.chunk_part = g->chunk_part;
@@ -613,19 +687,21 @@ extern "C" int bns_spmm_sum_f32(const bns_graph_t *g, const float *X, int64_t ld
     a.row_scale = row_scale; a.col_scale = col_scale; a.row_map = row_map; a.col_map = col_map;
     a.n_direct = (int32_t)n_direct; a.accumulate = accumulate ? 1 : 0;
     a.ws = reinterpret_cast<float *>(ws); a.ldws = ws_ld(F);
+    a.n_tiles = 1;
     cudaStream_t st = as_stream(stream);
     const bool vec = (F % 4 == 0) && (ldx % 4 == 0) && (ldy % 4 == 0) &&
                      ((reinterpret_cast<uintptr_t>(X) | reinterpret_cast<uintptr_t>(Y)) % 16 == 0);
     if (vec) {
-        if (F <= 128) {
-            if (F == 128) dispatch_flags<4, 1, false>(a, 1, st); else dispatch_flags<4, 1, true>(a, 1, st);
-        } else {
-            const int tiles = (int)((F + 255) / 256);
-            if (F % 256 == 0) dispatch_flags<4, 2, false>(a, tiles, st); else dispatch_flags<4, 2, true>(a, tiles, st);
+        int slab = pick_slab(F, x_rows, slab_hint);
+        while (slab > 32 && slab / 2 >= F) slab >>= 1;       // never wider than needed (F = 64 -> 64-wide groups)
+        switch (slab) {
+            case 256: dispatch_flags<4, 32, 2>(a, st); break;
+            case 128: dispatch_flags<4, 32, 1>(a, st); break;
+            case 64:  dispatch_flags<4, 16, 1>(a, st); break;
+            default:  dispatch_flags<4, 8, 1>(a, st); break;
         }
     } else {
-        const int tiles = (int)((F + 255) / 256);
-        dispatch_flags<1, 8, true>(a, tiles, st);
+        dispatch_flags<1, 32, 8>(a, st);
     }
     BNS_CUDA(cudaGetLastError());
     return BNS_OK;

@@ -115,7 +115,7 @@ class DeviceGraph:
 def spmm(g: DeviceGraph, x: torch.Tensor, out: Optional[torch.Tensor] = None, *, n_out_rows: Optional[int] = None,
          row_scale: Optional[torch.Tensor] = None, col_scale: Optional[torch.Tensor] = None,
          row_map: Optional[torch.Tensor] = None, col_map: Optional[torch.Tensor] = None, n_direct: int = 0,
-         accumulate: bool = False) -> torch.Tensor:
+         accumulate: bool = False, slab: int = 0) -> torch.Tensor:
     """``bns_spmm_sum_f32``: ``out[orow(r)] (+)= row_scale[r] * sum_k col_scale[c_k] * x[xrow(c_k)]``."""
     _req(x, torch.float32, "x")
     if x.dim() != 2 or x.stride(1) != 1:
@@ -141,7 +141,7 @@ def spmm(g: DeviceGraph, x: torch.Tensor, out: Optional[torch.Tensor] = None, *,
     with torch.cuda.device(x.device):
         check(lib.bns_spmm_sum_f32(g._h, x.data_ptr(), x.stride(0), F, out.data_ptr(), out.stride(0),
                                    _ptr(row_scale), _ptr(col_scale), _ptr(row_map), _ptr(col_map), n_direct,
-                                   1 if accumulate else 0, _ptr(ws), 0 if ws is None else ws.numel(), _stream_ptr()),
+                                   x.shape[0], slab, 1 if accumulate else 0, _ptr(ws), 0 if ws is None else ws.numel(), _stream_ptr()),
               "bns_spmm_sum_f32")
     if prof is not None:
         ev1.record(torch.cuda.current_stream(x.device))

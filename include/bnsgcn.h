@@ -87,6 +87,8 @@ int bns_graph_copy_csr(const bns_graph_t *g, int64_t *indptr_out, int32_t *indic
  * The 16-byte vector path needs F % 4 == 0, ldx % 4 == 0, ldy % 4 == 0 and 16-byte aligned X, Y;
  * anything else takes the scalar path (same results).
  * ws: scratch of at least bns_spmm_workspace_bytes(g, F) bytes (0 when no row is split).
+ * L2 blocking: the feature dimension is processed in column slabs (256/128/64/32 floats) picked so that
+ * x_rows * slab * 4 bytes stays resident in L2 (override: slab_hint, or env BNS_SPMM_SLAB).
  * ----------------------------------------------------------------------------------------------*/
 size_t bns_spmm_workspace_bytes(const bns_graph_t *g, int64_t F);
 int bns_spmm_sum_f32(const bns_graph_t *g,
@@ -96,6 +98,8 @@ int bns_spmm_sum_f32(const bns_graph_t *g,
                      const float *col_scale /*device [n_cols] or NULL*/,
                      const int32_t *row_map /*device [n_rows] or NULL*/,
                      const int32_t *col_map /*device [n_cols - n_direct] or NULL*/, int64_t n_direct,
+                     int64_t x_rows /*rows of X that can be referenced (0 = n_cols); sizes the L2 blocking*/,
+                     int32_t slab_hint /*0 = automatic; 256 | 128 | 64 | 32 forces the column-slab width*/,
                      int accumulate, void *ws, size_t ws_bytes, void *stream);
 
 /* ------------------------------------------------------------------------------------------------

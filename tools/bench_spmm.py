@@ -45,9 +45,17 @@ def main():
     ap.add_argument("--iters", type=int, default=10)
     ap.add_argument("--no-cusparse", action="store_true")
     ap.add_argument("--transpose", action="store_true")
+    ap.add_argument("--slab", type=int, default=0)
+    ap.add_argument("--n", type=int, default=0, help="override node count")
+    ap.add_argument("--e", type=int, default=0, help="override edge count")
     a = ap.parse_args()
     dev = torch.device("cuda:0")
-    fg = make_graph(a.shape, with_feat=False)
+    ov = {}
+    if a.n:
+        ov["n"] = a.n
+    if a.e:
+        ov["e"] = a.e
+    fg = make_graph(a.shape, with_feat=False, **ov)
     if a.parts == 1:
         indptr, idx, n_src = fg.indptr, fg.src, fg.n_nodes
     else:
@@ -61,10 +69,10 @@ def main():
     x = torch.randn(n_src, a.F, device=dev)
     y = torch.empty(n_dst, a.F, device=dev)
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
-    med, best = time_it(lambda: ops.spmm(g, x, y), a.iters, flush)
+    med, best = time_it(lambda: ops.spmm(g, x, y, slab=a.slab), a.iters, flush)
     bytes_alg = 8 * (n_dst + 1) + 4 * nnz + 4 * a.F * n_src + 4 * a.F * n_dst
     bytes_gather = 8 * (n_dst + 1) + 4 * nnz + 4 * a.F * nnz + 4 * a.F * n_dst
-    res = {"case": f"{a.shape}/P{a.parts}/F{a.F}" + ("/T" if a.transpose else ""), "n_dst": n_dst, "n_src": n_src,
+    res = {"case": f"{a.shape}/P{a.parts}/F{a.F}/slab{a.slab}" + ("/T" if a.transpose else ""), "n_dst": n_dst, "n_src": n_src,
            "nnz": nnz, "chunks": g.n_chunks, "split_rows": g.n_split_rows, "ms_median": round(med, 4),
            "ms_best": round(best, 4), "alg_GBs": round(bytes_alg / med / 1e6, 1),
            "alg_frac_of_hbm": round(bytes_alg / (med * 1e-3) / HBM_PEAK, 4),
