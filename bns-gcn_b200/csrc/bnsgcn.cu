@@ -649,10 +649,17 @@ int pick_slab(int64_t F, int64_t x_rows, int32_t forced) {
         int v = atoi(env);
         if (v == 256 || v == 128 || v == 64 || v == 32) return v;
     }
-    const double budget = 0.55 * (double)l2_bytes();      // leave room for the index stream, Y and the other die
-    int slab = 256;
-    while (slab > 32 && (double)x_rows * 4.0 * (double)(slab < F ? slab : F) > budget) slab >>= 1;
-    return slab;
+    // Measured on B200 (profiles/spmm_slab_sweep_r1.md, Reddit-shape, F = 256, 238 MB of sources): slab 256 ->
+    // 10.2 ms, 128 -> 8.1 ms, 64 -> 8.5 ms, 32 -> 14.1 ms; a 51 MB source matrix is fastest unblocked.  So: full
+    // rows while they fit comfortably, else 128 floats (a slab about the size of L2 still wins: the slab-major
+    // order keeps the hot part resident and halves the index re-reads of 64), else 64; never 32.  When even a
+    // 64-float slab cannot be L2-resident the gather is a pure HBM stream and the widest slab is best.
+    const double l2 = (double)l2_bytes(), bytes_per_col = (double)x_rows * 4.0;
+    const int fmax = F >= 256 ? 256 : (F > 64 ? 128 : 64);
+    if (fmax >= 256 && bytes_per_col * 256.0 <= 0.55 * l2) return 256;
+    if (fmax >= 128 && bytes_per_col * 128.0 <= 1.0 * l2) return 128;
+    if (bytes_per_col * 64.0 <= 1.0 * l2) return 64;
+    return fmax;
 }
 
 }  // namespace
