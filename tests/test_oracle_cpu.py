@@ -1,0 +1,125 @@
+"""CPU tests of the oracle (test infrastructure) -- these pin it:
+ * against the golden vectors minted by the reference's own code (tests/golden/make_golden.py),
+ * against the known-answer properties of SURVEY.md §4 (P-invariance, SpMM vs an independent index_add_),
+ * Philox4x32-10 against the published Random123 known-answer vectors."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+
+def _rel(a, b):
+    return ((a.double() - b.double()).norm() / b.double().norm().clamp(min=1e-30)).item()
+
+
+def _oracle_run(cfg, selected_per_epoch):
+    import bns_gcn_b200  # noqa: F401
+    from bns_gcn_b200.data import make_graph, partition_graph
+    from oracle import bns_oracle as O
+    fg = make_graph(cfg["shape"], seed=0, device=torch.device("cpu"))
+    parts = partition_graph(fg, cfg["n_parts"], "random", seed=0, device=torch.device("cpu"))
+
+    def fn(comm, r):
+        rk = O.OracleRank(O.RankInput.from_partition(parts[r]), comm, model=cfg["model"], n_layers=cfg["n_layers"],
+                          n_hidden=cfg["n_hidden"], sampling_rate=cfg["rate"], dropout=0.0, seed=0)
+        for e in range(cfg["epochs"]):
+            rk.epoch(selected=selected_per_epoch[e][r], trace=True)
+        return rk
+    return O.run_threads(cfg["n_parts"], fn)
+
+
+@pytest.mark.parametrize("name", ["graphsage", "gcn"])
+def test_oracle_reproduces_reference_golden(name):
+    """The oracle, fed the index sets the reference drew, reproduces what the reference computed:
+    boundary sets exactly; precomputed features, layer outputs, logits, reduced grads, updated weights to 1e-5."""
+    gold = torch.load(os.path.join(GOLD, f"ref_{name}_p2.pt"))
+    cfg, ranks = gold["config"], gold["ranks"]
+    sel = [[ranks[r]["selected"][e] for r in range(cfg["n_parts"])] for e in range(cfg["epochs"])]
+    out = _oracle_run(cfg, sel)
+    for r, rk in enumerate(out):
+        g = ranks[r]
+        for j, b in enumerate(g["boundary"]):
+            if b is not None:
+                assert torch.equal(rk.boundary[j], b)
+        assert _rel(rk.feat, g["feat0"]) < 1e-6
+        for i, lo in enumerate(g["layer_out"][-1]):
+            assert _rel(rk.trace[f"layer{i}"], lo) < 1e-5, (r, i)
+        assert _rel(rk.trace["logits"], g["logits"][-1]) < 1e-5
+        for k, (p, gp, gg) in enumerate(zip(rk.net.parameters(), g["params"], g["grads"])):
+            assert _rel(p.detach(), gp) < 1e-5, (r, g["param_names"][k])
+            assert _rel(p.grad, gg) < 1e-5, (r, g["param_names"][k])
+        # parameter order / names are the reference's
+        assert [n for n, _ in rk.net.named_parameters()] == g["param_names"]
+
+
+@pytest.mark.parametrize("model", ["graphsage", "gcn"])
+def test_oracle_p_invariance(model):
+    """Sampling rate 1, dropout 0: any partitioning gives the single-partition loss and gradients."""
+    import bns_gcn_b200  # noqa: F401
+    from bns_gcn_b200.data import make_graph, partition_graph
+    from oracle import bns_oracle as O
+    fg = make_graph("tiny", seed=0, device=torch.device("cpu"))
+    ref = None
+    for P in (1, 2, 3):
+        parts = partition_graph(fg, P, "random", seed=0, device=torch.device("cpu"))
+
+        def fn(comm, r):
+            rk = O.OracleRank(O.RankInput.from_partition(parts[r]), comm, model=model, n_layers=3, n_hidden=16,
+                              sampling_rate=1.0, dropout=0.0, seed=0)
+            loss = [rk.epoch(rng=np.random.RandomState(r)) for _ in range(2)]
+            return loss, [p.grad.clone() for p in rk.net.parameters()]
+        res = O.run_threads(P, fn)
+        loss = [sum(x[0][e] for x in res) for e in range(2)]
+        if ref is None:
+            ref = (loss, res[0][1])
+            continue
+        for a, b in zip(loss, ref[0]):
+            assert abs(a - b) < 1e-5 * abs(b)
+        for a, b in zip(res[0][1], ref[1]):
+            assert _rel(a, b) < 1e-5
+
+
+def test_c_spmm_matches_index_add():
+    from oracle import bns_oracle as O
+    g = torch.Generator().manual_seed(0)
+    u = torch.randint(0, 500, (20000,), generator=g)
+    v = torch.randint(0, 300, (20000,), generator=g)
+    x = torch.randn(500, 37, generator=g, requires_grad=True)
+    e = O.EdgeList(u, v, 500, 300)
+    y = O.CopyUSum.apply(e, x)
+    assert _rel(y.detach(), O.copy_u_sum_indexadd(e, x.detach())) < 1e-6
+    w = torch.randn(300, 37, generator=g)
+    (y * w).sum().backward()
+    ref = torch.zeros(500, 37).index_add_(0, u, w[v])
+    assert _rel(x.grad, ref) < 1e-6
+    # empty rows / empty graph
+    e0 = O.EdgeList(torch.empty(0, dtype=torch.int64), torch.empty(0, dtype=torch.int64), 5, 4)
+    assert torch.all(O.CopyUSum.apply(e0, torch.randn(5, 3)) == 0)
+
+
+def test_philox_known_answers():
+    """Random123 kat_vectors for philox4x32-10."""
+    from oracle.philox import philox4x32_10
+    kat = [((0, 0, 0, 0), (0, 0), (0x6627e8d5, 0xe169c58d, 0xbc57ac4c, 0x9b00dbd8)),
+           ((0xffffffff,) * 4, (0xffffffff, 0xffffffff), (0x408f276d, 0x41c83b0e, 0xa20bc7c6, 0x6d5451fd)),
+           ((0x243f6a88, 0x85a308d3, 0x13198a2e, 0x03707344), (0xa4093822, 0x299f31d0),
+            (0xd16cfe09, 0x94fdcceb, 0x5001e420, 0x24126ea1))]
+    for ctr, key, want in kat:
+        got = philox4x32_10(*[np.array([c], dtype=np.uint32) for c in ctr], key[0], key[1])
+        assert tuple(int(x[0]) for x in got) == want
+
+
+def test_philox_sampler_properties():
+    from oracle.philox import sample_boundary
+    b = [np.arange(0, 3000, 3, dtype=np.int64), np.arange(5, 905, dtype=np.int64), np.empty(0, dtype=np.int64)]
+    k = [100, 900, 0]
+    s = sample_boundary(b, k, seed=7, offset=3)
+    for bi, ki, si in zip(b, k, s):
+        assert len(si) == ki and len(np.unique(si)) == ki and np.isin(si, bi).all()
+    assert np.array_equal(np.sort(s[1]), b[1])                   # k == b: a permutation
+    s2 = sample_boundary(b, k, seed=7, offset=4)
+    assert not np.array_equal(s[0], s2[0])
+    assert np.array_equal(s[0], sample_boundary(b, k, seed=7, offset=3)[0])

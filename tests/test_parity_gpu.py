@@ -62,3 +62,33 @@ def test_p_invariance_on_gpu(built):
 
 def test_metis_standin_partition_parity(built):
     _run(shape="tiny", n_parts=3, model="graphsage", sampling_rate=0.5, n_epochs=2, partition_method="metis")
+
+
+@pytest.mark.parametrize("name", ["graphsage", "gcn"])
+def test_cuda_path_reproduces_reference_golden(built, name):
+    """The CUDA path, fed the index sets the REFERENCE drew (tests/golden/make_golden.py ran the reference's own
+    train.run), reproduces the reference's precomputed features, layer outputs, logits, reduced gradients and
+    updated weights within 1e-4, and its boundary sets exactly."""
+    import os
+    from tests.harness import make_args, run_product, _relerr
+    from bns_gcn_b200.data import make_graph, partition_graph
+    gold = torch.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", f"ref_{name}_p2.pt"))
+    cfg, ranks = gold["config"], gold["ranks"]
+    fg = make_graph(cfg["shape"], seed=0)
+    parts = partition_graph(fg, cfg["n_parts"], "random", seed=0)
+    args = make_args(dataset=cfg["shape"], model=cfg["model"], sampling_rate=cfg["rate"], n_layers=cfg["n_layers"],
+                     n_hidden=cfg["n_hidden"], n_partitions=cfg["n_parts"])
+    sel = [[ranks[r]["selected"][e] for r in range(cfg["n_parts"])] for e in range(cfg["epochs"])]
+    out = run_product(parts, args, "cuda:0", cfg["epochs"], selected_per_epoch=sel)
+    for r, o in enumerate(out):
+        g = ranks[r]
+        for j, b in enumerate(g["boundary"]):
+            if b is not None:
+                assert torch.equal(o["boundary"][j], b)
+        assert _relerr(o["feat0"], g["feat0"]) < TOL
+        for i, lo in enumerate(g["layer_out"][-1]):
+            assert _relerr(o["layers"][f"layer{i}"], lo) < TOL, (r, i)
+        assert _relerr(o["logits"], g["logits"][-1]) < TOL
+        for k, (p, gp, gg) in enumerate(zip(o["params"], g["params"], g["grads"])):
+            assert _relerr(p, gp) < TOL, (r, g["param_names"][k])
+            assert _relerr(o["grads"][k], gg) < TOL, (r, g["param_names"][k])
