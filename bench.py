@@ -148,6 +148,9 @@ def run_ours(a):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return float(t.item())
 
+    # one device per process: run backward on this thread (no hand-off to autograd's device thread; it also keeps
+    # the NVTX range below around the backward kernels for the ncu launch list)
+    torch.autograd.set_multithreading_enabled(False)
     epoch = 0
     for _ in range(W):                                   # untimed warm-up
         train.train_epoch(st, epoch)
@@ -177,7 +180,7 @@ def run_ours(a):
     reduce_last = max_over_ranks(ctx.reducer.last_reduce_seconds()) if world > 1 else 0.0
     spmm_ms = sum(s.elapsed_time(e) for s, e, *_ in prof)
     spmm_alg = sum(p[2] for p in prof)
-    spmm_gather = sum(8 * 1 + 4 * p[3] + 4 * p[4] * p[3] for p in prof)
+    spmm_gather = sum(4 * p[3] + 4 * p[4] * p[5] for p in prof)        # p[5]: entries actually gathered (estimate)
     # ---------------- e2e: host-resident inputs, H2D + D2H inside the timed region -------------------
     feat_dev, lab_dev, mask_dev = st.feat, st.labels, st.train_mask
     feat_pin = feat_dev.cpu().pin_memory()

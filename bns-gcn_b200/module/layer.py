@@ -3,10 +3,27 @@
 import math
 
 import torch
+import torch.nn.functional as F
 from torch import nn
 
 from ..graph import FullGraphHandle, PartitionAggregate, PartitionGraph
 from ..ops import AggregateSum
+
+
+# Aggregate-after-transform.  The reference computes  linear(A @ h)  (module/layer.py:38, 91-92).  A is linear, so
+# (A @ h) @ W^T == A @ (h @ W^T): when the layer narrows (out_feats < in_feats, e.g. 256 -> 41 classes) doing the
+# dense transform first shrinks every gathered row of the SpMM -- forward and transpose -- by in/out (6x on the
+# last layer of the Reddit config), at the price of transforming the n_U - n_in halo rows too.  Same math, f32
+# rounding differs at the 1e-7 level (tests pin it against the oracle at 1e-4).  Set to False for the literal order.
+AGGREGATE_AFTER_TRANSFORM = True
+
+
+def _narrow_first(weight, feat):
+    """``feat @ W^T`` with the output padded to a multiple of 4 columns (16-byte SpMM lanes)."""
+    out = weight.shape[0]
+    pad = (-out) % 4
+    w = F.pad(weight, (0, 0, 0, pad)) if pad else weight
+    return F.linear(feat, w), out
 
 
 def _aggregate(graph, feat, rs, cs_u=None):
@@ -41,6 +58,10 @@ class GCNLayer(nn.Module):
         if self.training:
             if self.use_pp:
                 return self.linear(feat)                                            # layer.py:29-30
+            if AGGREGATE_AFTER_TRANSFORM and self.linear.out_features < self.linear.in_features:
+                t, out = _narrow_first(self.linear.weight, feat)
+                h = _aggregate(graph, t, graph.recip(in_norm), graph.recip(out_norm))[:, :out]
+                return h + self.linear.bias if self.linear.bias is not None else h
             h = _aggregate(graph, feat, graph.recip(in_norm), graph.recip(out_norm))  # :32-38
             return self.linear(h)
         in_n = torch.sqrt(graph.in_degrees().float())                                # :40-45
@@ -79,6 +100,11 @@ class GraphSAGELayer(nn.Module):
             if self.use_pp:
                 return self.linear(feat)                                            # layer.py:82-83
             num_dst = graph.num_nodes('_V')
+            if AGGREGATE_AFTER_TRANSFORM and self.linear2.out_features < self.linear2.in_features:
+                t, out = _narrow_first(self.linear2.weight, feat)
+                ah = _aggregate(graph, t, graph.recip(in_norm))[:, :out]
+                res = self.linear1(feat[0:num_dst]) + ah
+                return res + self.linear2.bias if self.linear2.bias is not None else res
             ah = _aggregate(graph, feat, graph.recip(in_norm))                       # :85-91  (sum / degs)
             return self.linear1(feat[0:num_dst]) + self.linear2(ah)                  # :92
         degs = graph.in_degrees()                                                    # :94-102

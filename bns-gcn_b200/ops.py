@@ -18,7 +18,7 @@ from . import _lib
 from ._lib import check, lib
 
 
-# bench.py sets this to a list to collect (start_event, end_event, algorithmic_bytes, nnz, F) per SpMM launch
+# bench.py sets this to a list to collect (start_event, end_event, algorithmic_bytes, nnz, F, live_nnz) per launch
 PROFILE = None
 
 
@@ -147,7 +147,13 @@ def spmm(g: DeviceGraph, x: torch.Tensor, out: Optional[torch.Tensor] = None, *,
         ev1.record(torch.cuda.current_stream(x.device))
         # every distinct operand byte once -- row offsets, column ids, source rows, output rows
         alg = 8 * (g.n_rows + 1) + 4 * g.nnz + 4 * F * x.shape[0] + 4 * F * out.shape[0]
-        prof.append((ev0, ev1, alg, g.nnz, F))
+        # entries whose source row is really gathered: all of them, or (sampled halo) the mapped fraction
+        live = g.nnz
+        if col_map is not None and g.n_cols > n_direct:
+            live = int(g.nnz * min(1.0, max(x.shape[0] - 0, 0) / max(g.n_cols - n_direct, 1)))
+        if row_map is not None:
+            live = int(g.nnz * min(1.0, out.shape[0] / max(g.n_rows, 1)))
+        prof.append((ev0, ev1, alg, g.nnz, F, live))
     return out
 
 
