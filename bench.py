@@ -133,7 +133,9 @@ def run_ours(a):
     part, gstats = build_partition(a.shape, world, rank, dev)
     args = make_args(world, a.backend, {"n_feat": part.meta["n_feat"], "n_class": part.meta["n_class"],
                                         "n_train": part.meta["n_train"], "dataset": a.shape})
-    st = train.setup(part.graph, part.node_dict, part.gpb, args, dev)
+    import contextlib
+    with contextlib.redirect_stdout(sys.stderr):          # stdout carries exactly one JSON line
+        st = train.setup(part.graph, part.node_dict, part.gpb, args, dev)
     torch.cuda.synchronize(dev)
 
     def barrier():
