@@ -19,7 +19,14 @@ AGGREGATE_AFTER_TRANSFORM = True
 
 
 def _narrow_first(weight, feat):
-    """``feat @ W^T`` with the output padded to a multiple of 4 columns (16-byte SpMM lanes)."""
+    """``feat @ W^T`` with the output padded to a multiple of 4 columns (16-byte SpMM lanes).
+
+    This reads EVERY row of ``feat`` -- including the halo rows an overlapped exchange may still be writing -- so it
+    first makes the current stream wait for that exchange (``Buffer.update(..., overlap=True)`` leaves the event on
+    the tensor)."""
+    ready = getattr(feat, '_bns_ready', None)
+    if ready is not None:
+        torch.cuda.current_stream(feat.device).wait_event(ready)
     out = weight.shape[0]
     pad = (-out) % 4
     w = F.pad(weight, (0, 0, 0, pad)) if pad else weight
