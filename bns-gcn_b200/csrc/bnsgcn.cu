@@ -1059,6 +1059,16 @@ extern "C" int bns_p2p_create(bns_p2p_t **out, int32_t rank, int32_t world, size
     p->peer_slab[rank] = p->slab;
     p->peer_flags[rank] = p->flags;
     p->peer_slab_bytes[rank] = p->slab_bytes;
+    // CUDA loads a kernel's code lazily at its first launch, and that load synchronises the context: a first-ever
+    // put launched while a flag wait is spinning in the same context would wait for the wait.  Load them now.
+    cudaFuncAttributes fa;
+    cudaFuncGetAttributes(&fa, p2p_put_rows_kernel<true>);
+    cudaFuncGetAttributes(&fa, p2p_put_rows_kernel<false>);
+    cudaFuncGetAttributes(&fa, p2p_wait_kernel);
+    cudaFuncGetAttributes(&fa, rows_kernel<true, true>);
+    cudaFuncGetAttributes(&fa, rows_kernel<false, true>);
+    cudaFuncGetAttributes(&fa, rows_kernel<true, false>);
+    cudaFuncGetAttributes(&fa, rows_kernel<false, false>);
     *out = p;
     return BNS_OK;
 }

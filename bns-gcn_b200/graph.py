@@ -73,7 +73,10 @@ class PartitionAggregate(torch.autograd.Function):
         ctx.g, ctx.rs, ctx.cs_in, ctx.cs_halo = g, rs, cs_in, cs_halo
         ctx.n_u = h_u.shape[0]
         h_u = h_u.contiguous()
-        y = ops.spmm(g.a_in, h_u, row_scale=rs, col_scale=cs_in)
+        # a per-source scale is applied ONCE per row here, not once per edge inside the gather (each source row is
+        # gathered ~degree times; the fused col_scale path costs an extra scalar gather per edge)
+        x_in = h_u if cs_in is None else h_u[:g.n_in] * cs_in.unsqueeze(1)
+        y = ops.spmm(g.a_in, x_in, row_scale=rs)
         if ready is not None:
             torch.cuda.current_stream(h_u.device).wait_event(ready)
         if g.a_out is not None and ctx.n_u > g.n_in:
@@ -84,12 +87,12 @@ class PartitionAggregate(torch.autograd.Function):
     @staticmethod
     def backward(ctx, dy):
         g = ctx.g
-        dy = dy.contiguous()
+        dy = dy.contiguous() if ctx.rs is None else dy * ctx.rs.unsqueeze(1)      # pre-scale once (see forward)
         du = torch.empty(ctx.n_u, dy.shape[1], dtype=torch.float32, device=dy.device)
         if ctx.n_u > g.n_in:
             tail = du[g.n_in:]
             tail.zero_()
             if g.a_out_t is not None:
-                ops.spmm(g.a_out_t, dy, tail, row_scale=ctx.cs_halo, col_scale=ctx.rs, row_map=g.slot)
-        ops.spmm(g.a_in_t, dy, du[:g.n_in], row_scale=ctx.cs_in, col_scale=ctx.rs)
+                ops.spmm(g.a_out_t, dy, tail, row_scale=ctx.cs_halo, row_map=g.slot)
+        ops.spmm(g.a_in_t, dy, du[:g.n_in], row_scale=ctx.cs_in)
         return du, None, None, None, None, None

@@ -167,12 +167,14 @@ class AggregateSum(torch.autograd.Function):
     @staticmethod
     def forward(ctx, x, g: DeviceGraph, row_scale, col_scale):
         ctx.g, ctx.rs, ctx.cs = g, row_scale, col_scale
-        return spmm(g, x.contiguous(), row_scale=row_scale, col_scale=col_scale)
+        x = x.contiguous() if col_scale is None else x * col_scale.unsqueeze(1)   # scale once per row, not per edge
+        return spmm(g, x, row_scale=row_scale)
 
     @staticmethod
     def backward(ctx, dy):
         gt = ctx.g.transpose()
-        dx = spmm(gt, dy.contiguous(), row_scale=ctx.cs, col_scale=ctx.rs)
+        dy = dy.contiguous() if ctx.rs is None else dy * ctx.rs.unsqueeze(1)
+        dx = spmm(gt, dy, row_scale=ctx.cs)
         return dx, None, None, None
 
 
