@@ -87,6 +87,20 @@ class ThreadComm:
         if out.is_cuda:                       # keep the sender's tensor alive until the copy ran
             t.record_stream(torch.cuda.current_stream(out.device))
 
+    def post_event(self, dst: int, tag: int, ev):
+        """Hand a recorded CUDA event to rank ``dst`` (in-process ranks only; see Buffer p2p transport)."""
+        self.fabric.box(self.rank, dst, tag).put((None, ev))
+
+    def take_event(self, src: int, tag: int):
+        box, waited = self.fabric.box(src, self.rank, tag), 0.0
+        while True:
+            try:
+                return box.get(timeout=0.5)[1]
+            except queue.Empty:
+                waited += 0.5
+                if self.fabric.failed or waited > 120:
+                    raise RuntimeError(f"rank {self.rank}: no event from rank {src} (tag {tag})")
+
     def alltoall(self, send, recv, tag: int = 0):
         """``recv[j] <- send_j_on_rank_j[self.rank]`` for all peers j (entries for self / None are skipped)."""
         for i in range(1, self.size):

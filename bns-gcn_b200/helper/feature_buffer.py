@@ -149,6 +149,21 @@ class Buffer(object):
                     check(lib.bns_p2p_import(h, j, table[j]["handle"], table[j]["slab_bytes"]), "bns_p2p_import")
         c.barrier()
 
+    # Ranks that are THREADS of one process share a CUDA context, where a kernel spinning on a flag can block the
+    # very launch that would set it (lazy module loading and stream->hardware-queue aliasing both synchronise the
+    # context).  There, the producer hands over an event recorded after its put and the consumer's stream waits on
+    # it BEFORE the flag-wait kernel is launched, so that kernel finds the flag already set and never spins.  With
+    # one process per GPU (the deployment shape) these two calls do nothing and the flag is the only signal.
+    def _post_put_event(self, peer, tag, stream):
+        if self._comm.kind == "thread":
+            ev = torch.cuda.Event()
+            ev.record(stream)
+            self._comm.post_event(peer, tag, ev)
+
+    def _await_put_event(self, peer, tag, stream):
+        if self._comm.kind == "thread":
+            stream.wait_event(self._comm.take_event(peer, tag))
+
     def _flag(self, layer, backward, src):
         return ((layer - 1) * 2 + (1 if backward else 0)) * self._size + src
 
@@ -208,8 +223,10 @@ class Buffer(object):
                                                        F, ops._ptr(self._selected[j]), self._send_shape[j],
                                                        float(self._ratio[j]), self._flag(layer, False, self._rank), seq,
                                                        cs.cuda_stream), "bns_p2p_put_rows_f32")
+                        self._post_put_event(j, 2000 + 2 * layer, cs)
                     for i in range(1, self._size):
                         j = (self._rank - i + self._size) % self._size
+                        self._await_put_event(j, 2000 + 2 * layer, cs)
                         check(lib.bns_p2p_wait_flag(self._p2p, self._flag(layer, False, j), seq, cs.cuda_stream),
                               "bns_p2p_wait_flag")
             ready.record(cs)
@@ -248,10 +265,12 @@ class Buffer(object):
                                                        None, self._recv_shape[j], 1.0,
                                                        self._flag(layer, True, self._rank), seq, cs.cuda_stream),
                               "bns_p2p_put_rows_f32")
+                        self._post_put_event(j, 2001 + 2 * layer, cs)
                     recv = [None] * self._size
                     bwd = self._slab_view(self._bwd_off[layer - 1], max(self._send_total, 1))
                     for i in range(1, self._size):
                         j = (self._rank - i + self._size) % self._size
+                        self._await_put_event(j, 2001 + 2 * layer, cs)
                         check(lib.bns_p2p_wait_flag(self._p2p, self._flag(layer, True, j), seq, cs.cuda_stream),
                               "bns_p2p_wait_flag")
                         recv[j] = bwd[self._send_begin[j]:self._send_begin[j] + self._send_shape[j], :F]

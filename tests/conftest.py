@@ -1,13 +1,6 @@
 import os
 import sys
 
-# P in-process ranks x (main + comm + reducer) streams must not alias onto the default 8 hardware queues: a
-# device-side flag wait (p2p transport) queued in front of the put it waits for would deadlock.  Must be set
-# before CUDA initialises.  (One process per GPU -- the deployment shape -- uses 3-4 streams and does not need it.)
-os.environ.setdefault("CUDA_DEVICE_MAX_CONNECTIONS", "32")
-# Same reason, second mechanism: CUDA loads kernel code lazily at first launch and the load synchronises the
-# context, so a rank's first-ever launch of ANY kernel would block behind another rank's spinning flag wait.
-os.environ.setdefault("CUDA_MODULE_LOADING", "EAGER")
 
 import pytest
 
