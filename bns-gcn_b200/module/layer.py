@@ -7,6 +7,7 @@ import torch.nn.functional as F
 from torch import nn
 
 from ..graph import FullGraphHandle, PartitionAggregate, PartitionGraph
+from . import dense
 from ..ops import AggregateSum
 
 
@@ -30,7 +31,7 @@ def _narrow_first(weight, feat):
     out = weight.shape[0]
     pad = (-out) % 4
     w = F.pad(weight, (0, 0, 0, pad)) if pad else weight
-    return F.linear(feat, w), out
+    return dense.linear(feat, w), out
 
 
 def _aggregate(graph, feat, rs, cs_u=None):
@@ -59,21 +60,25 @@ class GCNLayer(nn.Module):
         if self.linear.bias is not None:
             self.linear.bias.data.uniform_(-stdv, stdv)
 
+    @staticmethod
+    def _lin(lin, x):
+        return dense.linear(x, lin.weight, lin.bias)
+
     def forward(self, graph, feat, in_norm, out_norm):
         """``out_norm``: sqrt(out_deg) of every *local* node (inner then halo, static) -- the reference rebuilds a
         U-ordered copy of it every epoch (train.py:245-253), which the slot map makes unnecessary."""
         if self.training:
             if self.use_pp:
-                return self.linear(feat)                                            # layer.py:29-30
+                return self._lin(self.linear, feat)                                 # layer.py:29-30
             if AGGREGATE_AFTER_TRANSFORM and self.linear.out_features < self.linear.in_features:
                 t, out = _narrow_first(self.linear.weight, feat)
                 h = _aggregate(graph, t, graph.recip(in_norm), graph.recip(out_norm))[:, :out]
                 return h + self.linear.bias if self.linear.bias is not None else h
             h = _aggregate(graph, feat, graph.recip(in_norm), graph.recip(out_norm))  # :32-38
-            return self.linear(h)
+            return self._lin(self.linear, h)
         in_n = torch.sqrt(graph.in_degrees().float())                                # :40-45
         out_n = torch.sqrt(graph.out_degrees().float())
-        return self.linear(_aggregate(graph, feat, 1.0 / in_n, 1.0 / out_n))
+        return self._lin(self.linear, _aggregate(graph, feat, 1.0 / in_n, 1.0 / out_n))
 
 
 class GraphSAGELayer(nn.Module):
@@ -102,20 +107,24 @@ class GraphSAGELayer(nn.Module):
                 self.linear1.bias.data.uniform_(-stdv, stdv)
                 self.linear2.bias.data.uniform_(-stdv, stdv)
 
+    @staticmethod
+    def _lin(lin, x):
+        return dense.linear(x, lin.weight, lin.bias)
+
     def forward(self, graph, feat, in_norm):
         if self.training:
             if self.use_pp:
-                return self.linear(feat)                                            # layer.py:82-83
+                return self._lin(self.linear, feat)                                 # layer.py:82-83
             num_dst = graph.num_nodes('_V')
             if AGGREGATE_AFTER_TRANSFORM and self.linear2.out_features < self.linear2.in_features:
                 t, out = _narrow_first(self.linear2.weight, feat)
                 ah = _aggregate(graph, t, graph.recip(in_norm))[:, :out]
-                res = self.linear1(feat[0:num_dst]) + ah
+                res = self._lin(self.linear1, feat[0:num_dst]) + ah
                 return res + self.linear2.bias if self.linear2.bias is not None else res
             ah = _aggregate(graph, feat, graph.recip(in_norm))                       # :85-91  (sum / degs)
-            return self.linear1(feat[0:num_dst]) + self.linear2(ah)                  # :92
+            return self._lin(self.linear1, feat[0:num_dst]) + self._lin(self.linear2, ah)  # :92
         degs = graph.in_degrees()                                                    # :94-102
         ah = _aggregate(graph, feat, 1.0 / degs.float())
         if self.use_pp:
-            return self.linear(torch.cat((feat, ah), dim=1))
-        return self.linear1(feat) + self.linear2(ah)
+            return self._lin(self.linear, torch.cat((feat, ah), dim=1))
+        return self._lin(self.linear1, feat) + self._lin(self.linear2, ah)
