@@ -9,14 +9,16 @@ relative, i.e. f32-level accuracy.  The GEMMs themselves are library calls (cuBL
 plain GEMMs); a hand-written tcgen05 kernel with the LayerNorm / ReLU / dropout epilogue fused is the SURVEY §8(f)
 rank-2 follow-up.
 
-``MODE``: "3xtf32" (default) | "fp32" (the literal reference precision).
+``MODE`` (env BNS_DENSE): "fp32" (default, the reference precision) | "3xtf32".  Measured on B200 (round 1, Reddit
+shape, N=1): 3xtf32 built from three cuBLAS TF32 GEMMs + the split passes is SLOWER than fp32 SIMT cuBLAS (44.2 vs
+37.8 ms/epoch), so it is off by default; the win needs the split fused into a hand-written tcgen05 kernel.
 """
 import os
 
 import torch
 import torch.nn.functional as F
 
-MODE = os.environ.get("BNS_DENSE", "3xtf32")
+MODE = os.environ.get("BNS_DENSE", "fp32")
 
 
 def _split(t: torch.Tensor):
