@@ -92,3 +92,32 @@ def test_cuda_path_reproduces_reference_golden(built, name):
         for k, (p, gp, gg) in enumerate(zip(o["params"], g["params"], g["grads"])):
             assert _relerr(p, gp) < TOL, (r, g["param_names"][k])
             assert _relerr(o["grads"][k], gg) < TOL, (r, g["param_names"][k])
+
+
+@pytest.mark.parametrize("model", ["graphsage", "gcn"])
+def test_eval_branch_full_graph(built, model):
+    """module/layer.py:39-45, 93-102: evaluation on the full homogeneous graph (degrees from the graph itself)."""
+    from bns_gcn_b200 import ops
+    from bns_gcn_b200.data import make_graph
+    from bns_gcn_b200.graph import FullGraphHandle
+    from bns_gcn_b200.module.model import GCN, GraphSAGE
+    from oracle import bns_oracle as O
+    import torch.nn.functional as F
+    dev = torch.device("cuda:0")
+    fg = make_graph("tiny", seed=3)
+    layer_size = [fg.n_feat, 16, 16, fg.n_class]
+    torch.manual_seed(0)
+    net = (GraphSAGE if model == "graphsage" else GCN)(layer_size, F.relu, use_pp=False, dropout=0.5, norm="layer")
+    torch.manual_seed(0)
+    ref = O.build_model(model, layer_size, False, 0.5, "layer", None, 0)
+    for a, b in zip(net.parameters(), ref.parameters()):
+        assert torch.equal(a, b)                                   # same init order as the reference
+    net.to(dev).eval()
+    ref.eval()
+    a = ops.DeviceGraph.from_csr(fg.indptr.to(dev), fg.src.int().to(dev), fg.n_nodes)
+    g = FullGraphHandle(a, fg.in_degrees().to(dev), fg.out_degrees().to(dev))
+    with torch.no_grad():
+        out = net(g, fg.feat.to(dev)).cpu()
+        e = O.EdgeList(fg.src, fg.dst(), fg.n_nodes, fg.n_nodes)
+        want = ref(e, fg.feat)
+    assert ((out - want).norm() / want.norm()).item() < TOL
