@@ -220,6 +220,28 @@ def run_ours(a):
     e2e_s = max_over_ranks(time.perf_counter() - t0)
     st.feat, st.labels, st.train_mask = feat_dev, lab_dev, mask_dev
 
+    if a.profile and rank == 0:                            # diagnosis only (kineto); never a reported number
+        from torch.profiler import ProfilerActivity, profile
+        with profile(activities=[ProfilerActivity.CPU, ProfilerActivity.CUDA]) as prof_:
+            for _ in range(3):
+                train.train_epoch(st, epoch)
+                epoch += 1
+            torch.cuda.synchronize(dev)
+        with open(a.profile, "w") as f:
+            f.write(prof_.key_averages().table(sort_by="cuda_time_total", row_limit=45, max_name_column_width=70))
+    elif a.profile:
+        for _ in range(3):
+            train.train_epoch(st, epoch)
+            epoch += 1
+    # host-side enqueue time of one epoch (no sync inside): if it is close to ms_per_step the step is CPU-bound
+    barrier()
+    th = time.perf_counter()
+    for _ in range(5):
+        train.train_epoch(st, epoch)
+        epoch += 1
+    host_ms = (time.perf_counter() - th) / 5 * 1e3
+    barrier()
+
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -238,7 +260,7 @@ def run_ours(a):
                    "parallelism": f"partition-parallel x{world}", "exchange": a.backend,
                    "n_in_rank0": part.graph.n_in, "n_halo_rank0": part.graph.n_halo,
                    "local_edges_rank0": part.graph.num_edges()},
-        "comm_s_per_epoch": comm_last, "reduce_s_per_epoch": reduce_last,
+        "comm_s_per_epoch": comm_last, "reduce_s_per_epoch": reduce_last, "host_enqueue_ms_per_step": host_ms,
         "e2e": {"value": K / e2e_s, "unit": "epochs/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": 4,
                 "note": "features+labels+mask copied from pinned host memory every epoch (prefetched one step ahead on "
                         "a copy stream), loss read back every epoch"},
@@ -331,6 +353,7 @@ def main():
     ap.add_argument("--shape", default=WORKLOAD["shape"])
     ap.add_argument("--backend", default="nccl", choices=["nccl", "p2p"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--profile", default="", help="write a torch.profiler kernel table of 3 epochs (rank 0) to this file")
     a = ap.parse_args()
     if a.impl == "reference":
         run_reference(a)
