@@ -157,29 +157,61 @@ def run_ours(a):
     for _ in range(W):                                   # untimed warm-up
         train.train_epoch(st, epoch)
         epoch += 1
-    # ---------------- timed region: device-resident inputs -------------------------------------------
-    clocks = ClockSampler(local)
-    barrier()
-    if rank == 0:
-        clocks.start()
-    ops.PROFILE = prof = []
-    n0 = lib.bns_launch_count()
-    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    barrier()
-    ev0.record(torch.cuda.current_stream(dev))
-    torch.cuda.nvtx.range_push("bns_timed")              # ncu --nvtx --nvtx-include "bns_timed/" lists one step
-    for _ in range(K):
+
+    def timed(step_fn, n_steps, profile_spmm):
+        """n_steps of step_fn between barriers; device time by CUDA events, max over ranks."""
+        barrier()
+        if profile_spmm:
+            ops.PROFILE = []
+        c0 = lib.bns_launch_count()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        barrier()
+        e0.record(torch.cuda.current_stream(dev))
+        torch.cuda.nvtx.range_push("bns_timed")          # ncu --nvtx --nvtx-include "bns_timed/" lists the steps
+        for _ in range(n_steps):
+            step_fn()
+        torch.cuda.nvtx.range_pop()
+        e1.record(torch.cuda.current_stream(dev))
+        barrier()
+        pr, ops.PROFILE = ops.PROFILE, None
+        return max_over_ranks(e0.elapsed_time(e1)), lib.bns_launch_count() - c0, pr
+
+    def eager_step():
+        nonlocal epoch
         train.train_epoch(st, epoch)
         epoch += 1
-    torch.cuda.nvtx.range_pop()
-    ev1.record(torch.cuda.current_stream(dev))
-    barrier()
-    ops.PROFILE = None
-    n1 = lib.bns_launch_count()
-    clk = clocks.stop() if rank == 0 else None
-    dev_ms = max_over_ranks(ev0.elapsed_time(ev1))
+
+    # ---------------- eager pass: per-kernel CUDA events (roofline), Comm(s)/Reduce(s) -----------------------
+    clocks = ClockSampler(local)
+    if rank == 0:
+        clocks.start()
+    K_eager = K if a.mode == "eager" else min(K, 5)
+    eager_ms, eager_launches, prof = timed(eager_step, K_eager, True)
     comm_last = max_over_ranks(comm_timer.tot_time()) if world > 1 else 0.0     # Comm(s) of the last epoch
     reduce_last = max_over_ranks(ctx.reducer.last_reduce_seconds()) if world > 1 else 0.0
+    launches_per_step = eager_launches / K_eager
+    mode = "eager"
+    dev_ms, n_launch = eager_ms * K / K_eager, eager_launches * K // K_eager
+    step_fn = eager_step
+    # ---------------- timed region proper: the epoch replayed from one CUDA graph ----------------------------
+    if a.mode == "graph":
+        try:
+            ge = train.GraphedEpoch(st, warmup=1)
+            epoch += 1
+            for _ in range(2):
+                ge()
+            step_fn, mode = ge, "cuda-graph"
+            dev_ms, _, _ = timed(step_fn, K, False)
+            n_launch = int(launches_per_step * K)        # the same kernels, launched by the graph
+        except Exception as e:                           # noqa: BLE001
+            import traceback
+            traceback.print_exc(file=sys.stderr)
+            print(f"[bench] CUDA-graph capture failed, staying eager: {type(e).__name__}: {e}", file=sys.stderr)
+            if a.strict:
+                raise
+            dev_ms, n_launch, _ = timed(eager_step, K, False)
+    n0, n1 = 0, n_launch
+    clk = clocks.stop() if rank == 0 else None
     spmm_ms = sum(s.elapsed_time(e) for s, e, *_ in prof)
     spmm_alg = sum(p[2] for p in prof)
     spmm_gather = sum(4 * p[3] + 4 * p[4] * p[5] for p in prof)        # p[5]: entries actually gathered (estimate)
@@ -211,10 +243,15 @@ def run_ours(a):
         if i + 1 < K:
             prefetch(i + 1)                              # next step's inputs stream in behind this step's compute
         torch.cuda.current_stream(dev).wait_event(ready[i % 2])
-        st.feat, st.labels, st.train_mask = bufs[i % 2]
-        loss = train.train_epoch(st, epoch)
-        consumed[i % 2].record(torch.cuda.current_stream(dev))
-        epoch += 1
+        if mode == "cuda-graph":                         # the graph reads fixed addresses: stage -> device copy
+            feat_dev.copy_(bufs[i % 2][0]); lab_dev.copy_(bufs[i % 2][1]); mask_dev.copy_(bufs[i % 2][2])
+            consumed[i % 2].record(torch.cuda.current_stream(dev))
+            loss = step_fn()
+        else:
+            st.feat, st.labels, st.train_mask = bufs[i % 2]
+            loss = train.train_epoch(st, epoch)
+            consumed[i % 2].record(torch.cuda.current_stream(dev))
+            epoch += 1
         _ = loss.item()                                  # D2H read of the step's result
     barrier()
     e2e_s = max_over_ranks(time.perf_counter() - t0)
@@ -224,21 +261,18 @@ def run_ours(a):
         from torch.profiler import ProfilerActivity, profile
         with profile(activities=[ProfilerActivity.CPU, ProfilerActivity.CUDA]) as prof_:
             for _ in range(3):
-                train.train_epoch(st, epoch)
-                epoch += 1
+                step_fn()
             torch.cuda.synchronize(dev)
         with open(a.profile, "w") as f:
             f.write(prof_.key_averages().table(sort_by="cuda_time_total", row_limit=45, max_name_column_width=70))
     elif a.profile:
         for _ in range(3):
-            train.train_epoch(st, epoch)
-            epoch += 1
+            step_fn()
     # host-side enqueue time of one epoch (no sync inside): if it is close to ms_per_step the step is CPU-bound
     barrier()
     th = time.perf_counter()
     for _ in range(5):
-        train.train_epoch(st, epoch)
-        epoch += 1
+        step_fn()
     host_ms = (time.perf_counter() - th) / 5 * 1e3
     barrier()
 
@@ -257,10 +291,11 @@ def run_ours(a):
                                f"{gstats['n_edges']} edges, {gstats['n_feat']} feat, 41 classes; GraphSAGE 3-layer hidden 256 "
                                f"--use-pp, sampling-rate 0.1, dropout 0.5, {world} random partition(s); "
                                "inputs (1.1 GB features / rank-count) exceed L2, no flush needed",
-                   "parallelism": f"partition-parallel x{world}", "exchange": a.backend,
+                   "parallelism": f"partition-parallel x{world}", "exchange": a.backend, "execution": mode,
                    "n_in_rank0": part.graph.n_in, "n_halo_rank0": part.graph.n_halo,
                    "local_edges_rank0": part.graph.num_edges()},
         "comm_s_per_epoch": comm_last, "reduce_s_per_epoch": reduce_last, "host_enqueue_ms_per_step": host_ms,
+        "eager_ms_per_step": eager_ms / K_eager,
         "e2e": {"value": K / e2e_s, "unit": "epochs/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": 4,
                 "note": "features+labels+mask copied from pinned host memory every epoch (prefetched one step ahead on "
                         "a copy stream), loss read back every epoch"},
@@ -269,9 +304,9 @@ def run_ours(a):
         "roofline": {"bound": "hbm", "kernel": "spmm_kernel (bns_spmm_sum_f32)", "achieved": ach, "peak": peak,
                      "unit": "GB/s", "frac": ach / peak, "traffic": None, "peak_source": peak_src,
                      "launches_timed": len(prof), "avg_launch_ms": spmm_ms / n_spmm,
-                     "share_of_step": spmm_ms / dev_ms if dev_ms else None,
+                     "share_of_step": spmm_ms / eager_ms if eager_ms else None,
                      "gather_GBs": spmm_gather / (spmm_ms * 1e-3) / 1e9 if spmm_ms > 0 else 0.0,
-                     "note": "achieved = algorithmic bytes (each distinct operand byte once, SURVEY 8d) / CUDA-event time; "
+                     "note": "per-launch CUDA events from the eager pass of the same step inside this run (events cannot sit between nodes of the captured graph); achieved = algorithmic bytes (each distinct operand byte once, SURVEY 8d) / CUDA-event time; "
                              "gather_GBs counts one 4F-byte row read per edge (what actually crosses L2->SM): that is the "
                              "binding resource on this degree-492 graph, see DESIGN.md"},
     }
@@ -351,8 +386,11 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--shape", default=WORKLOAD["shape"])
-    ap.add_argument("--backend", default="nccl", choices=["nccl", "p2p"])
+    ap.add_argument("--backend", default="p2p", choices=["nccl", "p2p"])
+    ap.add_argument("--mode", default="graph", choices=["graph", "eager"],
+                    help="graph: the epoch is captured once into a CUDA graph and replayed (default); eager: launched op by op")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--strict", action="store_true", help="fail instead of falling back to eager when capture fails")
     ap.add_argument("--profile", default="", help="write a torch.profiler kernel table of 3 epochs (rank 0) to this file")
     a = ap.parse_args()
     if a.impl == "reference":

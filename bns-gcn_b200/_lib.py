@@ -37,7 +37,7 @@ SIGNATURES = {
     "bns_copy_rows_f32": (c_int, [c_void_p, c_int64, c_void_p, c_int64, c_int64, c_int64, c_void_p]),
     "bns_sample_workspace_bytes": (c_size_t, [c_int64]),
     "bns_sample_boundary": (c_int, [c_void_p, c_void_p, c_void_p, c_int32, c_int64, c_int64, c_uint64, c_uint64,
-                                    c_void_p, c_void_p, c_size_t, c_void_p]),
+                                    c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),
     "bns_fill_i32": (c_int, [c_void_p, c_int64, c_int32, c_void_p]),
     "bns_halo_slot_update": (c_int, [c_void_p, c_void_p, c_int64, c_int64, c_int32, c_void_p, c_void_p]),
     "bns_p2p_create": (c_int, [POINTER(c_void_p), c_int32, c_int32, c_size_t, c_int32]),
@@ -47,8 +47,8 @@ SIGNATURES = {
     "bns_p2p_import": (c_int, [c_void_p, c_int32, c_void_p, c_size_t]),
     "bns_p2p_set_peer": (c_int, [c_void_p, c_int32, c_void_p, c_void_p, c_size_t]),
     "bns_p2p_put_rows_f32": (c_int, [c_void_p, c_int32, c_size_t, c_int64, c_void_p, c_int64, c_int64, c_void_p,
-                                     c_int64, c_float, c_int32, c_uint64, c_void_p]),
-    "bns_p2p_wait_flag": (c_int, [c_void_p, c_int32, c_uint64, c_void_p]),
+                                     c_int64, c_float, c_int32, c_uint64, c_void_p, c_void_p]),
+    "bns_p2p_wait_flag": (c_int, [c_void_p, c_int32, c_uint64, c_void_p, c_void_p]),
 }
 
 

@@ -828,9 +828,11 @@ __device__ __forceinline__ void philox4x32_10(uint32_t c0, uint32_t c1, uint32_t
 }
 
 __global__ void sample_keys_kernel(const int64_t *__restrict__ seg_begin, int32_t n_seg, int64_t B, uint64_t seed,
-                                   uint64_t offset, uint64_t *__restrict__ keys, int32_t *__restrict__ vals) {
+                                   uint64_t offset, const uint64_t *__restrict__ offset_dev,
+                                   uint64_t *__restrict__ keys, int32_t *__restrict__ vals) {
     const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
     if (i >= B) return;
+    if (offset_dev) offset += *offset_dev;      // CUDA-graph replays: the epoch counter lives on the device
     int32_t lo = 0, hi = n_seg;   // segment s with seg_begin[s] <= i < seg_begin[s+1]
     while (hi - lo > 1) {
         const int32_t mid = (lo + hi) >> 1;
@@ -886,6 +888,7 @@ extern "C" size_t bns_sample_workspace_bytes(int64_t B) { return sample_layout(B
 
 extern "C" int bns_sample_boundary(const int64_t *boundary_cat, const int64_t *seg_begin, const int64_t *out_begin,
                                    int32_t n_seg, int64_t B, int64_t K_total, uint64_t seed, uint64_t offset,
+                                   const uint64_t *offset_dev,
                                    int64_t *selected, void *ws, size_t ws_bytes, void *stream) {
     BNS_REQUIRE(n_seg >= 0 && n_seg <= 255, "bns_sample_boundary: n_seg must be in [0, 255]");
     BNS_REQUIRE(B >= 0 && K_total >= 0 && K_total <= B, "bns_sample_boundary: need 0 <= K_total <= B");
@@ -901,7 +904,7 @@ extern "C" int bns_sample_boundary(const int64_t *boundary_cat, const int64_t *s
     int32_t *vals_in = reinterpret_cast<int32_t *>(base + l.vals_in);
     int32_t *vals_out = reinterpret_cast<int32_t *>(base + l.vals_out);
     cudaStream_t st = as_stream(stream);
-    sample_keys_kernel<<<(unsigned)((B + 255) / 256), 256, 0, st>>>(seg_begin, n_seg, B, seed, offset, keys_in, vals_in);
+    sample_keys_kernel<<<(unsigned)((B + 255) / 256), 256, 0, st>>>(seg_begin, n_seg, B, seed, offset, offset_dev, keys_in, vals_in);
     size_t tb = l.tmp_bytes;
     BNS_CUDA(cub::DeviceRadixSort::SortPairs(base + l.tmp, tb, keys_in, keys_out, vals_in, vals_out, (int)B, 0, 64, st));
     sample_take_kernel<<<(unsigned)((K_total + 255) / 256), 256, 0, st>>>(boundary_cat, seg_begin, out_begin, n_seg,
@@ -983,7 +986,8 @@ template <bool VEC>
 __global__ void __launch_bounds__(kThreads) p2p_put_rows_kernel(const float *__restrict__ H, int64_t ldh, int32_t F,
                                                                const int64_t *__restrict__ idx, int64_t k, float div,
                                                                float *remote, int64_t ldr, unsigned long long *flag,
-                                                               unsigned long long flag_value, unsigned int *ticket) {
+                                                               unsigned long long flag_value,
+                                                               const unsigned long long *flag_value_dev, unsigned int *ticket) {
     const int lane = threadIdx.x & 31;
     const int64_t warps_total = (int64_t)gridDim.x * kWarps;
     for (int64_t i = (int64_t)blockIdx.x * kWarps + (threadIdx.x >> 5); i < k; i += warps_total) {
@@ -1007,7 +1011,7 @@ __global__ void __launch_bounds__(kThreads) p2p_put_rows_kernel(const float *__r
         if (done == gridDim.x - 1) {
             *ticket = 0;               // re-arm for the next launch on this stream
             __threadfence_system();
-            st_release_sys(flag, flag_value);
+            st_release_sys(flag, flag_value + (flag_value_dev ? *flag_value_dev : 0ull));
         }
     }
 }
@@ -1019,8 +1023,10 @@ __device__ __forceinline__ unsigned long long global_ns() {
 }
 
 // Bounded spin: a peer that never signals (it failed, or the schedule is wrong) must not hang the GPU.
-__global__ void p2p_wait_kernel(const unsigned long long *flag, unsigned long long value, unsigned long long timeout_ns) {
+__global__ void p2p_wait_kernel(const unsigned long long *flag, unsigned long long value,
+                                const unsigned long long *value_dev, unsigned long long timeout_ns) {
     if (threadIdx.x == 0) {
+        if (value_dev) value += *value_dev;
         const unsigned long long t0 = global_ns();
         while (ld_acquire_sys(flag) < value) {
             __nanosleep(64);
@@ -1133,7 +1139,8 @@ extern "C" int bns_p2p_set_peer(bns_p2p_t *p, int32_t peer, void *slab, void *fl
 
 extern "C" int bns_p2p_put_rows_f32(bns_p2p_t *p, int32_t peer, size_t remote_off, int64_t ld_remote, const float *H,
                                     int64_t ldh, int64_t F, const int64_t *idx, int64_t k, float div,
-                                    int32_t flag_index, uint64_t flag_value, void *stream) {
+                                    int32_t flag_index, uint64_t flag_value, const uint64_t *flag_value_dev,
+                                    void *stream) {
     BNS_REQUIRE(p, "bns_p2p_put_rows_f32: NULL handle");
     BNS_REQUIRE(peer >= 0 && peer < p->world && peer != p->rank, "bns_p2p_put_rows_f32: bad peer %d", peer);
     BNS_REQUIRE(p->peer_slab[peer] && p->peer_flags[peer], "bns_p2p_put_rows_f32: peer %d not connected", peer);
@@ -1153,19 +1160,24 @@ extern "C" int bns_p2p_put_rows_f32(bns_p2p_t *p, int32_t peer, size_t remote_of
     const unsigned grid = rows_grid(k);
     if (vec_ok(H, remote, F, ldh, ld_remote))
         p2p_put_rows_kernel<true><<<grid, kThreads, 0, st>>>(H, ldh, (int32_t)F, idx, k, div, remote, ld_remote, flag,
-                                                             flag_value, ticket);
+                                                             flag_value,
+                                                             reinterpret_cast<const unsigned long long *>(flag_value_dev), ticket);
     else
         p2p_put_rows_kernel<false><<<grid, kThreads, 0, st>>>(H, ldh, (int32_t)F, idx, k, div, remote, ld_remote, flag,
-                                                              flag_value, ticket);
+                                                              flag_value,
+                                                              reinterpret_cast<const unsigned long long *>(flag_value_dev), ticket);
     ++g_launches;
     BNS_CUDA(cudaGetLastError());
     return BNS_OK;
 }
 
-extern "C" int bns_p2p_wait_flag(bns_p2p_t *p, int32_t flag_index, uint64_t flag_value, void *stream) {
+extern "C" int bns_p2p_wait_flag(bns_p2p_t *p, int32_t flag_index, uint64_t flag_value, const uint64_t *flag_value_dev,
+                                 void *stream) {
     BNS_REQUIRE(p, "bns_p2p_wait_flag: NULL handle");
     BNS_REQUIRE(flag_index >= 0 && flag_index < p->n_flags, "bns_p2p_wait_flag: bad flag index");
-    p2p_wait_kernel<<<1, 32, 0, as_stream(stream)>>>(p->flags + flag_index, flag_value, 20ull * 1000000000ull);
+    p2p_wait_kernel<<<1, 32, 0, as_stream(stream)>>>(p->flags + flag_index, flag_value,
+                                                     reinterpret_cast<const unsigned long long *>(flag_value_dev),
+                                                     20ull * 1000000000ull);
     ++g_launches;
     BNS_CUDA(cudaGetLastError());
     return BNS_OK;

@@ -53,6 +53,9 @@ class Buffer(object):
         self._send_buf, self._b_recv = None, None
         self._p2p = None
         self._seq = {}
+        # CUDA-graph mode (train.GraphedEpoch): no timing events, sequence numbers come from a device counter
+        self.graph_mode = False
+        self.seq_dev = None
 
     # helper/feature_buffer.py:23-33
     def __init_pl_pr(self):
@@ -164,6 +167,18 @@ class Buffer(object):
         if self._comm.kind == "thread":
             stream.wait_event(self._comm.take_event(peer, tag))
 
+    def _timer_ctx(self, name, stream):
+        import contextlib
+        return contextlib.nullcontext() if self.graph_mode else self._timer.timer(name, stream=stream)
+
+    def _seq_args(self, layer, backward):
+        """(immediate, device pointer) of this exchange's flag value."""
+        if self.graph_mode:
+            return 0, self.seq_dev.data_ptr()
+        key = (layer, 1 if backward else 0)
+        self._seq[key] = self._seq.get(key, 0) + 1
+        return self._seq[key], None
+
     def _flag(self, layer, backward, src):
         return ((layer - 1) * 2 + (1 if backward else 0)) * self._size + src
 
@@ -201,7 +216,7 @@ class Buffer(object):
         start.record(main)
         cs.wait_event(start)
         with torch.cuda.stream(cs):
-            with self._timer.timer(f'forward_{layer}', stream=cs):
+            with self._timer_ctx(f'forward_{layer}', cs):
                 if self._backend == 'nccl':
                     send = [None] * self._size
                     recv = [None] * self._size
@@ -214,7 +229,7 @@ class Buffer(object):
                         recv[j] = h_u[self._pl[j]:self._pr[j]]
                     self._comm.alltoall(send, recv, tag=16 + layer)                               # C1/C2
                 else:
-                    seq = self._seq[(layer, 0)] = self._seq.get((layer, 0), 0) + 1
+                    seq, seq_dev = self._seq_args(layer, False)
                     for i in range(1, self._size):
                         j = (self._rank + i) % self._size
                         lay = self._peer_layout[j]
@@ -222,16 +237,17 @@ class Buffer(object):
                         check(lib.bns_p2p_put_rows_f32(self._p2p, j, off, self._width, feat.data_ptr(), feat.stride(0),
                                                        F, ops._ptr(self._selected[j]), self._send_shape[j],
                                                        float(self._ratio[j]), self._flag(layer, False, self._rank), seq,
-                                                       cs.cuda_stream), "bns_p2p_put_rows_f32")
+                                                       seq_dev, cs.cuda_stream), "bns_p2p_put_rows_f32")
                         self._post_put_event(j, 2000 + 2 * layer, cs)
                     for i in range(1, self._size):
                         j = (self._rank - i + self._size) % self._size
                         self._await_put_event(j, 2000 + 2 * layer, cs)
-                        check(lib.bns_p2p_wait_flag(self._p2p, self._flag(layer, False, j), seq, cs.cuda_stream),
+                        check(lib.bns_p2p_wait_flag(self._p2p, self._flag(layer, False, j), seq, seq_dev, cs.cuda_stream),
                               "bns_p2p_wait_flag")
             ready.record(cs)
-        feat.record_stream(cs)
-        h_u.record_stream(cs)
+        if not self.graph_mode:
+            feat.record_stream(cs)
+            h_u.record_stream(cs)
         if not overlap:
             main.wait_event(ready)
         self._last_ready = ready
@@ -247,7 +263,7 @@ class Buffer(object):
         start.record(main)
         cs.wait_event(start)
         with torch.cuda.stream(cs):
-            with self._timer.timer(f'backward_{layer}', stream=cs):
+            with self._timer_ctx(f'backward_{layer}', cs):
                 if self._backend == 'nccl':
                     send = [None if j == self._rank else grad[self._pl[j]:self._pr[j]] for j in range(self._size)]
                     recv = [None if j == self._rank else
@@ -255,7 +271,7 @@ class Buffer(object):
                              torch.empty(self._send_shape[j], F, device=self._device)) for j in range(self._size)]
                     self._comm.alltoall(send, recv, tag=64 + layer)
                 else:
-                    seq = self._seq[(layer, 1)] = self._seq.get((layer, 1), 0) + 1
+                    seq, seq_dev = self._seq_args(layer, True)
                     for i in range(1, self._size):
                         j = (self._rank + i) % self._size
                         lay = self._peer_layout[j]
@@ -263,7 +279,7 @@ class Buffer(object):
                         src = grad[self._pl[j]:self._pr[j]]
                         check(lib.bns_p2p_put_rows_f32(self._p2p, j, off, self._width, src.data_ptr(), grad.stride(0), F,
                                                        None, self._recv_shape[j], 1.0,
-                                                       self._flag(layer, True, self._rank), seq, cs.cuda_stream),
+                                                       self._flag(layer, True, self._rank), seq, seq_dev, cs.cuda_stream),
                               "bns_p2p_put_rows_f32")
                         self._post_put_event(j, 2001 + 2 * layer, cs)
                     recv = [None] * self._size
@@ -271,11 +287,12 @@ class Buffer(object):
                     for i in range(1, self._size):
                         j = (self._rank - i + self._size) % self._size
                         self._await_put_event(j, 2001 + 2 * layer, cs)
-                        check(lib.bns_p2p_wait_flag(self._p2p, self._flag(layer, True, j), seq, cs.cuda_stream),
+                        check(lib.bns_p2p_wait_flag(self._p2p, self._flag(layer, True, j), seq, seq_dev, cs.cuda_stream),
                               "bns_p2p_wait_flag")
                         recv[j] = bwd[self._send_begin[j]:self._send_begin[j] + self._send_shape[j], :F]
             done.record(cs)
-        grad.record_stream(cs)
+        if not self.graph_mode:
+            grad.record_stream(cs)
         main.wait_event(done)
         inner = grad[:self._num_in]
         for i in range(1, self._size):               # the reference's order: idx = left, i = 1 .. P-1 (:111-129)

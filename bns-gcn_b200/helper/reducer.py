@@ -22,6 +22,7 @@ class Reducer(object):
         self._stream = None
         self._pending = []
         self._events = None
+        self.graph_mode = False
 
     def init(self, model):
         params = [(n, p) for n, p in model.named_parameters()]
@@ -50,11 +51,14 @@ class Reducer(object):
                 cur = torch.cuda.current_stream(self._flat.device)
                 self._stream.wait_stream(cur)
                 with torch.cuda.stream(self._stream):
-                    s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-                    s.record(self._stream)
-                    c.all_reduce_sum(self._flat)                                  # reducer.py:37 / :46, one message
-                    e.record(self._stream)
-                    self._events = (s, e)
+                    if self.graph_mode:
+                        c.all_reduce_sum(self._flat)
+                    else:
+                        s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                        s.record(self._stream)
+                        c.all_reduce_sum(self._flat)                              # reducer.py:37 / :46, one message
+                        e.record(self._stream)
+                        self._events = (s, e)
                 cur.wait_stream(self._stream)
             else:
                 c.all_reduce_sum(self._flat)

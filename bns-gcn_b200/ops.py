@@ -232,15 +232,16 @@ class BoundarySampler:
         self.ws = torch.empty(max(lib.bns_sample_workspace_bytes(self.B), 16), dtype=torch.uint8, device=device)
         self.world = len(boundary)
 
-    def sample(self, seed: int, offset: int):
-        """Returns ``(selected_cat, [per-peer views or None])``."""
+    def sample(self, seed: int, offset: int, offset_dev: Optional[torch.Tensor] = None):
+        """Returns ``(selected_cat, [per-peer views or None])``.  ``offset_dev`` (int64 ``[1]`` on the device) is added
+        to ``offset`` inside the kernel -- used when the epoch is replayed from a CUDA graph."""
         sel = torch.empty(self.K, dtype=torch.int64, device=self.device)
         if self.K:
             with torch.cuda.device(self.device):
                 check(lib.bns_sample_boundary(self.cat.data_ptr(), self.seg_begin.data_ptr(), self.out_begin.data_ptr(),
                                               len(self.peers), self.B, self.K, seed & (2**64 - 1), offset & (2**64 - 1),
-                                              sel.data_ptr(), self.ws.data_ptr(), self.ws.numel(), _stream_ptr()),
-                      "bns_sample_boundary")
+                                              _ptr(offset_dev), sel.data_ptr(), self.ws.data_ptr(), self.ws.numel(),
+                                              _stream_ptr()), "bns_sample_boundary")
         views = [None] * self.world
         for i, j in enumerate(self.peers):
             views[j] = sel[self.out_begin_host[i]:self.out_begin_host[i + 1]]

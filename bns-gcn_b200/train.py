@@ -258,6 +258,8 @@ class TrainState:
     selected: Optional[list] = None
     one_hops: Optional[list] = None
     last_logits: Optional[torch.Tensor] = None
+    epoch_dev: Optional[torch.Tensor] = None     # int64 [1] on the device: epochs started so far
+    graph_mode: bool = False
 
 
 def setup(graph: LocalGraph, node_dict, gpb, args, device=None) -> TrainState:
@@ -301,7 +303,8 @@ def setup(graph: LocalGraph, node_dict, gpb, args, device=None) -> TrainState:
         loss_fcn = torch.nn.BCEWithLogitsLoss(reduction='sum')              # train.py:358-361
     else:
         loss_fcn = torch.nn.CrossEntropyLoss(reduction='sum')
-    optimizer = torch.optim.Adam(model.parameters(), lr=args.lr, weight_decay=args.weight_decay)
+    # capturable: the step counter lives on the device, so the optimizer step can sit inside a CUDA graph
+    optimizer = torch.optim.Adam(model.parameters(), lr=args.lr, weight_decay=args.weight_decay, capturable=True)
     out_norm = None
     if args.model == 'gcn':
         in_norm = torch.sqrt(node_dict['in_deg'].float())                   # train.py:377-378
@@ -310,7 +313,8 @@ def setup(graph: LocalGraph, node_dict, gpb, args, device=None) -> TrainState:
         in_norm = node_dict['in_deg']                                       # train.py:380
     sampler = ops.BoundarySampler(boundary, send_size, dev) if size > 1 else None
     return TrainState(args, part, model, optimizer, loss_fcn, node_dict['feat'], labels, node_dict['train_mask'],
-                      in_norm, out_norm, boundary, pos, send_size, recv_size, ratio, sampler, part_train)
+                      in_norm, out_norm, boundary, pos, send_size, recv_size, ratio, sampler, part_train,
+                      epoch_dev=torch.zeros(1, dtype=torch.int64, device=dev))
 
 
 def train_epoch(st: TrainState, epoch: int, selected: Optional[list] = None) -> torch.Tensor:
@@ -318,9 +322,15 @@ def train_epoch(st: TrainState, epoch: int, selected: Optional[list] = None) -> 
     ``selected`` injects the sampled sets (parity runs); by default they come from the Philox sampler."""
     rank, size = _rank_size()
     args = st.args
-    comm_timer.clear()                      # train.py:425 (interval names are per epoch)
+    st.epoch_dev.add_(1)
+    if not st.graph_mode:
+        comm_timer.clear()                  # train.py:425 (interval names are per epoch)
     if size > 1:
-        if selected is None:
+        if selected is None and st.graph_mode:
+            # replayed from a CUDA graph: the Philox offset is (device epoch counter - 1), i.e. the same epoch
+            # index an eager run passes as an immediate
+            selected = st.sampler.sample(getattr(args, 'sampler_seed', 0), 2 ** 64 - 1, st.epoch_dev)[1]
+        elif selected is None:
             selected = st.sampler.sample(getattr(args, 'sampler_seed', 0), epoch)[1]            # K6
         recv_shape = [torch.Size([s]) for s in st.recv_size]
         one_hops = data_transfer(selected, recv_shape, tag=TransferTag.NODE, dtype=torch.long)  # C3
@@ -343,6 +353,48 @@ def train_epoch(st: TrainState, epoch: int, selected: Optional[list] = None) -> 
     st.optimizer.step()
     st.last_logits = logits
     return loss.detach()
+
+
+class GraphedEpoch:
+    """One whole training epoch -- boundary sampling, id exchange, slot-map refresh, forward (feature exchange on
+    the comm stream + SpMM + dense), loss, backward (SpMM^T + gradient exchange), weight-gradient all-reduce, Adam --
+    captured ONCE into a CUDA graph and replayed.  At 4-8 partitions of the Reddit-shape graph the eager epoch is
+    bound by the ~10 ms the host needs to enqueue ~300 launches (profiles/kineto_n4_r01.txt); a replay costs one.
+
+    What changes between replays is read from device memory, not baked into kernel arguments: the Philox offset of
+    the sampler and the flag sequence number of the p2p exchange both come from ``st.epoch_dev``; dropout uses
+    torch's graph-safe Philox state.  Sizes (sample counts, slab rows) are fixed for the run (train.py:344-345).
+    """
+
+    def __init__(self, st: TrainState, warmup: int = 3):
+        self.st = st
+        dev = st.feat.device
+        if st.args.model not in ('graphsage', 'gcn'):
+            raise NotImplementedError
+        # eager warm-up on a side stream (allocator, cuBLAS workspaces, lazy kernel loads) as torch.cuda.graphs asks
+        side = torch.cuda.Stream(dev)
+        side.wait_stream(torch.cuda.current_stream(dev))
+        with torch.cuda.stream(side):
+            for _ in range(warmup):
+                train_epoch(st, int(st.epoch_dev.item()))
+        torch.cuda.current_stream(dev).wait_stream(side)
+        torch.cuda.synchronize(dev)
+        buf, red = ctx.buffer._get(), ctx.reducer._get()
+        st.graph_mode = buf.graph_mode = red.graph_mode = True
+        buf.seq_dev = st.epoch_dev
+        self.graph = torch.cuda.CUDAGraph()
+        try:
+            # thread_local: other threads of the process (NCCL watchdog, copy threads) may keep calling CUDA meanwhile
+            with torch.cuda.graph(self.graph, capture_error_mode="thread_local"):
+                self.loss = train_epoch(st, -1)
+        except BaseException:
+            st.graph_mode = buf.graph_mode = red.graph_mode = False      # stay usable in eager mode
+            raise
+        torch.cuda.synchronize(dev)
+
+    def __call__(self) -> torch.Tensor:
+        self.graph.replay()
+        return self.loss
 
 
 def run(graph, node_dict, gpb, args, device=None):

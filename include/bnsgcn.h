@@ -134,6 +134,8 @@ int bns_copy_rows_f32(const float *src, int64_t lds, float *dst, int64_t ldd, in
 size_t bns_sample_workspace_bytes(int64_t B);
 int bns_sample_boundary(const int64_t *boundary_cat, const int64_t *seg_begin, const int64_t *out_begin,
                         int32_t n_seg, int64_t B, int64_t K_total, uint64_t seed, uint64_t offset,
+                        const uint64_t *offset_dev /*device, optional: added to `offset` at run time, so that a
+                                                     captured CUDA graph draws a new sample on every replay*/,
                         int64_t *selected, void *ws, size_t ws_bytes, void *stream);
 
 /* ------------------------------------------------------------------------------------------------
@@ -172,10 +174,13 @@ int bns_p2p_set_peer(bns_p2p_t *p, int32_t peer, void *slab, void *flags, size_t
  * then, after a system-scope fence, peer.flags[flag_index] = flag_value (release). */
 int bns_p2p_put_rows_f32(bns_p2p_t *p, int32_t peer, size_t remote_off, int64_t ld_remote,
                          const float *H, int64_t ldh, int64_t F, const int64_t *idx, int64_t k, float div,
-                         int32_t flag_index, uint64_t flag_value, void *stream);
+                         int32_t flag_index, uint64_t flag_value,
+                         const uint64_t *flag_value_dev /*device, optional: added to flag_value at run time (graph replays)*/,
+                         void *stream);
 /* Enqueue a wait on `stream` until this rank's flags[flag_index] >= flag_value (acquire).  The spin is bounded
  * (20 s): a peer that never signals traps the kernel (a loud CUDA error) instead of hanging the device. */
-int bns_p2p_wait_flag(bns_p2p_t *p, int32_t flag_index, uint64_t flag_value, void *stream);
+int bns_p2p_wait_flag(bns_p2p_t *p, int32_t flag_index, uint64_t flag_value, const uint64_t *flag_value_dev,
+                      void *stream);
 
 #ifdef __cplusplus
 }

@@ -121,3 +121,39 @@ def test_eval_branch_full_graph(built, model):
         e = O.EdgeList(fg.src, fg.dst(), fg.n_nodes, fg.n_nodes)
         want = ref(e, fg.feat)
     assert ((out - want).norm() / want.norm()).item() < TOL
+
+
+@pytest.mark.parametrize("model", ["graphsage", "gcn"])
+def test_cuda_graph_epoch_equals_eager(built, model):
+    """train.GraphedEpoch: replaying the captured epoch gives the losses and weights of the eager loop."""
+    import argparse
+    from tests.harness import make_args
+    from bns_gcn_b200 import train
+    from bns_gcn_b200.data import make_graph, partition_graph
+    from bns_gcn_b200.helper import context as ctx
+    dev = torch.device("cuda:0")
+    fg = make_graph("tiny", seed=0)
+    part = partition_graph(fg, 1, "random", seed=0)[0]
+
+    def fresh():
+        ctx.reset()
+        a = make_args(model=model, n_hidden=16)
+        a.n_feat, a.n_class, a.n_train = part.meta["n_feat"], part.meta["n_class"], part.meta["n_train"]
+        return train.setup(part.graph, part.node_dict, part.gpb, a, dev)
+    prev = torch.autograd.is_multithreading_enabled()
+    torch.autograd.set_multithreading_enabled(False)
+    try:
+        st = fresh()
+        eager = [train.train_epoch(st, e).item() for e in range(5)]
+        w_eager = [p.detach().clone() for p in st.model.parameters()]
+        st = fresh()
+        ge = train.GraphedEpoch(st, warmup=2)               # epochs 0, 1 eager
+        replay = [ge().item() for _ in range(3)]            # epochs 2, 3, 4 from the graph
+        w_graph = [p.detach().clone() for p in st.model.parameters()]
+    finally:
+        torch.autograd.set_multithreading_enabled(prev)
+        ctx.reset()
+    for a_, b_ in zip(replay, eager[2:]):
+        assert abs(a_ - b_) <= 1e-5 * abs(b_), (replay, eager)
+    for a_, b_ in zip(w_graph, w_eager):
+        assert ((a_ - b_).norm() / b_.norm()).item() < 1e-5
