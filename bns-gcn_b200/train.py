@@ -260,6 +260,7 @@ class TrainState:
     last_logits: Optional[torch.Tensor] = None
     epoch_dev: Optional[torch.Tensor] = None     # int64 [1] on the device: epochs started so far
     graph_mode: bool = False
+    train_idx: Optional[torch.Tensor] = None     # nonzero(train_mask), computed once (mask indexing would sync)
 
 
 def setup(graph: LocalGraph, node_dict, gpb, args, device=None) -> TrainState:
@@ -314,7 +315,8 @@ def setup(graph: LocalGraph, node_dict, gpb, args, device=None) -> TrainState:
     sampler = ops.BoundarySampler(boundary, send_size, dev) if size > 1 else None
     return TrainState(args, part, model, optimizer, loss_fcn, node_dict['feat'], labels, node_dict['train_mask'],
                       in_norm, out_norm, boundary, pos, send_size, recv_size, ratio, sampler, part_train,
-                      epoch_dev=torch.zeros(1, dtype=torch.int64, device=dev))
+                      epoch_dev=torch.zeros(1, dtype=torch.int64, device=dev),
+                      train_idx=torch.nonzero(node_dict['train_mask'], as_tuple=True)[0])
 
 
 def train_epoch(st: TrainState, epoch: int, selected: Optional[list] = None) -> torch.Tensor:
@@ -346,7 +348,8 @@ def train_epoch(st: TrainState, epoch: int, selected: Optional[list] = None) -> 
         logits = st.model(g, st.feat, st.in_norm)
     else:
         raise NotImplementedError
-    loss = st.loss_fcn(logits[st.train_mask], st.labels[st.train_mask])
+    # train.py:406 indexes with the boolean mask; the equivalent index list avoids a host sync per epoch
+    loss = st.loss_fcn(logits[st.train_idx], st.labels[st.train_idx])
     st.optimizer.zero_grad(set_to_none=True)
     loss.backward()
     ctx.reducer.synchronize()
