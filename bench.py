@@ -130,6 +130,9 @@ def run_ours(a):
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
     K, W = a.steps, max(a.warmup, 3)
+    # everything runs on ONE non-default stream: the epoch is later captured on it (see train.GraphedEpoch)
+    main_stream = torch.cuda.Stream(dev)
+    torch.cuda.set_stream(main_stream)
     part, gstats = build_partition(a.shape, world, rank, dev)
     args = make_args(world, a.backend, {"n_feat": part.meta["n_feat"], "n_class": part.meta["n_class"],
                                         "n_train": part.meta["n_train"], "dataset": a.shape})

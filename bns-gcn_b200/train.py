@@ -374,13 +374,16 @@ class GraphedEpoch:
         dev = st.feat.device
         if st.args.model not in ('graphsage', 'gcn'):
             raise NotImplementedError
-        # eager warm-up on a side stream (allocator, cuBLAS workspaces, lazy kernel loads) as torch.cuda.graphs asks
-        side = torch.cuda.Stream(dev)
-        side.wait_stream(torch.cuda.current_stream(dev))
-        with torch.cuda.stream(side):
-            for _ in range(warmup):
-                train_epoch(st, int(st.epoch_dev.item()))
-        torch.cuda.current_stream(dev).wait_stream(side)
+        cur = torch.cuda.current_stream(dev)
+        if cur == torch.cuda.default_stream(dev):
+            raise RuntimeError(
+                "GraphedEpoch must be built -- and train.setup() must have run -- under `with torch.cuda.stream(s)` "
+                "for one non-default stream s: autograd ties each parameter's gradient accumulator to the stream "
+                "that was current when its hook was registered, and a capturing stream may not synchronise with the "
+                "legacy default stream")
+        # eager warm-up on the capture stream (allocator, cuBLAS workspaces, lazy kernel loads)
+        for _ in range(warmup):
+            train_epoch(st, int(st.epoch_dev.item()))
         torch.cuda.synchronize(dev)
         buf, red = ctx.buffer._get(), ctx.reducer._get()
         st.graph_mode = buf.graph_mode = red.graph_mode = True
@@ -388,7 +391,7 @@ class GraphedEpoch:
         self.graph = torch.cuda.CUDAGraph()
         try:
             # thread_local: other threads of the process (NCCL watchdog, copy threads) may keep calling CUDA meanwhile
-            with torch.cuda.graph(self.graph, capture_error_mode="thread_local"):
+            with torch.cuda.graph(self.graph, stream=cur, capture_error_mode="thread_local"):
                 self.loss = train_epoch(st, -1)
         except BaseException:
             st.graph_mode = buf.graph_mode = red.graph_mode = False      # stay usable in eager mode

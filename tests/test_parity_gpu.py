@@ -142,6 +142,8 @@ def test_cuda_graph_epoch_equals_eager(built, model):
         return train.setup(part.graph, part.node_dict, part.gpb, a, dev)
     prev = torch.autograd.is_multithreading_enabled()
     torch.autograd.set_multithreading_enabled(False)
+    prev_stream = torch.cuda.current_stream(dev)
+    torch.cuda.set_stream(torch.cuda.Stream(dev))       # setup + eager + capture on one non-default stream
     try:
         st = fresh()
         eager = [train.train_epoch(st, e).item() for e in range(5)]
@@ -151,6 +153,8 @@ def test_cuda_graph_epoch_equals_eager(built, model):
         replay = [ge().item() for _ in range(3)]            # epochs 2, 3, 4 from the graph
         w_graph = [p.detach().clone() for p in st.model.parameters()]
     finally:
+        torch.cuda.synchronize(dev)
+        torch.cuda.set_stream(prev_stream)
         torch.autograd.set_multithreading_enabled(prev)
         ctx.reset()
     for a_, b_ in zip(replay, eager[2:]):

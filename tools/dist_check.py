@@ -63,6 +63,7 @@ def main():
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     dist.init_process_group("nccl", device_id=dev)
+    torch.cuda.set_stream(torch.cuda.Stream(dev))       # one non-default stream for setup, eager epochs and capture
     fg = make_graph(a.shape, seed=0, device=dev)
     parts = partition_graph(fg, world, "random", seed=0, device=dev)
     res = {}
