@@ -915,6 +915,237 @@ extern "C" int bns_sample_boundary(const int64_t *boundary_cat, const int64_t *s
 }
 
 // =================================================================================================
+// fused LayerNorm -> ReLU -> dropout  (module/model.py:88-91 then :45/:80 of the next layer)
+// =================================================================================================
+namespace {
+
+constexpr int kLnMaxNV = 8;      // F <= 1024
+
+struct LnArgs {
+    const float *x; int64_t ldx;
+    const float *dy; int64_t lddy;
+    float *y; int64_t ldy;          // forward output / backward dx
+    const float *gamma, *beta;
+    float *mean, *rstd;
+    int64_t n; int32_t F;
+    float eps, p, keep_scale;
+    uint64_t seed, offset;
+    const uint64_t *offset_dev;
+    float *partial;                 // backward: [gridDim.x][2][F] column partial sums (dgamma, dbeta)
+};
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+// keep-mask of the 4 elements of vector `vec` of row `row`: one Philox4x32-10 call
+__device__ __forceinline__ void drop_mask4(uint64_t seed, uint64_t offset, int64_t row, int vec, float p, bool keep[4]) {
+    uint32_t r[4];
+    philox4x32_10((uint32_t)row, (uint32_t)((uint64_t)row >> 32) ^ ((uint32_t)vec << 8), (uint32_t)offset,
+                  (uint32_t)(offset >> 32), (uint32_t)seed, (uint32_t)(seed >> 32), r);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) keep[i] = (float)r[i] * 2.3283064365386963e-10f >= p;
+}
+
+template <int NV, bool BACKWARD>
+__global__ void __launch_bounds__(kThreads) ln_relu_dropout_kernel(LnArgs a) {
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    const int64_t warps_total = (int64_t)gridDim.x * kWarps;
+    const uint64_t offset = a.offset + (a.offset_dev ? *a.offset_dev : 0ull);
+    const float invF = 1.f / (float)a.F;
+    float4 g4[NV], b4[NV];
+    float4 sg[NV], sb[NV];             // backward: this warp's column sums of dgamma / dbeta
+    bool ok[NV];
+#pragma unroll
+    for (int t = 0; t < NV; ++t) {
+        const int f = (lane + 32 * t) * 4;
+        ok[t] = f < a.F;
+        g4[t] = ok[t] ? *reinterpret_cast<const float4 *>(a.gamma + f) : make_float4(0.f, 0.f, 0.f, 0.f);
+        b4[t] = ok[t] ? *reinterpret_cast<const float4 *>(a.beta + f) : make_float4(0.f, 0.f, 0.f, 0.f);
+        sg[t] = make_float4(0.f, 0.f, 0.f, 0.f);
+        sb[t] = make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+    for (int64_t row = (int64_t)blockIdx.x * kWarps + w; row < a.n; row += warps_total) {
+        float4 v[NV];
+        float s = 0.f;
+#pragma unroll
+        for (int t = 0; t < NV; ++t) {
+            v[t] = ok[t] ? *reinterpret_cast<const float4 *>(a.x + row * a.ldx + (lane + 32 * t) * 4)
+                         : make_float4(0.f, 0.f, 0.f, 0.f);
+            s += (v[t].x + v[t].y) + (v[t].z + v[t].w);
+        }
+        float mean, rstd;
+        if (!BACKWARD) {
+            mean = warp_sum(s) * invF;
+            float q = 0.f;
+#pragma unroll
+            for (int t = 0; t < NV; ++t) {
+                if (!ok[t]) continue;
+                const float dx = v[t].x - mean, dy = v[t].y - mean, dz = v[t].z - mean, dw = v[t].w - mean;
+                q += (dx * dx + dy * dy) + (dz * dz + dw * dw);
+            }
+            rstd = rsqrtf(warp_sum(q) * invF + a.eps);
+            if (lane == 0) { a.mean[row] = mean; a.rstd[row] = rstd; }
+        } else {
+            mean = a.mean[row];
+            rstd = a.rstd[row];
+        }
+        float4 gz[NV];                 // backward: dL/dz * gamma ; forward: unused
+        float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+        for (int t = 0; t < NV; ++t) {
+            if (!ok[t]) continue;
+            const int f = (lane + 32 * t) * 4;
+            bool keep[4] = {true, true, true, true};
+            if (a.p > 0.f) drop_mask4(a.seed, offset, row, lane + 32 * t, a.p, keep);
+            float xh[4] = {(v[t].x - mean) * rstd, (v[t].y - mean) * rstd, (v[t].z - mean) * rstd, (v[t].w - mean) * rstd};
+            const float gg[4] = {g4[t].x, g4[t].y, g4[t].z, g4[t].w}, bb[4] = {b4[t].x, b4[t].y, b4[t].z, b4[t].w};
+            if (!BACKWARD) {
+                float o[4];
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    const float z = fmaf(xh[i], gg[i], bb[i]);
+                    o[i] = (z > 0.f && keep[i]) ? z * a.keep_scale : 0.f;
+                }
+                *reinterpret_cast<float4 *>(a.y + row * a.ldy + f) = make_float4(o[0], o[1], o[2], o[3]);
+            } else {
+                const float4 d4 = *reinterpret_cast<const float4 *>(a.dy + row * a.lddy + f);
+                const float dd[4] = {d4.x, d4.y, d4.z, d4.w};
+                float gzz[4];
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    const float z = fmaf(xh[i], gg[i], bb[i]);
+                    const float g = (z > 0.f && keep[i]) ? dd[i] * a.keep_scale : 0.f;      // dL/dz
+                    (&sg[t].x)[i] += g * xh[i];
+                    (&sb[t].x)[i] += g;
+                    gzz[i] = g * gg[i];                                                     // dL/dxhat
+                    s1 += gzz[i];
+                    s2 += gzz[i] * xh[i];
+                }
+                gz[t] = make_float4(gzz[0], gzz[1], gzz[2], gzz[3]);
+                v[t] = make_float4(xh[0], xh[1], xh[2], xh[3]);
+            }
+        }
+        if (BACKWARD) {
+            s1 = warp_sum(s1) * invF;
+            s2 = warp_sum(s2) * invF;
+#pragma unroll
+            for (int t = 0; t < NV; ++t) {
+                if (!ok[t]) continue;
+                const int f = (lane + 32 * t) * 4;
+                float4 o;
+                o.x = rstd * (gz[t].x - s1 - v[t].x * s2);
+                o.y = rstd * (gz[t].y - s1 - v[t].y * s2);
+                o.z = rstd * (gz[t].z - s1 - v[t].z * s2);
+                o.w = rstd * (gz[t].w - s1 - v[t].w * s2);
+                *reinterpret_cast<float4 *>(a.y + row * a.ldy + f) = o;
+            }
+        }
+    }
+    if (BACKWARD) {      // CTA-level column sums, warps added in a fixed order -> one partial row per CTA
+        __shared__ float red[2][NV * 128];
+        for (int i = threadIdx.x; i < 2 * NV * 128; i += kThreads) (&red[0][0])[i] = 0.f;
+        __syncthreads();
+        for (int ww = 0; ww < kWarps; ++ww) {
+            if (w == ww) {
+#pragma unroll
+                for (int t = 0; t < NV; ++t) {
+                    const int f = (lane + 32 * t) * 4;
+                    if (!ok[t]) continue;
+                    float4 r0 = *reinterpret_cast<float4 *>(&red[0][f]), r1 = *reinterpret_cast<float4 *>(&red[1][f]);
+                    r0.x += sg[t].x; r0.y += sg[t].y; r0.z += sg[t].z; r0.w += sg[t].w;
+                    r1.x += sb[t].x; r1.y += sb[t].y; r1.z += sb[t].z; r1.w += sb[t].w;
+                    *reinterpret_cast<float4 *>(&red[0][f]) = r0;
+                    *reinterpret_cast<float4 *>(&red[1][f]) = r1;
+                }
+            }
+            __syncthreads();
+        }
+        for (int i = threadIdx.x; i < 2 * a.F; i += kThreads) {
+            const int which = i / a.F, f = i % a.F;
+            a.partial[((int64_t)blockIdx.x * 2 + which) * a.F + f] = red[which][f];
+        }
+    }
+}
+
+__global__ void ln_colsum_kernel(const float *__restrict__ partial, int n_part, int F, float *__restrict__ dgamma,
+                                 float *__restrict__ dbeta) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= 2 * F) return;
+    const int which = i / F, f = i % F;
+    float acc = 0.f;
+    for (int p = 0; p < n_part; ++p) acc += partial[((int64_t)p * 2 + which) * F + f];
+    (which == 0 ? dgamma : dbeta)[f] = acc;
+}
+
+inline unsigned ln_grid(int64_t n) {
+    int64_t want = (n + kWarps - 1) / kWarps;
+    int64_t cap = (int64_t)sm_count() * 4;
+    return (unsigned)(want < cap ? (want > 0 ? want : 1) : cap);
+}
+
+template <bool BWD>
+int launch_ln(const LnArgs &a, unsigned grid, cudaStream_t st) {
+    const int nv = (a.F + 127) / 128;
+    switch (nv) {
+        case 1: ln_relu_dropout_kernel<1, BWD><<<grid, kThreads, 0, st>>>(a); break;
+        case 2: ln_relu_dropout_kernel<2, BWD><<<grid, kThreads, 0, st>>>(a); break;
+        case 3: case 4: ln_relu_dropout_kernel<4, BWD><<<grid, kThreads, 0, st>>>(a); break;
+        default: ln_relu_dropout_kernel<8, BWD><<<grid, kThreads, 0, st>>>(a); break;
+    }
+    return BNS_OK;
+}
+
+}  // namespace
+
+extern "C" size_t bns_ln_bwd_workspace_bytes(int64_t F) { return (size_t)sm_count() * 4 * 2 * (size_t)F * sizeof(float); }
+
+extern "C" int bns_ln_relu_dropout_fwd_f32(const float *x, int64_t ldx, int64_t n, int64_t F, const float *gamma,
+                                           const float *beta, float eps, float p, uint64_t seed, uint64_t offset,
+                                           const uint64_t *offset_dev, float *y, int64_t ldy, float *mean, float *rstd,
+                                           void *stream) {
+    BNS_REQUIRE(n >= 0 && F > 0 && F % 4 == 0 && F <= kLnMaxNV * 128, "bns_ln_relu_dropout_fwd_f32: need F %% 4 == 0, F <= 1024");
+    if (n == 0) return BNS_OK;
+    BNS_REQUIRE(x && y && gamma && beta && mean && rstd, "bns_ln_relu_dropout_fwd_f32: NULL pointer");
+    BNS_REQUIRE(ldx % 4 == 0 && ldy % 4 == 0 && ldx >= F && ldy >= F, "bns_ln_relu_dropout_fwd_f32: bad leading dimension");
+    BNS_REQUIRE(p >= 0.f && p < 1.f, "bns_ln_relu_dropout_fwd_f32: p must be in [0, 1)");
+    LnArgs a{};
+    a.x = x; a.ldx = ldx; a.y = y; a.ldy = ldy; a.gamma = gamma; a.beta = beta; a.mean = mean; a.rstd = rstd;
+    a.n = n; a.F = (int32_t)F; a.eps = eps; a.p = p; a.keep_scale = 1.f / (1.f - p);
+    a.seed = seed; a.offset = offset; a.offset_dev = offset_dev;
+    launch_ln<false>(a, ln_grid(n), as_stream(stream));
+    ++g_launches;
+    BNS_CUDA(cudaGetLastError());
+    return BNS_OK;
+}
+
+extern "C" int bns_ln_relu_dropout_bwd_f32(const float *dy, int64_t lddy, const float *x, int64_t ldx, int64_t n, int64_t F,
+                                           const float *gamma, const float *beta, const float *mean, const float *rstd,
+                                           float eps, float p, uint64_t seed, uint64_t offset, const uint64_t *offset_dev,
+                                           float *dx, int64_t lddx, float *dgamma, float *dbeta, void *ws, size_t ws_bytes,
+                                           void *stream) {
+    BNS_REQUIRE(n >= 0 && F > 0 && F % 4 == 0 && F <= kLnMaxNV * 128, "bns_ln_relu_dropout_bwd_f32: need F %% 4 == 0, F <= 1024");
+    BNS_REQUIRE(dy && x && dx && gamma && beta && mean && rstd && dgamma && dbeta, "bns_ln_relu_dropout_bwd_f32: NULL pointer");
+    BNS_REQUIRE(ldx % 4 == 0 && lddy % 4 == 0 && lddx % 4 == 0, "bns_ln_relu_dropout_bwd_f32: bad leading dimension");
+    const unsigned grid = ln_grid(n > 0 ? n : 1);
+    if (!ws || ws_bytes < (size_t)grid * 2 * F * sizeof(float))
+        return fail(BNS_E_WORKSPACE, "bns_ln_relu_dropout_bwd_f32: workspace too small");
+    LnArgs a{};
+    a.x = x; a.ldx = ldx; a.dy = dy; a.lddy = lddy; a.y = dx; a.ldy = lddx; a.gamma = gamma; a.beta = beta;
+    a.mean = const_cast<float *>(mean); a.rstd = const_cast<float *>(rstd);
+    a.n = n; a.F = (int32_t)F; a.eps = eps; a.p = p; a.keep_scale = 1.f / (1.f - p);
+    a.seed = seed; a.offset = offset; a.offset_dev = offset_dev; a.partial = reinterpret_cast<float *>(ws);
+    cudaStream_t st = as_stream(stream);
+    launch_ln<true>(a, grid, st);
+    ln_colsum_kernel<<<(unsigned)((2 * F + 255) / 256), 256, 0, st>>>(a.partial, (int)grid, (int)F, dgamma, dbeta);
+    g_launches += 2;
+    BNS_CUDA(cudaGetLastError());
+    return BNS_OK;
+}
+
+// =================================================================================================
 // halo slot map
 // =================================================================================================
 namespace {

@@ -1,9 +1,15 @@
 """``GCN`` / ``GraphSAGE`` layer stacks with the reference's constructor and ``forward`` signatures
 (module/model.py:7-93).  ``GAT`` and ``--norm batch`` are SURVEY.md §8(f) "next" rows."""
+import torch.nn.functional as F
 from torch import nn
 
+from .. import ops
 from ..helper import context as ctx
 from .layer import GCNLayer, GraphSAGELayer
+
+# LayerNorm -> ReLU -> (next layer's) dropout as one fused kernel each way (ops.LnReluDropout) when the model uses
+# `--norm layer` with ReLU on CUDA; False = the three separate ATen ops of the reference (module/model.py:88-91, :80)
+FUSE_NORM_ACT_DROPOUT = True
 
 
 class GNNBase(nn.Module):
@@ -38,8 +44,11 @@ class GNNBase(nn.Module):
 
     def _forward(self, g, feat, *norms):
         h = feat
+        dropped = False                      # this layer's input dropout was already applied by the fused op
         for i in range(self.n_layers):
-            h = self.dropout(h)
+            if not dropped:
+                h = self.dropout(h)
+            dropped = False
             if i < self.n_layers - self.n_linear:
                 if self.training and (i > 0 or not self.use_pp):
                     h = ctx.buffer.update(i, h, overlap=True)          # model.py:47-48, 82-83
@@ -47,9 +56,16 @@ class GNNBase(nn.Module):
             else:
                 h = self.layers[i](h)
             if i < self.n_layers - 1:
-                if self.use_norm:
-                    h = self.norm[i](h)
-                h = self.activation(h)
+                nm = self.norm[i] if self.use_norm else None
+                if (FUSE_NORM_ACT_DROPOUT and isinstance(nm, nn.LayerNorm) and self.activation is F.relu
+                        and nm.elementwise_affine and ops.ln_relu_dropout_supported(h, h.shape[1])):
+                    p = self.dropout.p if self.training else 0.0
+                    h = ops.LnReluDropout.apply(h, nm.weight, nm.bias, nm.eps, p, ops.RNG["seed"] + 7919 * (i + 1))
+                    dropped = True
+                else:
+                    if self.use_norm:
+                        h = nm(h)
+                    h = self.activation(h)
         return h
 
 

@@ -262,3 +262,55 @@ def halo_slot_update(pos: torch.Tensor, one_hops: torch.Tensor, n_in: int, slab_
     with torch.cuda.device(slot.device):
         check(lib.bns_halo_slot_update(pos.data_ptr(), one_hops.data_ptr(), one_hops.numel(), n_in, slab_offset,
                                        slot.data_ptr(), _stream_ptr()), "bns_halo_slot_update")
+
+
+# ---- fused LayerNorm -> ReLU -> dropout --------------------------------------------------------------------------
+# Philox stream of the dropout masks: (seed, offset [+ *offset_dev]); train.train_epoch sets it once per epoch
+# (offset = epoch index; under CUDA-graph replay the epoch index comes from the device counter).
+RNG = {"seed": 0, "offset": 0, "offset_dev": None}
+_LN_WS: Dict[tuple, torch.Tensor] = {}
+
+
+class LnReluDropout(torch.autograd.Function):
+    """``dropout_p(relu(layer_norm(x)))`` in one pass each way (``bns_ln_relu_dropout_{fwd,bwd}_f32``)."""
+
+    @staticmethod
+    def forward(ctx, x, gamma, beta, eps: float, p: float, seed: int):
+        x = x.contiguous()
+        n, F = x.shape
+        y = torch.empty_like(x)
+        mean = torch.empty(n, dtype=torch.float32, device=x.device)
+        rstd = torch.empty(n, dtype=torch.float32, device=x.device)
+        off, off_dev = RNG["offset"], RNG["offset_dev"]
+        with torch.cuda.device(x.device):
+            check(lib.bns_ln_relu_dropout_fwd_f32(x.data_ptr(), x.stride(0), n, F, gamma.data_ptr(), beta.data_ptr(),
+                                                  eps, p, seed & (2**64 - 1), off & (2**64 - 1), _ptr(off_dev),
+                                                  y.data_ptr(), y.stride(0), mean.data_ptr(), rstd.data_ptr(),
+                                                  _stream_ptr()), "bns_ln_relu_dropout_fwd_f32")
+        ctx.save_for_backward(x, gamma, beta, mean, rstd)
+        ctx.cfg = (eps, p, seed, off, off_dev)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, gamma, beta, mean, rstd = ctx.saved_tensors
+        eps, p, seed, off, off_dev = ctx.cfg
+        dy = dy.contiguous()
+        n, F = x.shape
+        dx = torch.empty_like(x)
+        dgamma, dbeta = torch.empty_like(gamma), torch.empty_like(beta)
+        key = (x.device, F)
+        ws = _LN_WS.get(key)
+        if ws is None:
+            ws = _LN_WS[key] = torch.empty(lib.bns_ln_bwd_workspace_bytes(F), dtype=torch.uint8, device=x.device)
+        with torch.cuda.device(x.device):
+            check(lib.bns_ln_relu_dropout_bwd_f32(dy.data_ptr(), dy.stride(0), x.data_ptr(), x.stride(0), n, F,
+                                                  gamma.data_ptr(), beta.data_ptr(), mean.data_ptr(), rstd.data_ptr(),
+                                                  eps, p, seed & (2**64 - 1), off & (2**64 - 1), _ptr(off_dev),
+                                                  dx.data_ptr(), dx.stride(0), dgamma.data_ptr(), dbeta.data_ptr(),
+                                                  ws.data_ptr(), ws.numel(), _stream_ptr()), "bns_ln_relu_dropout_bwd_f32")
+        return dx, dgamma, dbeta, None, None, None
+
+
+def ln_relu_dropout_supported(x: torch.Tensor, F: int) -> bool:
+    return x.is_cuda and x.dtype == torch.float32 and x.dim() == 2 and F % 4 == 0 and F <= 1024

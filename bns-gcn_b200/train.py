@@ -325,7 +325,12 @@ def train_epoch(st: TrainState, epoch: int, selected: Optional[list] = None) -> 
     rank, size = _rank_size()
     args = st.args
     st.epoch_dev.add_(1)
-    if not st.graph_mode:
+    # Philox stream of this epoch's dropout masks (ops.LnReluDropout): (model seed, epoch index)
+    ops.RNG["seed"] = int(getattr(args, 'seed', 0)) * 1000003 + rank
+    if st.graph_mode:
+        ops.RNG["offset"], ops.RNG["offset_dev"] = 2 ** 64 - 1, st.epoch_dev
+    else:
+        ops.RNG["offset"], ops.RNG["offset_dev"] = int(epoch), None
         comm_timer.clear()                  # train.py:425 (interval names are per epoch)
     if size > 1:
         if selected is None and st.graph_mode:

@@ -151,6 +151,27 @@ int bns_halo_slot_update(const int64_t *pos /*device [part size of the peer]*/, 
                          int64_t r, int64_t n_in, int32_t slab_offset, int32_t *slot /*device [n_halo]*/, void *stream);
 
 /* ------------------------------------------------------------------------------------------------
+ * K9 (fused): LayerNorm -> ReLU -> dropout between two layers.  Replaces the three ATen ops of
+ * module/model.py:88-91 (`h = self.norm[i](h); h = self.activation(h)`) and :45/:80 of the next iteration
+ * (`h = self.dropout(h)`), forward and backward, in one pass each:
+ *     y = dropout_p( relu( (x - mean) * rstd * gamma + beta ) )        mean / biased var over the F columns
+ * The dropout mask is Philox4x32-10(counter = (row, vector, offset), key = seed) -- regenerated, not stored, in
+ * backward; offset_dev (optional, device) is added to offset at run time (CUDA-graph replays).  F % 4 == 0,
+ * F <= 1024.  Backward also returns dgamma / dbeta (column sums, fixed summation order: deterministic);
+ * ws: bns_ln_bwd_workspace_bytes(F) bytes.
+ * ----------------------------------------------------------------------------------------------*/
+size_t bns_ln_bwd_workspace_bytes(int64_t F);
+int bns_ln_relu_dropout_fwd_f32(const float *x, int64_t ldx, int64_t n, int64_t F, const float *gamma,
+                                const float *beta, float eps, float p, uint64_t seed, uint64_t offset,
+                                const uint64_t *offset_dev, float *y, int64_t ldy, float *mean /*[n]*/,
+                                float *rstd /*[n]*/, void *stream);
+int bns_ln_relu_dropout_bwd_f32(const float *dy, int64_t lddy, const float *x, int64_t ldx, int64_t n, int64_t F,
+                                const float *gamma, const float *beta, const float *mean, const float *rstd,
+                                float eps, float p, uint64_t seed, uint64_t offset, const uint64_t *offset_dev,
+                                float *dx, int64_t lddx, float *dgamma /*[F]*/, float *dbeta /*[F]*/, void *ws,
+                                size_t ws_bytes, void *stream);
+
+/* ------------------------------------------------------------------------------------------------
  * C1/C2 fused with K3/K5: the boundary exchange over peer-mapped memory (NVLink 5 / NVSwitch).
  * Replaces Buffer.__gloo_all_to_all / __mpi_all_to_all (helper/feature_buffer.py:101-153): the pack
  * kernel of rank a stores  H[selected_b] / ratio_b  straight into rank b's receive slab, then raises a

@@ -284,3 +284,45 @@ def test_dense_3xtf32_is_fp32_accurate(built):
     # plain fp32 cuBLAS for comparison: same order of magnitude of error
     y32 = torch.nn.functional.linear(x.detach(), w.detach(), b.detach())
     assert _relerr(y.detach().cpu(), y32.cpu()) < 1e-5
+
+
+@pytest.mark.parametrize("F,p", [(256, 0.0), (256, 0.5), (64, 0.3), (600, 0.5), (16, 0.0)])
+def test_fused_layernorm_relu_dropout(built, F, p):
+    """ops.LnReluDropout == dropout(relu(layer_norm(x))) forward and backward (mask recovered from the output),
+    mask keep-rate ~ 1-p, masks differ across offsets and repeat for the same (seed, offset)."""
+    import torch.nn.functional as Fn
+    from bns_gcn_b200 import ops
+    dev = torch.device("cuda:0")
+    g = torch.Generator().manual_seed(F)
+    n = 3000
+    x = (torch.randn(n, F, generator=g) * 2 + 0.3).to(dev).requires_grad_(True)
+    gamma = (torch.rand(F, generator=g) + 0.5).to(dev).requires_grad_(True)
+    beta = (torch.randn(F, generator=g) * 0.2).to(dev).requires_grad_(True)
+    dy = torch.randn(n, F, generator=g).to(dev)
+    ops.RNG.update(seed=123, offset=5, offset_dev=None)
+    y = ops.LnReluDropout.apply(x, gamma, beta, 1e-5, p, 77)
+    y.backward(dy)
+    got = (y.detach().clone(), x.grad.clone(), gamma.grad.clone(), beta.grad.clone())
+    # reference with the same mask
+    xr, gr, br = (t.detach().clone().requires_grad_(True) for t in (x, gamma, beta))
+    z = Fn.relu(Fn.layer_norm(xr, (F,), gr, br, 1e-5))
+    if p > 0:
+        mask = ((y.detach() != 0) | (z.detach() <= 0)).float()
+        keep = mask[z.detach() > 0].mean().item()
+        assert abs(keep - (1 - p)) < 0.01, keep
+        ref = z * mask / (1 - p)
+    else:
+        ref = z
+    ref.backward(dy)
+    for a, b in zip(got, (ref.detach(), xr.grad, gr.grad, br.grad)):
+        assert _relerr(a.cpu(), b.cpu()) < 2e-5
+    if p > 0:
+        y2 = ops.LnReluDropout.apply(x.detach(), gamma.detach(), beta.detach(), 1e-5, p, 77)
+        assert torch.equal(y2, y.detach())                            # same (seed, offset) -> same mask
+        off_dev = torch.tensor([1], dtype=torch.int64, device=dev)    # 5 + 1: offset read from the device
+        ops.RNG.update(offset=5, offset_dev=off_dev)
+        y3 = ops.LnReluDropout.apply(x.detach(), gamma.detach(), beta.detach(), 1e-5, p, 77)
+        ops.RNG.update(offset=6, offset_dev=None)
+        y4 = ops.LnReluDropout.apply(x.detach(), gamma.detach(), beta.detach(), 1e-5, p, 77)
+        assert torch.equal(y3, y4) and not torch.equal(y3, y.detach())
+    ops.RNG.update(seed=0, offset=0, offset_dev=None)
