@@ -67,6 +67,7 @@ SHAPES = {
     "yelp": dict(n=716_847, e=13_954_819, n_feat=300, n_class=100, train=0.75, multilabel=True, law="powerlaw"),
     # small shapes used by tests / smoke
     "tiny": dict(n=600, e=6_000, n_feat=16, n_class=5, train=0.5, multilabel=False, law="powerlaw"),
+    "tiny-ml": dict(n=500, e=5_000, n_feat=12, n_class=6, train=0.6, multilabel=True, law="powerlaw"),
     "small": dict(n=6_000, e=240_000, n_feat=32, n_class=7, train=0.6, multilabel=False, law="powerlaw"),
 }
 

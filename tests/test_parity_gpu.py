@@ -161,3 +161,16 @@ def test_cuda_graph_epoch_equals_eager(built, model):
         assert abs(a_ - b_) <= 1e-5 * abs(b_), (replay, eager)
     for a_, b_ in zip(w_graph, w_eager):
         assert ((a_ - b_).norm() / b_.norm()).item() < 1e-5
+
+
+@pytest.mark.parametrize("kw", [
+    dict(n_parts=3, sampling_rate=0.004),                 # int(p * b) == 0 for every peer: nothing is exchanged
+    dict(n_parts=2, sampling_rate=0.5, n_linear=1),       # --n-linear: the last layer is a plain nn.Linear
+    dict(n_parts=2, sampling_rate=0.5, inductive=True),   # --inductive: partition the train-node subgraph
+    dict(n_parts=2, sampling_rate=0.5, shape="tiny-ml", multilabel=True),          # BCE-with-logits (yelp-style)
+    dict(n_parts=2, sampling_rate=0.5, model="gcn", n_layers=4, backend="p2p"),    # deeper GCN over the p2p transport
+], ids=["zero-sample", "n-linear", "inductive", "multilabel", "gcn4-p2p"])
+def test_training_parity_variants(built, kw):
+    kw = dict(kw)
+    kw.setdefault("shape", "tiny")
+    _run(n_epochs=2, **kw)
