@@ -304,6 +304,9 @@ class OracleRank:
             torch.manual_seed(seed)                                                          # train.py:331
             self.net = build_model(model, self.layer_size, use_pp, dropout, norm, inp.n_train, n_linear)
         self.net.oracle = self
+        for m in self.net.modules():
+            if isinstance(m, SyncBNRef):
+                m.comm = comm
         self.loss_fn = (nn.BCEWithLogitsLoss(reduction="sum") if multilabel
                         else nn.CrossEntropyLoss(reduction="sum"))                            # train.py:358-361
         self.opt = torch.optim.Adam(self.net.parameters(), lr=lr, weight_decay=weight_decay)
@@ -601,6 +604,56 @@ class GCNLayerRef(nn.Module):
         return self.linear(CopyUSum.apply(g, feat / out_n) / in_n)               # :40-45
 
 
+class _SyncBNFunc(torch.autograd.Function):
+    """``SyncBatchNormFunc`` (module/sync_bn.py:7-39), four all-reduces as in the reference."""
+
+    @staticmethod
+    def forward(ctx, x, weight, bias, whole_size, running_mean, running_var, training, momentum, eps, comm):
+        if not training:
+            mean, var = running_mean, running_var
+        else:
+            sum_x, sum_x2 = x.sum(axis=0), (x ** 2).sum(axis=0)
+            comm.all_reduce_sum(sum_x)
+            comm.all_reduce_sum(sum_x2)
+            mean = sum_x / whole_size
+            var = (sum_x2 - mean * sum_x) / whole_size
+            running_mean.mul_(1 - momentum).add_(mean * momentum)
+            running_var.mul_(1 - momentum).add_(var * momentum)
+        std = torch.sqrt(var + eps)
+        x_hat = (x - mean) / std
+        if training:
+            ctx.save_for_backward(x_hat, weight, std)
+            ctx.whole_size, ctx.comm = whole_size, comm
+        return x_hat * weight + bias
+
+    @staticmethod
+    def backward(ctx, grad):
+        x_hat, weight, std = ctx.saved_tensors
+        dbias, dweight = grad.sum(axis=0), (grad * x_hat).sum(axis=0)
+        ctx.comm.all_reduce_sum(dbias)
+        ctx.comm.all_reduce_sum(dweight)
+        n = ctx.whole_size
+        dx = (weight / n) / std * (n * grad - dbias - x_hat * dweight)
+        return dx, dweight, dbias, None, None, None, None, None, None, None
+
+
+class SyncBNRef(nn.Module):
+    """``SyncBatchNorm`` (module/sync_bn.py:42-56)."""
+
+    def __init__(self, num_features, whole_size, eps=1e-5, momentum=0.1):
+        super().__init__()
+        self.register_buffer("running_mean", torch.zeros(num_features))
+        self.register_buffer("running_var", torch.ones(num_features))
+        self.whole_size, self.eps, self.momentum = whole_size, eps, momentum
+        self.weight = nn.Parameter(torch.ones(num_features))
+        self.bias = nn.Parameter(torch.zeros(num_features))
+        self.comm = None
+
+    def forward(self, x):
+        return _SyncBNFunc.apply(x, self.weight, self.bias, self.whole_size, self.running_mean, self.running_var,
+                                 self.training, self.momentum, self.eps, self.comm)
+
+
 class GNNRef(nn.Module):
     """``GCN`` / ``GraphSAGE`` (module/model.py:26-93)."""
 
@@ -623,9 +676,10 @@ class GNNRef(nn.Module):
             else:
                 self.layers.append(nn.Linear(layer_size[i], layer_size[i + 1]))
             if i < self.n_layers - 1 and self.use_norm:
-                if norm != "layer":
-                    raise NotImplementedError("SyncBatchNorm: SURVEY §8(f) rank 4")
-                self.norm.append(nn.LayerNorm(layer_size[i + 1], elementwise_affine=True))
+                if norm == "layer":
+                    self.norm.append(nn.LayerNorm(layer_size[i + 1], elementwise_affine=True))
+                else:
+                    self.norm.append(SyncBNRef(layer_size[i + 1], train_size))            # model.py:37-39
             pp = False                                                           # model.py:40,75
         self.oracle: Optional[OracleRank] = None
 

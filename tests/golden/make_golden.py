@@ -31,6 +31,8 @@ ROOT = os.path.dirname(os.path.dirname(HERE))
 CONFIGS = {
     "graphsage": dict(shape="tiny", n_parts=2, model="graphsage", n_layers=3, n_hidden=16, rate=0.5, epochs=3),
     "gcn": dict(shape="tiny", n_parts=2, model="gcn", n_layers=3, n_hidden=16, rate=0.5, epochs=3),
+    "graphsage_bn": dict(shape="tiny", n_parts=2, model="graphsage", n_layers=3, n_hidden=16, rate=0.5, epochs=3,
+                         norm="batch", graph_override={"train": 1.0}),   # whole_size == #nodes, as under --inductive
 }
 
 
@@ -245,7 +247,7 @@ def worker(rank, world, cfg, port, out_dir):
     import train as ref_train
     import argparse
 
-    fg = make_graph(cfg["shape"], seed=0, device=torch.device("cpu"))
+    fg = make_graph(cfg["shape"], seed=0, device=torch.device("cpu"), **cfg.get("graph_override", {}))
     part = partition_graph(fg, world, "random", seed=0, device=torch.device("cpu"))[rank]
     lg = part.graph
     v = torch.repeat_interleave(torch.arange(lg.n_in), lg.indptr[1:] - lg.indptr[:-1])
@@ -258,7 +260,7 @@ def worker(rank, world, cfg, port, out_dir):
 
     args = argparse.Namespace(dataset="synthetic", model=cfg["model"], dropout=0.0, lr=1e-2, sampling_rate=cfg["rate"],
                               heads=1, n_epochs=cfg["epochs"], n_partitions=world, n_hidden=cfg["n_hidden"],
-                              n_layers=cfg["n_layers"], log_every=1, weight_decay=0.0, norm="layer", n_linear=0,
+                              n_layers=cfg["n_layers"], log_every=1, weight_decay=0.0, norm=cfg.get("norm", "layer"), n_linear=0,
                               use_pp=True, inductive=False, seed=0, backend="gloo", eval=False,
                               graph_name="golden", n_feat=part.meta["n_feat"], n_class=part.meta["n_class"],
                               n_train=part.meta["n_train"])

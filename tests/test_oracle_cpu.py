@@ -19,19 +19,20 @@ def _oracle_run(cfg, selected_per_epoch):
     import bns_gcn_b200  # noqa: F401
     from bns_gcn_b200.data import make_graph, partition_graph
     from oracle import bns_oracle as O
-    fg = make_graph(cfg["shape"], seed=0, device=torch.device("cpu"))
+    fg = make_graph(cfg["shape"], seed=0, device=torch.device("cpu"), **cfg.get("graph_override", {}))
     parts = partition_graph(fg, cfg["n_parts"], "random", seed=0, device=torch.device("cpu"))
 
     def fn(comm, r):
         rk = O.OracleRank(O.RankInput.from_partition(parts[r]), comm, model=cfg["model"], n_layers=cfg["n_layers"],
-                          n_hidden=cfg["n_hidden"], sampling_rate=cfg["rate"], dropout=0.0, seed=0)
+                          n_hidden=cfg["n_hidden"], sampling_rate=cfg["rate"], dropout=0.0, seed=0,
+                          norm=cfg.get("norm", "layer"))
         for e in range(cfg["epochs"]):
             rk.epoch(selected=selected_per_epoch[e][r], trace=True)
         return rk
     return O.run_threads(cfg["n_parts"], fn)
 
 
-@pytest.mark.parametrize("name", ["graphsage", "gcn"])
+@pytest.mark.parametrize("name", ["graphsage", "gcn", "graphsage_bn"])
 def test_oracle_reproduces_reference_golden(name):
     """The oracle, fed the index sets the reference drew, reproduces what the reference computed:
     boundary sets exactly; precomputed features, layer outputs, logits, reduced grads, updated weights to 1e-5."""
@@ -39,6 +40,11 @@ def test_oracle_reproduces_reference_golden(name):
     cfg, ranks = gold["config"], gold["ranks"]
     sel = [[ranks[r]["selected"][e] for r in range(cfg["n_parts"])] for e in range(cfg["epochs"])]
     out = _oracle_run(cfg, sel)
+    # --norm batch: a bias that feeds a BatchNorm has an exactly-zero true gradient (BN removes the mean), so what
+    # reaches Adam is rounding noise that it normalises into +-lr steps; BN cancels the resulting shift downstream.
+    # Those biases, and the pre-BN layer outputs they shift, are not comparable; everything else is.
+    bn = cfg.get("norm") == "batch"
+    last = cfg["n_layers"] - 1
     for r, rk in enumerate(out):
         g = ranks[r]
         for j, b in enumerate(g["boundary"]):
@@ -46,11 +52,16 @@ def test_oracle_reproduces_reference_golden(name):
                 assert torch.equal(rk.boundary[j], b)
         assert _rel(rk.feat, g["feat0"]) < 1e-6
         for i, lo in enumerate(g["layer_out"][-1]):
+            if bn and i < last:
+                continue
             assert _rel(rk.trace[f"layer{i}"], lo) < 1e-5, (r, i)
         assert _rel(rk.trace["logits"], g["logits"][-1]) < 1e-5
         for k, (p, gp, gg) in enumerate(zip(rk.net.parameters(), g["params"], g["grads"])):
-            assert _rel(p.detach(), gp) < 1e-5, (r, g["param_names"][k])
-            assert _rel(p.grad, gg) < 1e-5, (r, g["param_names"][k])
+            nm = g["param_names"][k]
+            if bn and nm.endswith("bias") and nm.startswith("layers.") and int(nm.split(".")[1]) < last:
+                continue
+            assert _rel(p.detach(), gp) < 1e-5, (r, nm)
+            assert _rel(p.grad, gg) < 1e-5, (r, nm)
         # parameter order / names are the reference's
         assert [n for n, _ in rk.net.named_parameters()] == g["param_names"]
 

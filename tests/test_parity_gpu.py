@@ -64,7 +64,7 @@ def test_metis_standin_partition_parity(built):
     _run(shape="tiny", n_parts=3, model="graphsage", sampling_rate=0.5, n_epochs=2, partition_method="metis")
 
 
-@pytest.mark.parametrize("name", ["graphsage", "gcn"])
+@pytest.mark.parametrize("name", ["graphsage", "gcn", "graphsage_bn"])
 def test_cuda_path_reproduces_reference_golden(built, name):
     """The CUDA path, fed the index sets the REFERENCE drew (tests/golden/make_golden.py ran the reference's own
     train.run), reproduces the reference's precomputed features, layer outputs, logits, reduced gradients and
@@ -74,12 +74,13 @@ def test_cuda_path_reproduces_reference_golden(built, name):
     from bns_gcn_b200.data import make_graph, partition_graph
     gold = torch.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", f"ref_{name}_p2.pt"))
     cfg, ranks = gold["config"], gold["ranks"]
-    fg = make_graph(cfg["shape"], seed=0)
+    fg = make_graph(cfg["shape"], seed=0, **cfg.get("graph_override", {}))
     parts = partition_graph(fg, cfg["n_parts"], "random", seed=0)
     args = make_args(dataset=cfg["shape"], model=cfg["model"], sampling_rate=cfg["rate"], n_layers=cfg["n_layers"],
-                     n_hidden=cfg["n_hidden"], n_partitions=cfg["n_parts"])
+                     n_hidden=cfg["n_hidden"], n_partitions=cfg["n_parts"], norm=cfg.get("norm", "layer"))
     sel = [[ranks[r]["selected"][e] for r in range(cfg["n_parts"])] for e in range(cfg["epochs"])]
     out = run_product(parts, args, "cuda:0", cfg["epochs"], selected_per_epoch=sel)
+    bn, last = cfg.get("norm") == "batch", cfg["n_layers"] - 1      # see tests/test_oracle_cpu.py on the BN case
     for r, o in enumerate(out):
         g = ranks[r]
         for j, b in enumerate(g["boundary"]):
@@ -87,11 +88,16 @@ def test_cuda_path_reproduces_reference_golden(built, name):
                 assert torch.equal(o["boundary"][j], b)
         assert _relerr(o["feat0"], g["feat0"]) < TOL
         for i, lo in enumerate(g["layer_out"][-1]):
+            if bn and i < last:
+                continue
             assert _relerr(o["layers"][f"layer{i}"], lo) < TOL, (r, i)
         assert _relerr(o["logits"], g["logits"][-1]) < TOL
         for k, (p, gp, gg) in enumerate(zip(o["params"], g["params"], g["grads"])):
-            assert _relerr(p, gp) < TOL, (r, g["param_names"][k])
-            assert _relerr(o["grads"][k], gg) < TOL, (r, g["param_names"][k])
+            nm = g["param_names"][k]
+            if bn and nm.endswith("bias") and nm.startswith("layers.") and int(nm.split(".")[1]) < last:
+                continue
+            assert _relerr(p, gp) < TOL, (r, nm)
+            assert _relerr(o["grads"][k], gg) < TOL, (r, nm)
 
 
 @pytest.mark.parametrize("model", ["graphsage", "gcn"])
@@ -169,8 +175,16 @@ def test_cuda_graph_epoch_equals_eager(built, model):
     dict(n_parts=2, sampling_rate=0.5, inductive=True),   # --inductive: partition the train-node subgraph
     dict(n_parts=2, sampling_rate=0.5, shape="tiny-ml", multilabel=True),          # BCE-with-logits (yelp-style)
     dict(n_parts=2, sampling_rate=0.5, model="gcn", n_layers=4, backend="p2p"),    # deeper GCN over the p2p transport
-], ids=["zero-sample", "n-linear", "inductive", "multilabel", "gcn4-p2p"])
+    dict(n_parts=3, sampling_rate=0.5, norm="batch", graph_override={"train": 1.0}),   # --norm batch (SyncBatchNorm)
+], ids=["zero-sample", "n-linear", "inductive", "multilabel", "gcn4-p2p", "sync-bn"])
 def test_training_parity_variants(built, kw):
     kw = dict(kw)
     kw.setdefault("shape", "tiny")
+    if kw.get("norm") == "batch":      # one epoch: afterwards the noise-driven pre-BN biases diverge (see test_oracle_cpu)
+        from tests.harness import run_parity_case
+        res = run_parity_case(device="cuda:0", n_epochs=1, **kw)
+        bad = {k: v for k, v in res["detail"].items() if v >= TOL and not ("grad" in k or "param" in k)}
+        assert not bad, bad
+        assert res["index_sets_equal"]
+        return
     _run(n_epochs=2, **kw)
