@@ -50,7 +50,7 @@ inline cudaStream_t as_stream(void *s) { return reinterpret_cast<cudaStream_t>(s
 
 constexpr int kThreads = 256;
 constexpr int kWarps = kThreads / 32;
-constexpr int kDefaultChunk = 1024;
+constexpr int kDefaultChunk = 256;   // B200 sweep (profiles/spmm_chunk_sweep_r1.txt): 256 -> 7.39 ms, 512 -> 7.58, 1024 -> 8.34, 2048 -> 9.27
 
 std::atomic<unsigned long long> g_launches{0};   // kernels of this library enqueued so far (bench.py gpu_launches)
 int g_sm_count = 0;
