@@ -29,8 +29,11 @@ SIGNATURES = {
                                POINTER(c_int64)]),
     "bns_graph_copy_csr": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p]),
     "bns_spmm_workspace_bytes": (c_size_t, [c_void_p, c_int64]),
-    "bns_spmm_sum_f32": (c_int, [c_void_p, c_void_p, c_int64, c_int64, c_void_p, c_int64, c_void_p, c_void_p,
+    "bns_spmm_sum_f32": (c_int, [c_void_p, c_void_p, c_int64, c_int64, c_void_p, c_int64, c_void_p, c_void_p, c_void_p,
                                  c_void_p, c_void_p, c_int64, c_int64, c_int32, c_int, c_void_p, c_size_t, c_void_p]),
+    "bns_sddmm_dot_f32": (c_int, [c_void_p, c_void_p, c_int64, c_void_p, c_int64, c_int64, c_void_p, c_void_p, c_int64,
+                                  c_void_p, c_int64, c_void_p]),
+    "bns_graph_copy_perm": (c_int, [c_void_p, c_void_p, c_void_p]),
     "bns_gather_div_f32": (c_int, [c_void_p, c_int64, c_int64, c_void_p, c_int64, c_float, c_void_p, c_int64, c_void_p]),
     "bns_scatter_add_div_f32": (c_int, [c_void_p, c_int64, c_int64, c_void_p, c_int64, c_float, c_void_p, c_int64,
                                         c_void_p]),

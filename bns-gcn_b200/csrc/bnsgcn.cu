@@ -79,6 +79,7 @@ struct bns_graph {
     int32_t *chunk_part = nullptr;  // [n_chunks]  partial-sum slot, -1 when the row is a single chunk
     int32_t *split_row = nullptr;   // [n_split]
     int32_t *split_part = nullptr;  // [n_split+1] first partial slot of each split row
+    int32_t *perm = nullptr;        // transposes only: [nnz] entry k of this graph is entry perm[k] of its source
 };
 
 // =================================================================================================
@@ -143,6 +144,17 @@ __global__ void lower_bound_kernel(const int32_t *__restrict__ sorted_keys, int6
         if ((int64_t)sorted_keys[mid] < c) lo = mid + 1; else hi = mid;
     }
     indptr[c] = lo;
+}
+
+__global__ void iota_i32_kernel(int32_t *dst, int64_t n) {
+    int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (i < n) dst[i] = (int32_t)i;
+}
+
+__global__ void gather_i32_kernel(const int32_t *__restrict__ src, const int32_t *__restrict__ idx, int64_t n,
+                                  int32_t *__restrict__ dst) {
+    int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (i < n) dst[i] = src[idx[i]];
 }
 
 __global__ void check_indices_kernel(const int32_t *__restrict__ idx, int64_t nnz, int64_t n_cols, int *bad) {
@@ -225,7 +237,7 @@ extern "C" int bns_device_info(char *name, size_t name_len, int *sms, int64_t *l
 extern "C" int bns_graph_destroy(bns_graph_t *g) {
     if (!g) return BNS_OK;
     cudaFree(g->indptr); cudaFree(g->indices); cudaFree(g->chunk_row); cudaFree(g->chunk_start);
-    cudaFree(g->chunk_part); cudaFree(g->split_row); cudaFree(g->split_part);
+    cudaFree(g->chunk_part); cudaFree(g->split_row); cudaFree(g->split_part); cudaFree(g->perm);
     delete g;
     return BNS_OK;
 }
@@ -297,19 +309,35 @@ extern "C" int bns_graph_transpose(const bns_graph_t *g, bns_graph_t **out, void
         int64_t threads = g->n_rows * 32;
         expand_rows_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, st>>>(g->indptr, g->n_rows, rows);
     }
+    int32_t *eid = nullptr, *perm = nullptr;
+    BNS_CUDA(cudaMalloc(&eid, (nnz + 1) * sizeof(int32_t)));
+    BNS_CUDA(cudaMalloc(&perm, (nnz + 1) * sizeof(int32_t)));
+    if (nnz > 0) iota_i32_kernel<<<(unsigned)((nnz + 255) / 256), 256, 0, st>>>(eid, nnz);
     int end_bit = 1;
     while (end_bit < 32 && ((int64_t)1 << end_bit) < g->n_cols) ++end_bit;
-    BNS_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, g->indices, keys_out, rows, vals_out, (int)nnz, 0,
+    // stable sort of the entries by column: values = entry ids, so the permutation survives (per-entry weights of
+    // the source graph -- GAT attention -- are carried to the transpose with it)
+    BNS_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, g->indices, keys_out, eid, perm, (int)nnz, 0,
                                              end_bit, st));
     BNS_CUDA(cudaMalloc(&tmp, tmp_bytes ? tmp_bytes : 16));
-    BNS_CUDA(cub::DeviceRadixSort::SortPairs(tmp, tmp_bytes, g->indices, keys_out, rows, vals_out, (int)nnz, 0,
+    BNS_CUDA(cub::DeviceRadixSort::SortPairs(tmp, tmp_bytes, g->indices, keys_out, eid, perm, (int)nnz, 0,
                                              end_bit, st));
+    if (nnz > 0) gather_i32_kernel<<<(unsigned)((nnz + 255) / 256), 256, 0, st>>>(rows, perm, nnz, vals_out);
     lower_bound_kernel<<<(unsigned)((g->n_cols + 1 + 255) / 256), 256, 0, st>>>(keys_out, nnz, g->n_cols, t_indptr);
     BNS_CUDA(cudaGetLastError());
     BNS_CUDA(cudaStreamSynchronize(st));
     int rc = bns_graph_create(out, g->n_cols, g->n_rows, nnz, t_indptr, vals_out, g->chunk_nnz, stream);
-    cudaFree(rows); cudaFree(keys_out); cudaFree(vals_out); cudaFree(t_indptr); cudaFree(tmp);
+    if (rc == BNS_OK) (*out)->perm = perm; else cudaFree(perm);
+    cudaFree(rows); cudaFree(keys_out); cudaFree(vals_out); cudaFree(t_indptr); cudaFree(tmp); cudaFree(eid);
     return rc;
+}
+
+extern "C" int bns_graph_copy_perm(const bns_graph_t *g, int32_t *perm_out, void *stream) {
+    BNS_REQUIRE(g && perm_out, "bns_graph_copy_perm: NULL argument");
+    BNS_REQUIRE(g->perm != nullptr, "bns_graph_copy_perm: not a graph made by bns_graph_transpose");
+    if (g->nnz)
+        BNS_CUDA(cudaMemcpyAsync(perm_out, g->perm, g->nnz * sizeof(int32_t), cudaMemcpyDeviceToDevice, as_stream(stream)));
+    return BNS_OK;
 }
 
 extern "C" int bns_graph_info(const bns_graph_t *g, int64_t *n_rows, int64_t *n_cols, int64_t *nnz,
@@ -355,6 +383,7 @@ struct SpmmArgs {
     int32_t F;
     const float *row_scale;
     const float *col_scale;
+    const float *edge_weight;   // per entry (CSR order) or NULL
     const int32_t *row_map;
     const int32_t *col_map;
     int32_t n_direct;
@@ -392,6 +421,12 @@ template <> struct Vec<1> {
     __device__ __forceinline__ void scale(float s) { v *= s; }
     __device__ __forceinline__ void add_shfl_xor(int off) { v += __shfl_xor_sync(0xffffffffu, v, off); }
 };
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
 
 __device__ __forceinline__ int32_t ld_stream_i32(const int32_t *p) {
     int32_t r;
@@ -452,7 +487,10 @@ __global__ void __launch_bounds__(kThreads) spmm_kernel(SpmmArgs a) {
             float sc = 1.f;
             if (k < e) {
                 col = ld_stream_i32(a.indices + k);
-                if (CSCALE) sc = __ldg(a.col_scale + col);
+                if (CSCALE) {        // per-source and / or per-entry weight (GAT attention) -> the FMA path
+                    if (a.col_scale) sc = __ldg(a.col_scale + col);
+                    if (a.edge_weight) sc *= __ldg(a.edge_weight + k);
+                }
                 if (MAP) {
                     if (col >= a.n_direct) col = __ldg(a.col_map + (col - a.n_direct));
                 }
@@ -612,7 +650,7 @@ int launch_spmm(SpmmArgs a, cudaStream_t st) {
 
 template <int W, int G, int NV>
 int dispatch_flags(const SpmmArgs &a, cudaStream_t st) {
-    const bool map = a.col_map != nullptr, cs = a.col_scale != nullptr;
+    const bool map = a.col_map != nullptr, cs = a.col_scale != nullptr || a.edge_weight != nullptr;
     const bool guard = (a.F % (G * W * NV)) != 0;
     if (guard) {
         if (map && cs) return launch_spmm<W, G, NV, true, true, true>(a, st);
@@ -670,9 +708,9 @@ extern "C" size_t bns_spmm_workspace_bytes(const bns_graph_t *g, int64_t F) {
 }
 
 extern "C" int bns_spmm_sum_f32(const bns_graph_t *g, const float *X, int64_t ldx, int64_t F, float *Y, int64_t ldy,
-                                const float *row_scale, const float *col_scale, const int32_t *row_map,
-                                const int32_t *col_map, int64_t n_direct, int64_t x_rows, int32_t slab_hint,
-                                int accumulate, void *ws, size_t ws_bytes, void *stream) {
+                                const float *row_scale, const float *col_scale, const float *edge_weight,
+                                const int32_t *row_map, const int32_t *col_map, int64_t n_direct, int64_t x_rows,
+                                int32_t slab_hint, int accumulate, void *ws, size_t ws_bytes, void *stream) {
     BNS_REQUIRE(g, "bns_spmm_sum_f32: NULL graph");
     BNS_REQUIRE(F > 0 && F < (1 << 24), "bns_spmm_sum_f32: bad feature width %lld", (long long)F);
     if (g->n_rows == 0) return BNS_OK;      // nothing to write (Y may legitimately be NULL)
@@ -691,7 +729,7 @@ extern "C" int bns_spmm_sum_f32(const bns_graph_t *g, const float *X, int64_t ld
     a.split_row = g->split_row; a.split_part = g->split_part;
     a.n_chunks = g->n_chunks; a.n_split = g->n_split; a.chunk_nnz = g->chunk_nnz;
     a.X = X; a.ldx = ldx; a.Y = Y; a.ldy = ldy; a.F = (int32_t)F;
-    a.row_scale = row_scale; a.col_scale = col_scale; a.row_map = row_map; a.col_map = col_map;
+    a.row_scale = row_scale; a.col_scale = col_scale; a.edge_weight = edge_weight; a.row_map = row_map; a.col_map = col_map;
     a.n_direct = (int32_t)n_direct; a.accumulate = accumulate ? 1 : 0;
     a.ws = reinterpret_cast<float *>(ws); a.ldws = ws_ld(F);
     a.n_tiles = 1;
@@ -710,6 +748,112 @@ extern "C" int bns_spmm_sum_f32(const bns_graph_t *g, const float *X, int64_t ld
     } else {
         dispatch_flags<1, 32, 8>(a, st);
     }
+    BNS_CUDA(cudaGetLastError());
+    return BNS_OK;
+}
+
+// =================================================================================================
+// SDDMM (dot): out[k] = < A[arow(r), :], B[xrow(c_k), :] > for every entry k of row r
+// (the attention gradient of GAT: d a_uv = <dOut[v], ft[u]>, the transpose partner of the weighted SpMM)
+// =================================================================================================
+namespace {
+
+struct SddmmArgs {
+    const int64_t *indptr;
+    const int32_t *indices;
+    const int32_t *chunk_row;
+    const int64_t *chunk_start;
+    int64_t n_chunks;
+    int32_t chunk_nnz;
+    const float *A; int64_t lda;
+    const float *B; int64_t ldb;
+    int32_t F;
+    const int32_t *row_map, *col_map;
+    int32_t n_direct;
+    float *out; int64_t ldo;          // out[k * ldo]
+};
+
+// one warp per chunk; the lanes keep their slice of A[row] in registers and walk the entries like the SpMM does
+template <int NV>
+__global__ void __launch_bounds__(kThreads) sddmm_dot_kernel(SddmmArgs a) {
+    __shared__ int32_t s_col[kWarps][32];
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    const int64_t warps_total = (int64_t)gridDim.x * kWarps;
+    for (int64_t c = (int64_t)blockIdx.x * kWarps + w; c < a.n_chunks; c += warps_total) {
+        const int32_t row = a.chunk_row[c];
+        const int64_t s = a.chunk_start[c];
+        int64_t e = a.indptr[row + 1];
+        if (e > s + a.chunk_nnz) e = s + a.chunk_nnz;
+        int32_t arow = row;
+        if (a.row_map) arow = a.row_map[row];
+        float4 av[NV];
+#pragma unroll
+        for (int t = 0; t < NV; ++t) {
+            const int f = (lane + 32 * t) * 4;
+            av[t] = (arow >= 0 && f < a.F) ? *reinterpret_cast<const float4 *>(a.A + (int64_t)arow * a.lda + f)
+                                            : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+        for (int64_t k0 = s; k0 < e; k0 += 32) {
+            const int64_t k = k0 + lane;
+            int32_t col = -1;
+            if (k < e) {
+                col = ld_stream_i32(a.indices + k);
+                if (a.col_map && col >= a.n_direct) col = __ldg(a.col_map + (col - a.n_direct));
+                if (arow < 0) col = -1;
+            }
+            s_col[w][lane] = col;
+            __syncwarp();
+            const int cnt = (e - k0) < 32 ? (int)(e - k0) : 32;
+            float mine = 0.f;
+            for (int j = 0; j < cnt; ++j) {
+                const int32_t cj = s_col[w][j];
+                float d = 0.f;
+                if (cj >= 0) {
+                    const float *br = a.B + (int64_t)cj * a.ldb;
+#pragma unroll
+                    for (int t = 0; t < NV; ++t) {
+                        const int f = (lane + 32 * t) * 4;
+                        if (f < a.F) {
+                            const float4 b = __ldg(reinterpret_cast<const float4 *>(br + f));
+                            d += (av[t].x * b.x + av[t].y * b.y) + (av[t].z * b.z + av[t].w * b.w);
+                        }
+                    }
+                }
+                d = warp_sum(d);
+                if (lane == j) mine = d;
+            }
+            if (k < e) a.out[k * a.ldo] = mine;
+            __syncwarp();
+        }
+    }
+}
+
+}  // namespace
+
+extern "C" int bns_sddmm_dot_f32(const bns_graph_t *g, const float *A, int64_t lda, const float *B, int64_t ldb, int64_t F,
+                                 const int32_t *row_map, const int32_t *col_map, int64_t n_direct, float *out,
+                                 int64_t ldo, void *stream) {
+    BNS_REQUIRE(g, "bns_sddmm_dot_f32: NULL graph");
+    BNS_REQUIRE(F > 0 && F % 4 == 0 && F <= 1024, "bns_sddmm_dot_f32: need F %% 4 == 0 and F <= 1024 (got %lld)", (long long)F);
+    if (g->nnz == 0) return BNS_OK;
+    BNS_REQUIRE(A && B && out, "bns_sddmm_dot_f32: NULL pointer");
+    BNS_REQUIRE(lda % 4 == 0 && ldb % 4 == 0 && lda >= F && ldb >= F && ldo >= 1, "bns_sddmm_dot_f32: bad leading dimension");
+    BNS_REQUIRE(((reinterpret_cast<uintptr_t>(A) | reinterpret_cast<uintptr_t>(B)) % 16) == 0, "bns_sddmm_dot_f32: unaligned");
+    if (col_map == nullptr) n_direct = g->n_cols;
+    SddmmArgs a;
+    a.indptr = g->indptr; a.indices = g->indices; a.chunk_row = g->chunk_row; a.chunk_start = g->chunk_start;
+    a.n_chunks = g->n_chunks; a.chunk_nnz = g->chunk_nnz;
+    a.A = A; a.lda = lda; a.B = B; a.ldb = ldb; a.F = (int32_t)F; a.row_map = row_map; a.col_map = col_map;
+    a.n_direct = (int32_t)n_direct; a.out = out; a.ldo = ldo;
+    int64_t want = (a.n_chunks + kWarps - 1) / kWarps, cap = (int64_t)sm_count() * 6;
+    unsigned gx = (unsigned)(want < cap ? (want > 0 ? want : 1) : cap);
+    cudaStream_t st = as_stream(stream);
+    const int nv = (int)((F + 127) / 128);
+    if (nv <= 1) sddmm_dot_kernel<1><<<gx, kThreads, 0, st>>>(a);
+    else if (nv == 2) sddmm_dot_kernel<2><<<gx, kThreads, 0, st>>>(a);
+    else if (nv <= 4) sddmm_dot_kernel<4><<<gx, kThreads, 0, st>>>(a);
+    else sddmm_dot_kernel<8><<<gx, kThreads, 0, st>>>(a);
+    ++g_launches;
     BNS_CUDA(cudaGetLastError());
     return BNS_OK;
 }
@@ -933,12 +1077,6 @@ struct LnArgs {
     const uint64_t *offset_dev;
     float *partial;                 // backward: [gridDim.x][2][F] column partial sums (dgamma, dbeta)
 };
-
-__device__ __forceinline__ float warp_sum(float v) {
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-    return v;
-}
 
 // keep-mask of the 4 elements of vector `vec` of row `row`: one Philox4x32-10 call
 __device__ __forceinline__ void drop_mask4(uint64_t seed, uint64_t offset, int64_t row, int vec, float p, bool keep[4]) {

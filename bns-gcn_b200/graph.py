@@ -96,3 +96,57 @@ class PartitionAggregate(torch.autograd.Function):
                 ops.spmm(g.a_out_t, dy, tail, row_scale=ctx.cs_halo, row_map=g.slot)
         ops.spmm(g.a_in_t, dy, du[:g.n_in], row_scale=ctx.cs_in)
         return du, None, None, None, None, None
+
+
+def _entry_rows(a: ops.DeviceGraph):
+    """(row id, column id) of every CSR entry of ``a`` as int64 vectors (static, built once)."""
+    indptr, indices = a.csr()
+    rows = torch.repeat_interleave(torch.arange(a.n_rows, device=indptr.device), indptr[1:] - indptr[:-1])
+    return rows, indices.long()
+
+
+def gat_entries(g: PartitionGraph):
+    """Static per-entry index vectors the attention scores are computed on (rows / cols of a_in and a_out)."""
+    if getattr(g, "_gat_entries", None) is None:
+        rin, cin = _entry_rows(g.a_in)
+        if g.a_out is not None:
+            rout, cout = _entry_rows(g.a_out)
+        else:
+            rout = cout = torch.empty(0, dtype=torch.int64, device=g.device)
+        g._gat_entries = (rin, cin, rout, cout)
+    return g._gat_entries
+
+
+class WeightedAggregate(torch.autograd.Function):
+    """``rst[v] = sum_k w_k * ft_u[xrow(c_k)]`` over the inner entries (weights ``w_in``) and the sampled halo entries
+    (``w_out``; unsampled entries are skipped through the slot map) -- DGL's ``update_all(u_mul_e, sum)`` of GATConv.
+    Backward: ``d ft = A_w^T d rst`` (weights carried to the transposes by their entry permutation) and
+    ``d w_k = <d rst[v], ft_u[xrow(c_k)]>`` (``bns_sddmm_dot_f32``)."""
+
+    @staticmethod
+    def forward(ctx, ft_u, w_in, w_out, g: PartitionGraph):
+        ft_u, w_in, w_out = ft_u.contiguous(), w_in.contiguous(), w_out.contiguous()
+        ctx.g = g
+        ctx.save_for_backward(ft_u, w_in, w_out)
+        y = ops.spmm(g.a_in, ft_u, edge_weight=w_in)
+        if g.a_out is not None and ft_u.shape[0] > g.n_in:
+            ops.spmm(g.a_out, ft_u[g.n_in:], y, edge_weight=w_out, col_map=g.slot, n_direct=0, accumulate=True)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        g = ctx.g
+        ft_u, w_in, w_out = ctx.saved_tensors
+        dy = dy.contiguous()
+        n_u, n_in = ft_u.shape[0], g.n_in
+        d_ft = torch.empty_like(ft_u)
+        ops.spmm(g.a_in_t, dy, d_ft[:n_in], edge_weight=w_in[g.a_in_t.perm().long()])
+        d_w_in = ops.sddmm_dot(g.a_in, dy, ft_u)
+        d_w_out = torch.zeros_like(w_out)
+        if n_u > n_in:
+            tail = d_ft[n_in:]
+            tail.zero_()
+            if g.a_out_t is not None:
+                ops.spmm(g.a_out_t, dy, tail, edge_weight=w_out[g.a_out_t.perm().long()], row_map=g.slot)
+                ops.sddmm_dot(g.a_out, dy, ft_u[n_in:], col_map=g.slot, n_direct=0, out=d_w_out)
+        return d_ft, d_w_in, d_w_out, None

@@ -90,6 +90,42 @@ class GraphSAGE(GNNBase):
 
 
 class GAT(GNNBase):
+    """module/model.py:96-132."""
 
-    def __init__(self, *a, **k):
-        raise NotImplementedError("GAT (dgl.nn.GATConv, module/model.py:96-132) is a SURVEY.md §8(f) 'next' row")
+    def __init__(self, layer_size, activation, use_pp, heads=1, dropout=0.5, norm='layer', train_size=None, n_linear=0):
+        super(GAT, self).__init__(layer_size, activation, use_pp, dropout, norm, n_linear)
+        from .gat import GATConv
+        for i in range(self.n_layers):
+            if i < self.n_layers - self.n_linear:
+                self.layers.append(GATConv(layer_size[i], layer_size[i + 1], heads, dropout, dropout))
+            else:
+                self.layers.append(nn.Linear(layer_size[i], layer_size[i + 1]))
+            if i < self.n_layers - 1 and self.use_norm:
+                if norm == 'layer':
+                    self.norm.append(nn.LayerNorm(layer_size[i + 1], elementwise_affine=True))
+                elif norm == 'batch':
+                    from .sync_bn import SyncBatchNorm
+                    self.norm.append(SyncBatchNorm(layer_size[i + 1], train_size))
+
+    def forward(self, g, feat):
+        h = feat
+        for i in range(self.n_layers):
+            if i < self.n_layers - self.n_linear:
+                if self.training:
+                    if i > 0 or not self.use_pp:
+                        h1 = ctx.buffer.update(i, h, overlap=True)                # model.py:117-118
+                    else:
+                        h1 = h
+                        h = h[0:g.num_nodes('_V')]                                # :120-121
+                    h = self.layers[i](g, (h1, h))
+                else:
+                    h = self.layers[i](g, h)
+                h = h.mean(1)
+            else:
+                h = self.dropout(h)
+                h = self.layers[i](h)
+            if i < self.n_layers - 1:
+                if self.use_norm:
+                    h = self.norm[i](h)
+                h = self.activation(h)
+        return h

@@ -93,6 +93,15 @@ class DeviceGraph:
                                          _stream_ptr()), "bns_graph_copy_csr")
         return indptr, indices
 
+    def perm(self) -> torch.Tensor:
+        """For a transpose: ``perm[k]`` = position in the source graph's CSR of the entry that is entry ``k`` here."""
+        if getattr(self, "_perm", None) is None:
+            p = torch.empty(self.nnz, dtype=torch.int32, device=self.device)
+            with torch.cuda.device(self.device):
+                check(lib.bns_graph_copy_perm(self._h, p.data_ptr(), _stream_ptr()), "bns_graph_copy_perm")
+            self._perm = p
+        return self._perm
+
     def workspace(self, F: int) -> Optional[torch.Tensor]:
         need = lib.bns_spmm_workspace_bytes(self._h, F)
         if need == 0:
@@ -115,7 +124,7 @@ class DeviceGraph:
 def spmm(g: DeviceGraph, x: torch.Tensor, out: Optional[torch.Tensor] = None, *, n_out_rows: Optional[int] = None,
          row_scale: Optional[torch.Tensor] = None, col_scale: Optional[torch.Tensor] = None,
          row_map: Optional[torch.Tensor] = None, col_map: Optional[torch.Tensor] = None, n_direct: int = 0,
-         accumulate: bool = False, slab: int = 0) -> torch.Tensor:
+         accumulate: bool = False, slab: int = 0, edge_weight: Optional[torch.Tensor] = None) -> torch.Tensor:
     """``bns_spmm_sum_f32``: ``out[orow(r)] (+)= row_scale[r] * sum_k col_scale[c_k] * x[xrow(c_k)]``."""
     _req(x, torch.float32, "x")
     if x.dim() != 2 or x.stride(1) != 1:
@@ -140,8 +149,8 @@ def spmm(g: DeviceGraph, x: torch.Tensor, out: Optional[torch.Tensor] = None, *,
         ev0.record(torch.cuda.current_stream(x.device))
     with torch.cuda.device(x.device):
         check(lib.bns_spmm_sum_f32(g._h, x.data_ptr(), x.stride(0), F, out.data_ptr(), out.stride(0),
-                                   _ptr(row_scale), _ptr(col_scale), _ptr(row_map), _ptr(col_map), n_direct,
-                                   x.shape[0], slab, 1 if accumulate else 0, _ptr(ws), 0 if ws is None else ws.numel(), _stream_ptr()),
+                                   _ptr(row_scale), _ptr(col_scale), _ptr(edge_weight), _ptr(row_map), _ptr(col_map),
+                                   n_direct, x.shape[0], slab, 1 if accumulate else 0, _ptr(ws), 0 if ws is None else ws.numel(), _stream_ptr()),
               "bns_spmm_sum_f32")
     if prof is not None:
         ev1.record(torch.cuda.current_stream(x.device))
@@ -154,6 +163,21 @@ def spmm(g: DeviceGraph, x: torch.Tensor, out: Optional[torch.Tensor] = None, *,
         if row_map is not None:
             live = int(g.nnz * min(1.0, out.shape[0] / max(g.n_rows, 1)))
         prof.append((ev0, ev1, alg, g.nnz, F, live))
+    return out
+
+
+def sddmm_dot(g: DeviceGraph, a: torch.Tensor, b: torch.Tensor, *, row_map=None, col_map=None, n_direct: int = 0,
+              out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """``out[k] = <a[arow(r)], b[xrow(c_k)]>`` for every entry ``k`` (``bns_sddmm_dot_f32``)."""
+    _req(a, torch.float32, "a")
+    _req(b, torch.float32, "b")
+    F = a.shape[1]
+    if out is None:
+        out = torch.zeros(g.nnz, dtype=torch.float32, device=a.device)
+    with torch.cuda.device(a.device):
+        check(lib.bns_sddmm_dot_f32(g._h, a.data_ptr(), a.stride(0), b.data_ptr(), b.stride(0), F, _ptr(row_map),
+                                    _ptr(col_map), n_direct, out.data_ptr(), out.stride(0) if out.dim() else 1,
+                                    _stream_ptr()), "bns_sddmm_dot_f32")
     return out
 
 

@@ -181,6 +181,20 @@ def construct_out_norm(num, norm, pos, one_hops):
     return norm
 
 
+def construct_feat(num, feat, pos, one_hops):
+    """train.py:284-297 (GAT layer 0): ``[inner features | stored features of this epoch's sampled halo nodes]``."""
+    rank, size = _rank_size()
+    res = [feat[0:num]]
+    for i in range(size):
+        if i == rank:
+            continue
+        u = one_hops[i]
+        if u is None or u.shape[0] == 0:
+            continue
+        res.append(feat[pos[i][u]])
+    return torch.cat(res)
+
+
 def precompute(part: PartitionGraph, graph, node_dict, boundary, model, gpb, pos, out_deg_all=None):
     """train.py:170-211: the one-time layer-0 aggregation over ALL boundary nodes (sampling rate 1)."""
     rank, size = _rank_size()
@@ -311,7 +325,7 @@ def setup(graph: LocalGraph, node_dict, gpb, args, device=None) -> TrainState:
         in_norm = torch.sqrt(node_dict['in_deg'].float())                   # train.py:377-378
         out_norm = torch.sqrt(out_deg_all.float())
     else:
-        in_norm = node_dict['in_deg']                                       # train.py:380
+        in_norm = node_dict['in_deg']                                       # train.py:380 (unused by GAT)
     sampler = ops.BoundarySampler(boundary, send_size, dev) if size > 1 else None
     return TrainState(args, part, model, optimizer, loss_fcn, node_dict['feat'], labels, node_dict['train_mask'],
                       in_norm, out_norm, boundary, pos, send_size, recv_size, ratio, sampler, part_train,
@@ -351,6 +365,8 @@ def train_epoch(st: TrainState, epoch: int, selected: Optional[list] = None) -> 
         logits = st.model(g, st.feat, st.in_norm, st.out_norm)
     elif args.model == 'graphsage':
         logits = st.model(g, st.feat, st.in_norm)
+    elif args.model == 'gat':
+        logits = st.model(g, construct_feat(g.num_nodes('_V'), st.feat, st.pos, one_hops))     # train.py:401-402
     else:
         raise NotImplementedError
     # train.py:406 indexes with the boolean mask; the equivalent index list avoids a host sync per epoch

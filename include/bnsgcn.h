@@ -68,6 +68,9 @@ int bns_graph_transpose(const bns_graph_t *g, bns_graph_t **out, void *stream);
 int bns_graph_destroy(bns_graph_t *g);
 int bns_graph_info(const bns_graph_t *g, int64_t *n_rows, int64_t *n_cols, int64_t *nnz,
                    int64_t *n_chunks, int64_t *n_split_rows);
+/* For a graph made by bns_graph_transpose: perm_out[k] (device [nnz]) = index, in the SOURCE graph's CSR order, of
+ * the entry that became entry k of the transpose -- carries per-entry weights across (w_T[k] = w[perm[k]]). */
+int bns_graph_copy_perm(const bns_graph_t *gT, int32_t *perm_out, void *stream);
 /* Copy the library-owned CSR into caller buffers (device [n_rows+1] / [nnz]); for tests and tools. */
 int bns_graph_copy_csr(const bns_graph_t *g, int64_t *indptr_out, int32_t *indices_out, void *stream);
 
@@ -96,11 +99,24 @@ int bns_spmm_sum_f32(const bns_graph_t *g,
                      float *Y, int64_t ldy,
                      const float *row_scale /*device [n_rows] or NULL*/,
                      const float *col_scale /*device [n_cols] or NULL*/,
+                     const float *edge_weight /*device [nnz], CSR order, or NULL: multiplies entry k's source row
+                                                (GAT attention, u_mul_e + sum of dgl.nn.GATConv)*/,
                      const int32_t *row_map /*device [n_rows] or NULL*/,
                      const int32_t *col_map /*device [n_cols - n_direct] or NULL*/, int64_t n_direct,
                      int64_t x_rows /*rows of X that can be referenced (0 = n_cols); sizes the L2 blocking*/,
                      int32_t slab_hint /*0 = automatic; 256 | 128 | 64 | 32 forces the column-slab width*/,
                      int accumulate, void *ws, size_t ws_bytes, void *stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * K10 (GAT, module/model.py:96-132 via dgl.nn.GATConv): the attention gradient.  For every entry k of row r:
+ *     out[k * ldo] = < A[arow(r), :F], B[xrow(c_k), :F] >      (0 when the row or the entry is skipped)
+ * arow / xrow as in bns_spmm_sum_f32 (row_map / col_map / n_direct).  F % 4 == 0, F <= 1024, 16-byte aligned rows.
+ * With bns_spmm_sum_f32(edge_weight) and the transpose permutation this is all GATConv needs besides elementwise
+ * work on per-entry vectors: forward  rst = A_w ft,  backward  d ft = A_w^T d rst,  d w = sddmm(d rst, ft).
+ * ----------------------------------------------------------------------------------------------*/
+int bns_sddmm_dot_f32(const bns_graph_t *g, const float *A, int64_t lda, const float *B, int64_t ldb, int64_t F,
+                      const int32_t *row_map, const int32_t *col_map, int64_t n_direct, float *out, int64_t ldo,
+                      void *stream);
 
 /* ------------------------------------------------------------------------------------------------
  * K3 / K4 / K5: boundary pack / concat / scatter.  helper/feature_buffer.py:

@@ -270,7 +270,7 @@ class OracleRank:
     def __init__(self, inp: RankInput, comm, model: str = "graphsage", n_layers: int = 3, n_hidden: int = 16,
                  sampling_rate: float = 1.0, use_pp: bool = True, dropout: float = 0.0, norm: Optional[str] = "layer",
                  lr: float = 1e-2, weight_decay: float = 0.0, seed: int = 0, n_linear: int = 0,
-                 multilabel: bool = False):
+                 multilabel: bool = False, heads: int = 1):
         self.inp, self.comm = inp, comm
         self.rank, self.size = comm.rank, comm.size
         self.model_name, self.rate = model, sampling_rate
@@ -302,7 +302,7 @@ class OracleRank:
         self.feat = self._precompute()                                                       # train.py:351-352
         with _SEED_LOCK:          # ranks may be threads of one process: the global RNG is shared
             torch.manual_seed(seed)                                                          # train.py:331
-            self.net = build_model(model, self.layer_size, use_pp, dropout, norm, inp.n_train, n_linear)
+            self.net = build_model(model, self.layer_size, use_pp, dropout, norm, inp.n_train, n_linear, heads)
         self.net.oracle = self
         for m in self.net.modules():
             if isinstance(m, SyncBNRef):
@@ -436,6 +436,8 @@ class OracleRank:
             s = CopyUSum.apply(g, h_u)
             cnt = (g.csr()[0][1:] - g.csr()[0][:-1]).clamp(min=1).unsqueeze(-1)     # fn.mean: / #messages
             return torch.cat([feat, s / cnt], dim=1)
+        if self.model_name == "gat":
+            return h_u                                                                       # train.py:208-209
         raise NotImplementedError(self.model_name)
 
     # ---- train.py:225-236 --------------------------------------------------------------------
@@ -507,6 +509,12 @@ class OracleRank:
             parts = [self.out_norm[:self.n_in]] + [self.out_norm[self.pos[i][one_hops[i]]]
                                                    for i in range(self.size) if i != self.rank]   # train.py:245-253
             logits = self.net(g, self.feat, self.in_norm, torch.cat(parts))
+        elif self.model_name == "gat":
+            res = [self.feat[0:self.n_in]]                                                   # construct_feat, train.py:284-297
+            for i in range(self.size):
+                if i != self.rank and one_hops[i].shape[0] > 0:
+                    res.append(self.feat[self.pos[i][one_hops[i]]])
+            logits = self.net(g, torch.cat(res))
         else:
             logits = self.net(g, self.feat, self.in_norm)
         mask = self.inp.train_mask
@@ -706,7 +714,94 @@ class GNNRef(nn.Module):
         return h
 
 
-def build_model(kind, layer_size, use_pp, dropout, norm, train_size, n_linear) -> GNNRef:
+class GATConvRef(nn.Module):
+    """``dgl.nn.GATConv(in, out, heads, feat_drop, attn_drop)`` as module/model.py:102 constructs it.  DGL 0.9 is not
+    vendored with the reference, so this restates its published layer (Velickovic et al. 2018 as implemented in
+    python/dgl/nn/pytorch/conv/gatconv.py): shared ``fc`` for source and destination, ``attn_l`` / ``attn_r``,
+    LeakyReLU(0.2), softmax over each destination's in-edges, dropout on features and on attention, bias, no residual
+    or activation; xavier-normal init with the ReLU gain, zero bias.  PARITY UNPINNED for this layer's internals."""
+
+    def __init__(self, in_feats, out_feats, num_heads, feat_drop=0.0, attn_drop=0.0, negative_slope=0.2):
+        super().__init__()
+        self.H, self.Fo = num_heads, out_feats
+        self.fc = nn.Linear(in_feats, out_feats * num_heads, bias=False)
+        self.attn_l = nn.Parameter(torch.empty(1, num_heads, out_feats))
+        self.attn_r = nn.Parameter(torch.empty(1, num_heads, out_feats))
+        self.feat_drop, self.attn_drop = nn.Dropout(feat_drop), nn.Dropout(attn_drop)
+        self.negative_slope = negative_slope
+        self.bias = nn.Parameter(torch.empty(num_heads * out_feats))
+        gain = nn.init.calculate_gain("relu")
+        nn.init.xavier_normal_(self.fc.weight, gain=gain)
+        nn.init.xavier_normal_(self.attn_l, gain=gain)
+        nn.init.xavier_normal_(self.attn_r, gain=gain)
+        nn.init.constant_(self.bias, 0)
+
+    def forward(self, g: EdgeList, feat):
+        H, Fo = self.H, self.Fo
+        h_src, h_dst = (self.feat_drop(feat[0]), self.feat_drop(feat[1])) if isinstance(feat, tuple) \
+            else (self.feat_drop(feat),) * 2
+        ft_src = self.fc(h_src).view(-1, H, Fo)
+        ft_dst = self.fc(h_dst).view(-1, H, Fo)
+        el = (ft_src * self.attn_l).sum(-1)
+        er = (ft_dst * self.attn_r).sum(-1)
+        e = F.leaky_relu(el[g.u] + er[g.v], self.negative_slope)                        # u_add_v, leaky_relu
+        idx = g.v.unsqueeze(1).expand(-1, H)
+        m = torch.full((g.n_v, H), float("-inf")).scatter_reduce(0, idx, e.detach(), "amax")
+        ex = torch.exp(e - m[g.v])
+        den = torch.zeros(g.n_v, H).index_add(0, g.v, ex)
+        a = self.attn_drop(ex / den[g.v])                                               # edge_softmax
+        rst = torch.zeros(g.n_v, H, Fo).index_add(0, g.v, a.unsqueeze(-1) * ft_src[g.u])   # u_mul_e, sum
+        return rst + self.bias.view(1, H, Fo)
+
+
+class GATRef(nn.Module):
+    """``GAT`` (module/model.py:96-132)."""
+
+    def __init__(self, layer_size, use_pp, heads, dropout, norm, train_size, n_linear):
+        super().__init__()
+        self.n_layers, self.n_linear, self.use_pp = len(layer_size) - 1, n_linear, use_pp
+        self.layers = nn.ModuleList()
+        self.use_norm = norm is not None
+        if self.use_norm:
+            self.norm = nn.ModuleList()
+        self.dropout = nn.Dropout(p=dropout)
+        for i in range(self.n_layers):
+            if i < self.n_layers - n_linear:
+                self.layers.append(GATConvRef(layer_size[i], layer_size[i + 1], heads, dropout, dropout))
+            else:
+                self.layers.append(nn.Linear(layer_size[i], layer_size[i + 1]))
+            if i < self.n_layers - 1 and self.use_norm:
+                self.norm.append(nn.LayerNorm(layer_size[i + 1], elementwise_affine=True) if norm == "layer"
+                                 else SyncBNRef(layer_size[i + 1], train_size))
+        self.oracle: Optional[OracleRank] = None
+
+    def forward(self, g, feat):
+        h, rk = feat, self.oracle
+        for i in range(self.n_layers):
+            if i < self.n_layers - self.n_linear:
+                if self.training:
+                    if i > 0 or not self.use_pp:
+                        h1 = _Exchange.apply(h, rk, i) if rk.size > 1 else h          # model.py:117-118
+                    else:
+                        h1, h = h, h[0:g.num_nodes("_V")]                              # :120-121
+                    h = self.layers[i](g, (h1, h))
+                else:
+                    h = self.layers[i](g, h)
+                h = h.mean(1)
+            else:
+                h = self.layers[i](self.dropout(h))
+            if rk is not None and rk.trace is not None:
+                rk.trace[f"layer{i}"] = h.detach().clone()
+            if i < self.n_layers - 1:
+                if self.use_norm:
+                    h = self.norm[i](h)
+                h = F.relu(h)
+        return h
+
+
+def build_model(kind, layer_size, use_pp, dropout, norm, train_size, n_linear, heads=1):
+    if kind == "gat":
+        return GATRef(layer_size, True, heads, dropout, norm, train_size, n_linear)     # train.py:222: use_pp=True
     if kind not in ("graphsage", "gcn"):
         raise NotImplementedError(kind)
     return GNNRef(kind, layer_size, use_pp, dropout, norm, train_size, n_linear)

@@ -39,7 +39,8 @@ def run_product(parts, args, device, n_epochs, selected_per_epoch=None, capture=
         if capture:
             for i, layer in enumerate(st.model.layers):
                 hooks.append(layer.register_forward_hook(
-                    lambda m, inp, out, i=i: outs.__setitem__(f"layer{i}", out.detach().clone())))
+                    lambda m, inp, out, i=i: outs.__setitem__(
+                        f"layer{i}", (out.mean(1) if out.dim() == 3 else out).detach().clone())))
         losses, sel_log, hops_log = [], [], []
         for e in range(n_epochs):
             inj = None
@@ -72,7 +73,7 @@ def run_oracle(parts, args, n_epochs, selected_per_epoch):
         rk = O.OracleRank(O.RankInput.from_partition(p), comm, model=args.model, n_layers=args.n_layers,
                           n_hidden=args.n_hidden, sampling_rate=args.sampling_rate, use_pp=args.use_pp,
                           dropout=args.dropout, norm=args.norm, lr=args.lr, weight_decay=args.weight_decay,
-                          seed=args.seed, n_linear=args.n_linear, 
+                          seed=args.seed, n_linear=args.n_linear, heads=getattr(args, "heads", 1),
                           multilabel=(args.dataset == "yelp" or getattr(args, "multilabel", False)))
         losses = []
         for e in range(n_epochs):
@@ -89,7 +90,7 @@ def run_oracle(parts, args, n_epochs, selected_per_epoch):
 def run_parity_case(shape="tiny", n_parts=2, model="graphsage", sampling_rate=0.5, n_epochs=2, device="cuda:0",
                     backend="nccl", n_layers=3, n_hidden=16, partition_method="random", graph_seed=0,
                     sampler_seed=0, chunk_nnz=0, n_linear=0, inductive=False, multilabel=False, norm="layer",
-                    graph_override=None) -> dict:
+                    graph_override=None, heads=1) -> dict:
     """Product vs oracle on one seeded configuration.  Returns the worst relative error over layer outputs, logits,
     reduced gradients and updated weights, plus the exactness checks on index sets."""
     from bns_gcn_b200.data import make_graph, partition_graph
@@ -99,7 +100,7 @@ def run_parity_case(shape="tiny", n_parts=2, model="graphsage", sampling_rate=0.
     parts = partition_graph(fg, n_parts, partition_method, seed=graph_seed, inductive=inductive)
     args = make_args(dataset=shape, model=model, sampling_rate=sampling_rate, backend=backend, n_layers=n_layers,
                      n_hidden=n_hidden, n_partitions=n_parts, sampler_seed=sampler_seed, chunk_nnz=chunk_nnz,
-                     n_linear=n_linear, inductive=inductive, multilabel=multilabel, norm=norm)
+                     n_linear=n_linear, inductive=inductive, multilabel=multilabel, norm=norm, heads=heads)
     prod = run_product(parts, args, device, n_epochs)
     selected = [[prod[r]["selected"][e] for r in range(n_parts)] for e in range(n_epochs)]
     orc = run_oracle(parts, args, n_epochs, selected if n_parts > 1 else None)

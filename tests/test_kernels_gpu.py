@@ -326,3 +326,48 @@ def test_fused_layernorm_relu_dropout(built, F, p):
         y4 = ops.LnReluDropout.apply(x.detach(), gamma.detach(), beta.detach(), 1e-5, p, 77)
         assert torch.equal(y3, y4) and not torch.equal(y3, y.detach())
     ops.RNG.update(seed=0, offset=0, offset_dev=None)
+
+
+@pytest.mark.parametrize("F", [64, 256, 44])
+def test_weighted_spmm_perm_and_sddmm(built, F):
+    """GAT primitives: per-entry weights in the SpMM, the transpose's entry permutation, and the SDDMM dot."""
+    from bns_gcn_b200 import ops
+    dev = torch.device("cuda:0")
+    gen = torch.Generator().manual_seed(F)
+    n_rows, n_direct, n_halo, n_slab = 300, 300, 200, 70
+    indptr, idx = _rand_csr(n_rows, n_direct + n_halo, 14, seed=F + 3, heavy=1)
+    nnz = idx.numel()
+    rows = torch.repeat_interleave(torch.arange(n_rows), indptr[1:] - indptr[:-1])
+    w = torch.rand(nnz, generator=gen)
+    slot = torch.full((n_halo,), -1, dtype=torch.int32)
+    chosen = torch.randperm(n_halo, generator=gen)[:n_slab]
+    slot[chosen] = torch.randperm(n_slab, generator=gen).int()
+    col_map = torch.where(slot >= 0, slot + n_direct, slot)
+    x = torch.randn(n_direct + n_slab, F, generator=gen)
+    g = ops.DeviceGraph.from_csr(indptr.to(dev), idx.int().to(dev), n_direct + n_halo, 64)
+    y = ops.spmm(g, x.to(dev), edge_weight=w.to(dev), col_map=col_map.to(dev), n_direct=n_direct).cpu()
+    xrow = idx.clone()
+    m = idx >= n_direct
+    xrow[m] = col_map[idx[m] - n_direct].long()
+    keep = xrow >= 0
+    ref = torch.zeros(n_rows, F).index_add_(0, rows[keep], x[xrow[keep]] * w[keep].unsqueeze(1))
+    assert _relerr(y, ref) < RTOL
+    # transpose permutation: entry k of g^T is entry perm[k] of g
+    gt = g.transpose()
+    perm = gt.perm().cpu().long()
+    tp, tx = (t.cpu() for t in gt.csr())
+    assert torch.equal(tx.long(), rows[perm])
+    tcols = torch.repeat_interleave(torch.arange(gt.n_rows), tp[1:] - tp[:-1])
+    assert torch.equal(tcols, idx[perm])
+    # weighted transpose SpMM == autograd of the forward
+    dy = torch.randn(n_rows, F, generator=gen)
+    dx = ops.spmm(gt, dy.to(dev), edge_weight=w[perm].to(dev)).cpu()
+    ref_dx = torch.zeros(n_direct + n_halo, F).index_add_(0, idx, dy[rows] * w.unsqueeze(1))
+    assert _relerr(dx, ref_dx) < RTOL
+    # SDDMM dot with the column map: d w_k = <dy[row_k], x[xrow_k]>, 0 for skipped entries
+    if F % 4 == 0:
+        dw = ops.sddmm_dot(g, dy.to(dev), x.to(dev), col_map=col_map.to(dev), n_direct=n_direct).cpu()
+        ref_dw = torch.zeros(nnz)
+        ref_dw[keep] = (dy[rows[keep]] * x[xrow[keep]]).sum(1)
+        assert _relerr(dw, ref_dw) < RTOL
+        assert torch.all(dw[~keep] == 0)

@@ -188,3 +188,19 @@ def test_training_parity_variants(built, kw):
         assert res["index_sets_equal"]
         return
     _run(n_epochs=2, **kw)
+
+
+@pytest.mark.parametrize("kw", [
+    dict(n_parts=1, sampling_rate=1.0),
+    dict(n_parts=2, sampling_rate=1.0, heads=2),
+    dict(n_parts=3, sampling_rate=0.5),
+    dict(n_parts=3, sampling_rate=0.3, heads=2, backend="p2p", n_layers=3),
+    dict(n_parts=2, sampling_rate=0.5, shape="tiny"),            # single-label CE, 5 classes (per-head width padded to 8)
+], ids=["p1", "p2-heads2", "p3", "p3-heads2-p2p", "tiny-ce"])
+def test_gat_training_parity(built, kw):
+    """GAT (module/model.py:96-132 + dgl.nn.GATConv) against the oracle's explicit-edge-list restatement:
+    BASELINE configs[3]-style multi-label BCE by default."""
+    kw = dict(kw)
+    shape = kw.pop("shape", "tiny-ml")
+    kw.setdefault("n_layers", 2)
+    _run(shape=shape, model="gat", n_epochs=2, multilabel=(shape == "tiny-ml"), **kw)
