@@ -35,6 +35,12 @@ WORKLOAD = dict(shape="reddit", model="graphsage", n_layers=3, n_hidden=256, sam
                 lr=0.01, norm="layer", partition="random")
 
 
+def METRIC():
+    if (WORKLOAD["shape"], WORKLOAD["model"], WORKLOAD["n_layers"]) == ("reddit", "graphsage", 3):
+        return "epochs/sec (3-layer GraphSAGE, Reddit-shape graph)"
+    return f"epochs/sec ({WORKLOAD['n_layers']}-layer {WORKLOAD['model']}, {WORKLOAD['shape']}-shape graph)"
+
+
 def load_peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -94,7 +100,7 @@ def make_args(n_parts: int, backend: str, extra: dict):
                             dropout=WORKLOAD["dropout"], norm=WORKLOAD["norm"], lr=WORKLOAD["lr"], weight_decay=0.0,
                             seed=0, n_linear=0, backend=backend, sampler_seed=0, n_epochs=0, log_every=10 ** 9,
                             heads=1, n_partitions=n_parts, inductive=False, partition_method=WORKLOAD["partition"],
-                            eval=False, chunk_nnz=0)
+                            eval=False, chunk_nnz=0, multilabel=(WORKLOAD["shape"] == "yelp"))
     for k, v in extra.items():
         setattr(ns, k, v)
     return ns
@@ -287,13 +293,15 @@ def run_ours(a):
     n_spmm = max(len(prof), 1)
     ach = spmm_alg / (spmm_ms * 1e-3) / 1e9 if spmm_ms > 0 else 0.0
     out = {
-        "metric": "epochs/sec (3-layer GraphSAGE, Reddit-shape graph)", "value": K / (dev_ms * 1e-3),
+        "metric": METRIC(), "value": K / (dev_ms * 1e-3),
         "unit": "epochs/s", "n_gpus": world, "steps": K, "warmup": W, "ms_per_step": dev_ms / K,
         "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": f"BASELINE configs[1]: Reddit-shape synthetic power-law graph, {gstats['n_nodes']} nodes, "
-                               f"{gstats['n_edges']} edges, {gstats['n_feat']} feat, 41 classes; GraphSAGE 3-layer hidden 256 "
-                               f"--use-pp, sampling-rate 0.1, dropout 0.5, {world} random partition(s); "
-                               "inputs (1.1 GB features / rank-count) exceed L2, no flush needed",
+        "config": {"workload": f"{'BASELINE configs[1]: ' if (WORKLOAD['shape'], WORKLOAD['model']) == ('reddit', 'graphsage') else ''}"
+                               f"{WORKLOAD['shape']}-shape synthetic power-law graph, {gstats['n_nodes']} nodes, "
+                               f"{gstats['n_edges']} edges, {gstats['n_feat']} feat; {WORKLOAD['model']} "
+                               f"{WORKLOAD['n_layers']}-layer hidden {WORKLOAD['n_hidden']} --use-pp, sampling-rate "
+                               f"{WORKLOAD['sampling_rate']}, dropout {WORKLOAD['dropout']}, {world} random partition(s); "
+                               "per-rank inputs exceed L2, no flush needed",
                    "parallelism": f"partition-parallel x{world}", "exchange": a.backend, "execution": mode,
                    "n_in_rank0": part.graph.n_in, "n_halo_rank0": part.graph.n_halo,
                    "local_edges_rank0": part.graph.num_edges()},
@@ -338,7 +346,7 @@ def cpu_epochs_per_sec(shape: str, n_parts: int, steps: int, warmup: int, budget
         rk = O.OracleRank(O.RankInput.from_partition(parts[r]), comm, model=WORKLOAD["model"],
                           n_layers=WORKLOAD["n_layers"], n_hidden=WORKLOAD["n_hidden"],
                           sampling_rate=WORKLOAD["sampling_rate"], use_pp=True, dropout=WORKLOAD["dropout"],
-                          norm=WORKLOAD["norm"], lr=WORKLOAD["lr"], seed=0)
+                          norm=WORKLOAD["norm"], lr=WORKLOAD["lr"], seed=0, multilabel=(WORKLOAD["shape"] == "yelp"))
         rng = np.random.RandomState(1234 + r)
         t_begin = time.perf_counter()
         for e in range(warmup + steps):
@@ -371,7 +379,7 @@ def run_reference(a):
         return
     K, W = a.steps, a.warmup
     res = cpu_epochs_per_sec(a.shape, a.gpus, steps=K, warmup=min(W, 1))
-    out = {"impl": "reference", "metric": "epochs/sec (3-layer GraphSAGE, Reddit-shape graph)", "value": res["value"],
+    out = {"impl": "reference", "metric": METRIC(), "value": res["value"],
            "unit": "epochs/s", "n_gpus": a.gpus, "steps": K, "warmup": W, "ms_per_step": 1e3 * res["seconds_per_epoch"],
            "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
            "config": {"workload": f"BASELINE configs[1] on host cores: Reddit-shape synthetic graph, GraphSAGE 3-layer "
@@ -383,6 +391,7 @@ def run_reference(a):
 
 
 def main():
+    global WORKLOAD
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=10)
@@ -395,7 +404,17 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--strict", action="store_true", help="fail instead of falling back to eager when capture fails")
     ap.add_argument("--profile", default="", help="write a torch.profiler kernel table of 3 epochs (rank 0) to this file")
+    # non-default workloads (the other BASELINE.json configs); the driver's contract run uses the defaults above
+    ap.add_argument("--model", default=None, choices=["graphsage", "gcn", "gat"])
+    ap.add_argument("--n-layers", type=int, default=None)
+    ap.add_argument("--n-hidden", type=int, default=None)
+    ap.add_argument("--rate", type=float, default=None)
+    ap.add_argument("--dropout", type=float, default=None)
     a = ap.parse_args()
+    for k, v in (("model", a.model), ("n_layers", a.n_layers), ("n_hidden", a.n_hidden), ("sampling_rate", a.rate),
+                 ("dropout", a.dropout), ("shape", a.shape)):
+        if v is not None:
+            WORKLOAD[k] = v
     if a.impl == "reference":
         run_reference(a)
     else:
