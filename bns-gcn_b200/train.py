@@ -393,8 +393,6 @@ class GraphedEpoch:
     def __init__(self, st: TrainState, warmup: int = 3):
         self.st = st
         dev = st.feat.device
-        if st.args.model not in ('graphsage', 'gcn'):
-            raise NotImplementedError
         cur = torch.cuda.current_stream(dev)
         if cur == torch.cuda.default_stream(dev):
             raise RuntimeError(
