@@ -64,8 +64,59 @@ class _Linear3x(torch.autograd.Function):
         return dx, dw, db
 
 
+# ---- bf16x3: x = b0 + b1 + b2 (24 mantissa bits), six bf16 tensor-core GEMMs, f32 accumulation ----------------------
+_PAIRS = ((2, 0), (0, 2), (1, 1), (1, 0), (0, 1), (0, 0))          # small terms first
+
+
+def _split3(t: torch.Tensor):
+    from .._lib import check, lib
+    t = t.contiguous()
+    n = t.numel()
+    if n % 4:
+        raise RuntimeError("bf16x3 split needs a multiple of 4 elements")
+    outs = [torch.empty(t.shape, dtype=torch.bfloat16, device=t.device) for _ in range(3)]
+    with torch.cuda.device(t.device):
+        check(lib.bns_split_bf16x3_f32(t.data_ptr(), n, outs[0].data_ptr(), outs[1].data_ptr(), outs[2].data_ptr(),
+                                       torch.cuda.current_stream().cuda_stream), "bns_split_bf16x3_f32")
+    return outs
+
+
+def _mm6(a3, b3, trans_a=False, trans_b=False):
+    """sum over i + j <= 2 of  op(a_i) @ op(b_j)  in f32."""
+    acc = None
+    for i, j in _PAIRS:
+        a = a3[i].t() if trans_a else a3[i]
+        b = b3[j].t() if trans_b else b3[j]
+        acc = torch.mm(a, b, out_dtype=torch.float32) if acc is None else torch.addmm(acc, a, b, out_dtype=torch.float32)
+    return acc
+
+
+class _LinearBf16x3(torch.autograd.Function):
+
+    @staticmethod
+    def forward(ctx, x, weight, bias):
+        x3, w3 = _split3(x), _split3(weight)
+        ctx.x3, ctx.w3, ctx.has_bias = x3, w3, bias is not None
+        y = _mm6(x3, w3, trans_b=True)                      # [M,K] @ [N,K]^T
+        if bias is not None:
+            y += bias
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        d3 = _split3(dy)
+        dx = _mm6(d3, ctx.w3) if ctx.needs_input_grad[0] else None                # [M,N] @ [N,K]
+        dw = _mm6(d3, ctx.x3, trans_a=True) if ctx.needs_input_grad[1] else None  # [M,N]^T @ [M,K]
+        db = dy.sum(0) if ctx.has_bias and ctx.needs_input_grad[2] else None
+        ctx.x3 = ctx.w3 = None
+        return dx, dw, db
+
+
 def linear(x: torch.Tensor, weight: torch.Tensor, bias=None) -> torch.Tensor:
     """Drop-in for ``F.linear`` on 2-D f32 CUDA inputs."""
-    if MODE == "3xtf32" and x.is_cuda and x.dtype == torch.float32 and x.dim() == 2:
+    ok = x.is_cuda and x.dtype == torch.float32 and x.dim() == 2
+    if MODE == "bf16x3" and ok and x.numel() % 4 == 0 and weight.numel() % 4 == 0 and weight.shape[0] % 4 == 0:
+        return _LinearBf16x3.apply(x, weight, bias)
+    if MODE == "3xtf32" and ok:
         return _Linear3x.apply(x, weight, bias)
     return F.linear(x, weight, bias)

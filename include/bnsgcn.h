@@ -108,6 +108,13 @@ int bns_spmm_sum_f32(const bns_graph_t *g,
                      int accumulate, void *ws, size_t ws_bytes, void *stream);
 
 /* ------------------------------------------------------------------------------------------------
+ * K8 helper (dense layers): split n contiguous f32 values into three bf16 arrays with x = b0 + b1 + b2 exact to
+ * 24 mantissa bits (round-to-nearest-even at each step).  Six bf16 tensor-core GEMMs b_i * w_j (i + j <= 2) with f32
+ * accumulation then reproduce the f32 product to ~2^-23 (module/dense.py, mode "bf16x3").  n % 4 == 0.
+ * ----------------------------------------------------------------------------------------------*/
+int bns_split_bf16x3_f32(const float *x, int64_t n, void *out0 /*bf16 [n]*/, void *out1, void *out2, void *stream);
+
+/* ------------------------------------------------------------------------------------------------
  * K10 (GAT, module/model.py:96-132 via dgl.nn.GATConv): the attention gradient.  For every entry k of row r:
  *     out[k * ldo] = < A[arow(r), :F], B[xrow(c_k), :F] >      (0 when the row or the entry is skipped)
  * arow / xrow as in bns_spmm_sum_f32 (row_map / col_map / n_direct).  F % 4 == 0, F <= 1024, 16-byte aligned rows.

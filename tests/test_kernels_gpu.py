@@ -371,3 +371,23 @@ def test_weighted_spmm_perm_and_sddmm(built, F):
         ref_dw[keep] = (dy[rows[keep]] * x[xrow[keep]]).sum(1)
         assert _relerr(dw, ref_dw) < RTOL
         assert torch.all(dw[~keep] == 0)
+
+
+def test_dense_bf16x3_is_fp32_accurate(built):
+    """Three-way bf16 split + six tensor-core GEMMs with f32 accumulation: f32-level accuracy vs an f64 reference."""
+    from bns_gcn_b200.module import dense
+    dev = torch.device("cuda:0")
+    g = torch.Generator().manual_seed(1)
+    x = torch.randn(4096, 1204, generator=g).to(dev).requires_grad_(True)
+    w = (torch.rand(256, 1204, generator=g) - 0.5).to(dev).requires_grad_(True)
+    b = torch.randn(256, generator=g).to(dev).requires_grad_(True)
+    x3 = dense._split3(x.detach())
+    assert torch.equal((x3[0].float() + x3[1].float()) + x3[2].float(), x.detach()) or \
+        _relerr(((x3[0].float() + x3[1].float()) + x3[2].float()).cpu(), x.detach().cpu()) < 1e-7
+    y = dense._LinearBf16x3.apply(x, w, b)
+    dy = torch.randn(4096, 256, generator=g).to(dev)
+    y.backward(dy)
+    xd, wd, bd = x.detach().double(), w.detach().double(), b.detach().double()
+    assert _relerr(y.detach().double().cpu(), (xd @ wd.t() + bd).cpu()) < 2e-6
+    assert _relerr(x.grad.double().cpu(), (dy.double() @ wd).cpu()) < 2e-6
+    assert _relerr(w.grad.double().cpu(), (dy.double().t() @ xd).cpu()) < 2e-6
