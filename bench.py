@@ -336,7 +336,9 @@ def cpu_epochs_per_sec(shape: str, n_parts: int, steps: int, warmup: int, budget
     from oracle import bns_oracle as O
     import numpy as np
     cores = os.cpu_count() or 1
-    torch.set_num_threads(max(1, cores // n_parts))
+    per_rank = max(1, cores // n_parts)
+    torch.set_num_threads(per_rank)          # torchrun exports OMP_NUM_THREADS=1: set both pools explicitly
+    O.set_threads(per_rank)
     fg = make_graph(shape, seed=0, device=torch.device("cuda") if torch.cuda.is_available() else None)
     parts = partition_graph(fg, n_parts, WORKLOAD["partition"], seed=0)
     del fg
@@ -369,7 +371,8 @@ def cpu_epochs_per_sec(shape: str, n_parts: int, steps: int, warmup: int, budget
     mean = sum(per_epoch) / len(per_epoch)
     return {"value": 1.0 / mean, "unit": "epochs/s", "cores": cores, "kind": "port",
             "sample": f"{done} full epoch(s) of the same workload ({n_parts} partition(s) as in-process ranks) after "
-                      f"{warmup} warm-up, oracle/bns_oracle.py + oracle/spmm_ref.c (OpenMP), {cores} host threads",
+                      f"{warmup} warm-up, oracle/bns_oracle.py + oracle/spmm_ref.c (OpenMP), {cores} host threads "
+                      f"({per_rank} per rank)",
             "seconds_per_epoch": mean}
 
 

@@ -48,8 +48,16 @@ def _lib():
         lib.bns_ref_coo_to_csr.restype = ctypes.c_int
         lib.bns_ref_spmm_sum_f32.argtypes = [i64, p, p, p, i64, i64, p, i64]
         lib.bns_ref_spmm_sum_f32.restype = ctypes.c_int
+        lib.bns_ref_set_threads.argtypes = [ctypes.c_int]
+        lib.bns_ref_set_threads.restype = None
         _LIB = lib
     return _LIB
+
+
+def set_threads(n: int) -> None:
+    """OpenMP threads per SpMM / COO->CSR call (0 = OpenMP default).  bench.py sets it explicitly because torchrun
+    exports OMP_NUM_THREADS=1."""
+    _lib().bns_ref_set_threads(int(n))
 
 
 # --------------------------------------------------------------------------------------------

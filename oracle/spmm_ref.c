@@ -21,10 +21,17 @@
  * counting sort: edges are cut into T contiguous blocks, each block histograms its rows, a scan turns the
  * histograms into per-(block,row) write cursors, then every block scatters its own edges in order. */
 #include <omp.h>
+
+/* Threads per call (0 = OpenMP default).  Set explicitly by the caller: torchrun exports OMP_NUM_THREADS=1, which
+ * would otherwise turn the CPU baseline single-threaded behind our back. */
+static int g_threads = 0;
+void bns_ref_set_threads(int n) { g_threads = n > 0 ? n : 0; }
+static int nthreads(void) { return g_threads > 0 ? g_threads : omp_get_max_threads(); }
+
 int bns_ref_coo_to_csr(int64_t n_dst, int64_t nnz, const int64_t *dst, const int64_t *src,
                        int64_t *indptr, int64_t *cols)
 {
-    int T = omp_get_max_threads();
+    int T = nthreads();
     if (T > 32) T = 32;
     if (nnz < (1 << 16)) T = 1;
     const int64_t rows = n_dst > 0 ? n_dst : 1;
@@ -66,7 +73,7 @@ int bns_ref_coo_to_csr(int64_t n_dst, int64_t nnz, const int64_t *dst, const int
 int bns_ref_spmm_sum_f32(int64_t n_dst, const int64_t *indptr, const int64_t *cols,
                          const float *X, int64_t ldx, int64_t F, float *Y, int64_t ldy)
 {
-#pragma omp parallel for schedule(dynamic, 64)
+#pragma omp parallel for schedule(dynamic, 64) num_threads(nthreads())
     for (int64_t v = 0; v < n_dst; ++v) {
         float *y = Y + v * ldy;
         for (int64_t f = 0; f < F; ++f) y[f] = 0.0f;
