@@ -345,6 +345,7 @@ def cpu_epochs_per_sec(shape: str, n_parts: int, steps: int, warmup: int, budget
     times = [[] for _ in range(n_parts)]
 
     def fn(comm, r):
+        torch.set_num_threads(per_rank)      # OpenMP's thread count is per calling thread: set it in every rank thread
         rk = O.OracleRank(O.RankInput.from_partition(parts[r]), comm, model=WORKLOAD["model"],
                           n_layers=WORKLOAD["n_layers"], n_hidden=WORKLOAD["n_hidden"],
                           sampling_rate=WORKLOAD["sampling_rate"], use_pp=True, dropout=WORKLOAD["dropout"],
