@@ -291,6 +291,15 @@ def run_ours(a):
         return
     peak, peak_src = load_peaks()
     n_spmm = max(len(prof), 1)
+    # boundary exchange (per rank, per epoch): rows sent forward + gradient rows returned, on every communicating layer
+    n_comm_layers = max(WORKLOAD["n_layers"] - 1, 0)
+    ex_bytes = 4 * WORKLOAD["n_hidden"] * (sum(st.send_size) + sum(st.recv_size)) * n_comm_layers if world > 1 else 0
+    traffic, traffic_src = None, None
+    tp = os.path.join(ROOT, "profiles", "spmm_traffic.json")
+    if os.path.exists(tp) and (WORKLOAD["shape"], world) == ("reddit", 1):
+        with open(tp) as f:
+            tj = json.load(f)
+        traffic, traffic_src = tj.get("dram_bytes_per_launch"), tj.get("source")
     ach = spmm_alg / (spmm_ms * 1e-3) / 1e9 if spmm_ms > 0 else 0.0
     out = {
         "metric": METRIC(), "value": K / (dev_ms * 1e-3),
@@ -310,10 +319,15 @@ def run_ours(a):
         "e2e": {"value": K / e2e_s, "unit": "epochs/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": 4,
                 "note": "features+labels+mask copied from pinned host memory every epoch (prefetched one step ahead on "
                         "a copy stream), loss read back every epoch"},
+        "exchange": {"bytes_per_epoch_per_rank": int(ex_bytes), "comm_s_per_epoch": comm_last,
+                     "GBs_over_comm_time": (ex_bytes / comm_last / 1e9) if comm_last > 0 else None,
+                     "note": "comm_s = CUDA-event time of the exchanges on the comm stream (pack + NVLink transfer + "
+                             "waiting for the peers' data), measured in the eager pass; it overlaps the inner-edge SpMM"},
         "gpu_launches": int(n1 - n0),
         "clocks": clk,
         "roofline": {"bound": "hbm", "kernel": "spmm_kernel (bns_spmm_sum_f32)", "achieved": ach, "peak": peak,
-                     "unit": "GB/s", "frac": ach / peak, "traffic": None, "peak_source": peak_src,
+                     "unit": "GB/s", "frac": ach / peak, "traffic": traffic, "traffic_source": traffic_src,
+                     "peak_source": peak_src,
                      "launches_timed": len(prof), "avg_launch_ms": spmm_ms / n_spmm,
                      "share_of_step": spmm_ms / eager_ms if eager_ms else None,
                      "gather_GBs": spmm_gather / (spmm_ms * 1e-3) / 1e9 if spmm_ms > 0 else 0.0,

@@ -31,9 +31,6 @@ def _ref_spmm(indptr, idx, x, row_scale=None, col_scale=None, col_map=None, n_di
     n_rows = indptr.numel() - 1
     rows = torch.repeat_interleave(torch.arange(n_rows), indptr[1:] - indptr[:-1])
     cols = idx.clone()
-    w_src = x
-    if col_scale is not None:
-        pass
     xrow = cols.clone()
     if col_map is not None:
         m = cols >= n_direct
@@ -46,9 +43,6 @@ def _ref_spmm(indptr, idx, x, row_scale=None, col_scale=None, col_map=None, n_di
     n_out = n_out if n_out is not None else n_rows
     # scale sources per EDGE (col_scale is indexed by the original column id)
     if col_scale is not None:
-        # build an expanded source matrix: one row per kept edge is too big in general; instead use
-        # the identity  sum_k cs[c_k] x[xrow_k] = sum over distinct (c, xrow) pairs.  For the test
-        # sizes a direct index_add_ is fine.
         contrib = x[xrow[keep]] * col_scale[cols[keep]].unsqueeze(1)
         out = torch.zeros(n_out, x.shape[1]).index_add_(0, orow[keep], contrib)
     else:
@@ -63,8 +57,6 @@ def _ref_spmm(indptr, idx, x, row_scale=None, col_scale=None, col_map=None, n_di
             rs[row_map[ok].long()] = row_scale[ok]
         out = out * rs.unsqueeze(1)
     if y0 is not None:
-        touched = torch.zeros(n_out, dtype=torch.bool)
-        touched[orow[keep] if row_map is not None else torch.arange(n_out)] = True
         out = out + y0
     return out
 
