@@ -47,6 +47,7 @@ SIGNATURES = {
     "bns_ln_relu_dropout_bwd_f32": (c_int, [c_void_p, c_int64, c_void_p, c_int64, c_int64, c_int64, c_void_p, c_void_p,
                                             c_void_p, c_void_p, c_float, c_float, c_uint64, c_uint64, c_void_p, c_void_p,
                                             c_int64, c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),
+    "bns_split_tf32_f32": (c_int, [c_void_p, c_int64, c_void_p, c_void_p, c_void_p]),
     "bns_split_bf16x3_f32": (c_int, [c_void_p, c_int64, c_void_p, c_void_p, c_void_p, c_void_p]),
     "bns_fill_i32": (c_int, [c_void_p, c_int64, c_int32, c_void_p]),
     "bns_halo_slot_update": (c_int, [c_void_p, c_void_p, c_int64, c_int64, c_int32, c_void_p, c_void_p]),

@@ -1317,6 +1317,36 @@ __global__ void split_bf16x3_kernel(const float4 *__restrict__ x, int64_t n4, us
 
 }  // namespace
 
+namespace {
+// hi = x with the 13 low mantissa bits cleared after round-to-nearest (exactly representable in TF32, so neither a
+// truncating nor a rounding tensor-core path changes it), lo = x - hi (exact in f32)
+__global__ void split_tf32_kernel(const float4 *__restrict__ x, int64_t n4, float4 *__restrict__ hi, float4 *__restrict__ lo) {
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n4; i += (int64_t)gridDim.x * blockDim.x) {
+        const float4 v = x[i];
+        float4 h, l;
+        h.x = __uint_as_float((__float_as_uint(v.x) + 0x1000u) & 0xffffe000u); l.x = v.x - h.x;
+        h.y = __uint_as_float((__float_as_uint(v.y) + 0x1000u) & 0xffffe000u); l.y = v.y - h.y;
+        h.z = __uint_as_float((__float_as_uint(v.z) + 0x1000u) & 0xffffe000u); l.z = v.z - h.z;
+        h.w = __uint_as_float((__float_as_uint(v.w) + 0x1000u) & 0xffffe000u); l.w = v.w - h.w;
+        hi[i] = h;
+        lo[i] = l;
+    }
+}
+}  // namespace
+
+extern "C" int bns_split_tf32_f32(const float *x, int64_t n, float *hi, float *lo, void *stream) {
+    BNS_REQUIRE(n >= 0 && n % 4 == 0, "bns_split_tf32_f32: element count must be a multiple of 4");
+    if (n == 0) return BNS_OK;
+    BNS_REQUIRE(x && hi && lo, "bns_split_tf32_f32: NULL pointer");
+    const int64_t n4 = n / 4;
+    int64_t want = (n4 + 255) / 256, cap = (int64_t)sm_count() * 16;
+    split_tf32_kernel<<<(unsigned)(want < cap ? want : cap), 256, 0, as_stream(stream)>>>(
+        reinterpret_cast<const float4 *>(x), n4, reinterpret_cast<float4 *>(hi), reinterpret_cast<float4 *>(lo));
+    ++g_launches;
+    BNS_CUDA(cudaGetLastError());
+    return BNS_OK;
+}
+
 extern "C" int bns_split_bf16x3_f32(const float *x, int64_t n, void *out0, void *out1, void *out2, void *stream) {
     BNS_REQUIRE(n >= 0 && n % 4 == 0, "bns_split_bf16x3_f32: element count must be a multiple of 4");
     if (n == 0) return BNS_OK;

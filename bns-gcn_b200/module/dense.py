@@ -9,7 +9,9 @@ relative, i.e. f32-level accuracy.  The GEMMs themselves are library calls (cuBL
 plain GEMMs); a hand-written tcgen05 kernel with the LayerNorm / ReLU / dropout epilogue fused is the SURVEY §8(f)
 rank-2 follow-up.
 
-``MODE`` (env BNS_DENSE): "fp32" (default, the reference precision) | "3xtf32".  Measured on B200 (round 1, Reddit
+``MODE`` (env BNS_DENSE): "auto" (default: 3xtf32 where K >= 512, i.e. the layer-0 GEMMs, fp32 cuBLAS elsewhere) |
+"fp32" (the literal reference precision everywhere) | "3xtf32" | "bf16x3".  tools/bench_dense.py on B200, M=232,965
+K=1204 N=256: fp32 2.37 ms, one TF32 GEMM 0.25 ms (585 TFLOP/s), fused split pass 0.5 ms.  First attempt, kept for the record:  Measured on B200 (round 1, Reddit
 shape, N=1): 3xtf32 built from three cuBLAS TF32 GEMMs + the split passes is SLOWER than fp32 SIMT cuBLAS (44.2 vs
 37.8 ms/epoch), so it is off by default; the win needs the split fused into a hand-written tcgen05 kernel.
 """
@@ -18,20 +20,33 @@ import os
 import torch
 import torch.nn.functional as F
 
-MODE = os.environ.get("BNS_DENSE", "fp32")
+MODE = os.environ.get("BNS_DENSE", "auto")
+MIN_K_3X = 512       # "auto": 3xTF32 only where the GEMM is big enough to repay the split pass (layer 0: K = 2 * n_feat)
 
 
 def _split(t: torch.Tensor):
-    """hi = t rounded to TF32 (10 explicit mantissa bits, round-to-nearest on the 13 dropped bits), lo = t - hi."""
-    bits = t.contiguous().view(torch.int32)
+    """hi = t rounded to TF32 (10 explicit mantissa bits, round-to-nearest on the 13 dropped bits), lo = t - hi.
+    One fused pass (``bns_split_tf32_f32``) on CUDA; torch ops elsewhere (CPU checks)."""
+    t = t.contiguous()
+    if t.is_cuda and t.numel() % 4 == 0:
+        from .._lib import check, lib
+        hi, lo = torch.empty_like(t), torch.empty_like(t)
+        with torch.cuda.device(t.device):
+            check(lib.bns_split_tf32_f32(t.data_ptr(), t.numel(), hi.data_ptr(), lo.data_ptr(),
+                                         torch.cuda.current_stream().cuda_stream), "bns_split_tf32_f32")
+        return hi, lo
+    bits = t.view(torch.int32)
     hi = ((bits + 0x1000) & -0x2000).view(torch.float32)
     return hi, t - hi
 
 
-def _mm3(a: torch.Tensor, b: torch.Tensor) -> torch.Tensor:
-    """a @ b with 3xTF32 error compensation (a: [m, k], b: [k, n], both f32)."""
-    ah, al = _split(a)
-    bh, bl = _split(b)
+def _mm3(a2, b2, trans_a=False, trans_b=False) -> torch.Tensor:
+    """op(a) @ op(b) with 3xTF32 error compensation; ``a2`` / ``b2`` are (hi, lo) pairs."""
+    (ah, al), (bh, bl) = a2, b2
+    if trans_a:
+        ah, al = ah.t(), al.t()
+    if trans_b:
+        bh, bl = bh.t(), bl.t()
     prev = torch.backends.cuda.matmul.allow_tf32
     torch.backends.cuda.matmul.allow_tf32 = True
     try:
@@ -47,20 +62,20 @@ class _Linear3x(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, x, weight, bias):
-        ctx.save_for_backward(x, weight)
-        ctx.has_bias = bias is not None
-        y = _mm3(x, weight.t())
+        x2, w2 = _split(x), _split(weight)
+        ctx.x2, ctx.w2, ctx.has_bias = x2, w2, bias is not None
+        y = _mm3(x2, w2, trans_b=True)
         if bias is not None:
             y += bias
         return y
 
     @staticmethod
     def backward(ctx, dy):
-        x, weight = ctx.saved_tensors
-        dy = dy.contiguous()
-        dx = _mm3(dy, weight) if ctx.needs_input_grad[0] else None
-        dw = _mm3(dy.t(), x) if ctx.needs_input_grad[1] else None
+        d2 = _split(dy)
+        dx = _mm3(d2, ctx.w2) if ctx.needs_input_grad[0] else None
+        dw = _mm3(d2, ctx.x2, trans_a=True) if ctx.needs_input_grad[1] else None
         db = dy.sum(0) if ctx.has_bias and ctx.needs_input_grad[2] else None
+        ctx.x2 = ctx.w2 = None
         return dx, dw, db
 
 
@@ -117,6 +132,6 @@ def linear(x: torch.Tensor, weight: torch.Tensor, bias=None) -> torch.Tensor:
     ok = x.is_cuda and x.dtype == torch.float32 and x.dim() == 2
     if MODE == "bf16x3" and ok and x.numel() % 4 == 0 and weight.numel() % 4 == 0 and weight.shape[0] % 4 == 0:
         return _LinearBf16x3.apply(x, weight, bias)
-    if MODE == "3xtf32" and ok:
+    if ok and (MODE == "3xtf32" or (MODE == "auto" and x.shape[1] >= MIN_K_3X)):
         return _Linear3x.apply(x, weight, bias)
     return F.linear(x, weight, bias)

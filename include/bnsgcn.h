@@ -113,6 +113,9 @@ int bns_spmm_sum_f32(const bns_graph_t *g,
  * accumulation then reproduce the f32 product to ~2^-23 (module/dense.py, mode "bf16x3").  n % 4 == 0.
  * ----------------------------------------------------------------------------------------------*/
 int bns_split_bf16x3_f32(const float *x, int64_t n, void *out0 /*bf16 [n]*/, void *out1, void *out2, void *stream);
+/* Same idea with TF32 (module/dense.py "3xtf32"): hi = x rounded to 10 mantissa bits, lo = x - hi (exact);
+ * hi*hi + hi*lo + lo*hi in three TF32 tensor-core GEMMs with f32 accumulation is f32-accurate to ~2^-21. */
+int bns_split_tf32_f32(const float *x, int64_t n, float *hi, float *lo, void *stream);
 
 /* ------------------------------------------------------------------------------------------------
  * K10 (GAT, module/model.py:96-132 via dgl.nn.GATConv): the attention gradient.  For every entry k of row r:
