@@ -20,6 +20,13 @@ import os
 import torch
 import torch.nn.functional as F
 
+import threading
+
+# torch.backends.cuda.matmul.allow_tf32 is process-global and read at enqueue time.  Ranks that are threads of one
+# process (tests, smoke) must not see each other's setting: every GEMM of this module is enqueued under this lock,
+# fp32 ones included (forward AND backward -- hence the custom fp32 Function below instead of F.linear).
+_GEMM_LOCK = threading.RLock()
+
 MODE = os.environ.get("BNS_DENSE", "auto")
 MIN_K_3X = 512       # "auto": 3xTF32 only where the GEMM is big enough to repay the split pass (layer 0: K = 2 * n_feat)
 
@@ -47,14 +54,15 @@ def _mm3(a2, b2, trans_a=False, trans_b=False) -> torch.Tensor:
         ah, al = ah.t(), al.t()
     if trans_b:
         bh, bl = bh.t(), bl.t()
-    prev = torch.backends.cuda.matmul.allow_tf32
-    torch.backends.cuda.matmul.allow_tf32 = True
-    try:
-        out = torch.mm(al, bh)          # small terms first, then the dominant one: better rounding
-        out.addmm_(ah, bl)
-        out.addmm_(ah, bh)
-    finally:
-        torch.backends.cuda.matmul.allow_tf32 = prev
+    with _GEMM_LOCK:
+        prev = torch.backends.cuda.matmul.allow_tf32
+        torch.backends.cuda.matmul.allow_tf32 = True
+        try:
+            out = torch.mm(al, bh)          # small terms first, then the dominant one: better rounding
+            out.addmm_(ah, bl)
+            out.addmm_(ah, bh)
+        finally:
+            torch.backends.cuda.matmul.allow_tf32 = prev
     return out
 
 
@@ -127,6 +135,26 @@ class _LinearBf16x3(torch.autograd.Function):
         return dx, dw, db
 
 
+class _LinearFp32(torch.autograd.Function):
+    """Plain f32 cuBLAS (the reference's precision), enqueued under ``_GEMM_LOCK`` in both directions."""
+
+    @staticmethod
+    def forward(ctx, x, weight, bias):
+        ctx.save_for_backward(x, weight)
+        ctx.has_bias = bias is not None
+        with _GEMM_LOCK:
+            return F.linear(x, weight, bias)
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, weight = ctx.saved_tensors
+        with _GEMM_LOCK:
+            dx = dy.mm(weight) if ctx.needs_input_grad[0] else None
+            dw = dy.t().mm(x) if ctx.needs_input_grad[1] else None
+        db = dy.sum(0) if ctx.has_bias and ctx.needs_input_grad[2] else None
+        return dx, dw, db
+
+
 def linear(x: torch.Tensor, weight: torch.Tensor, bias=None) -> torch.Tensor:
     """Drop-in for ``F.linear`` on 2-D f32 CUDA inputs."""
     ok = x.is_cuda and x.dtype == torch.float32 and x.dim() == 2
@@ -134,4 +162,6 @@ def linear(x: torch.Tensor, weight: torch.Tensor, bias=None) -> torch.Tensor:
         return _LinearBf16x3.apply(x, weight, bias)
     if ok and (MODE == "3xtf32" or (MODE == "auto" and x.shape[1] >= MIN_K_3X)):
         return _Linear3x.apply(x, weight, bias)
+    if ok:
+        return _LinearFp32.apply(x, weight, bias)
     return F.linear(x, weight, bias)
