@@ -1629,3 +1629,8 @@ extern "C" int bns_p2p_wait_flag(bns_p2p_t *p, int32_t flag_index, uint64_t flag
     BNS_CUDA(cudaGetLastError());
     return BNS_OK;
 }
+
+// =================================================================================================
+// K8: dense layers on tcgen05 (3xTF32 with the operand split fused into the pipeline)
+// =================================================================================================
+#include "dense_tc.cuh"

@@ -155,9 +155,71 @@ class _LinearFp32(torch.autograd.Function):
         return dx, dw, db
 
 
+# ---- "tc": hand-written tcgen05 kernels (csrc/dense_tc.cuh), 3xTF32 with the split fused into the pipeline ---------
+def _tc_operand(t: torch.Tensor) -> bool:
+    return (t.is_cuda and t.dtype == torch.float32 and t.dim() == 2 and t.stride(1) == 1 and t.stride(0) % 4 == 0
+            and t.stride(0) >= t.shape[1] and t.data_ptr() % 16 == 0 and t.shape[0] > 0 and t.shape[1] > 0)
+
+
+def tc_eligible(x: torch.Tensor, weight: torch.Tensor, bias=None) -> bool:
+    """Shapes the tcgen05 kernels take: 16-byte aligned rows everywhere the forward AND both gradients touch."""
+    return (_tc_operand(x) and _tc_operand(weight) and x.shape[1] == weight.shape[1] and weight.shape[0] % 4 == 0
+            and weight.shape[1] % 4 == 0
+            and (bias is None or (bias.is_cuda and bias.dtype == torch.float32 and bias.is_contiguous()
+                                  and bias.data_ptr() % 16 == 0)))
+
+
+def tc_mm_tn(a: torch.Tensor, b: torch.Tensor, bias=None) -> torch.Tensor:
+    """``a @ b.T (+ bias)``: a [M, K], b [N, K] (``bns_dense_tn_3xtf32``)."""
+    from .._lib import check, lib
+    M, K = a.shape
+    N = b.shape[0]
+    out = torch.empty((M, N), dtype=torch.float32, device=a.device)
+    with torch.cuda.device(a.device):
+        check(lib.bns_dense_tn_3xtf32(a.data_ptr(), a.stride(0), b.data_ptr(), b.stride(0),
+                                      None if bias is None else bias.data_ptr(), out.data_ptr(), out.stride(0), M, N, K,
+                                      torch.cuda.current_stream().cuda_stream), "bns_dense_tn_3xtf32")
+    return out
+
+
+def tc_mm_nt(a: torch.Tensor, b: torch.Tensor) -> torch.Tensor:
+    """``a.T @ b``: a [R, N1], b [R, N2] -> [N1, N2], contraction over the rows (``bns_dense_nt_3xtf32``)."""
+    from .._lib import check, lib
+    R, N1 = a.shape
+    N2 = b.shape[1]
+    out = torch.empty((N1, N2), dtype=torch.float32, device=a.device)
+    nbytes = lib.bns_dense_nt_workspace_bytes(R, N1, N2)
+    ws = torch.empty(max(nbytes, 16), dtype=torch.uint8, device=a.device)
+    with torch.cuda.device(a.device):
+        check(lib.bns_dense_nt_3xtf32(a.data_ptr(), a.stride(0), b.data_ptr(), b.stride(0), out.data_ptr(), out.stride(0),
+                                      R, N1, N2, ws.data_ptr(), nbytes, torch.cuda.current_stream().cuda_stream),
+              "bns_dense_nt_3xtf32")
+    return out
+
+
+class _LinearTc(torch.autograd.Function):
+
+    @staticmethod
+    def forward(ctx, x, weight, bias):
+        ctx.save_for_backward(x, weight)
+        ctx.has_bias = bias is not None
+        return tc_mm_tn(x, weight, bias)
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, weight = ctx.saved_tensors
+        dy = dy.contiguous()
+        dx = tc_mm_tn(dy, weight.t().contiguous()) if ctx.needs_input_grad[0] else None     # dY @ W
+        dw = tc_mm_nt(dy, x) if ctx.needs_input_grad[1] else None                            # dY^T @ X
+        db = dy.sum(0) if ctx.has_bias and ctx.needs_input_grad[2] else None
+        return dx, dw, db
+
+
 def linear(x: torch.Tensor, weight: torch.Tensor, bias=None) -> torch.Tensor:
     """Drop-in for ``F.linear`` on 2-D f32 CUDA inputs."""
     ok = x.is_cuda and x.dtype == torch.float32 and x.dim() == 2
+    if MODE == "tc" and ok and tc_eligible(x, weight, bias):
+        return _LinearTc.apply(x, weight, bias)
     if MODE == "bf16x3" and ok and x.numel() % 4 == 0 and weight.numel() % 4 == 0 and weight.shape[0] % 4 == 0:
         return _LinearBf16x3.apply(x, weight, bias)
     if ok and (MODE == "3xtf32" or (MODE == "auto" and x.shape[1] >= MIN_K_3X)):

@@ -118,6 +118,28 @@ int bns_split_bf16x3_f32(const float *x, int64_t n, void *out0 /*bf16 [n]*/, voi
 int bns_split_tf32_f32(const float *x, int64_t n, float *hi, float *lo, void *stream);
 
 /* ------------------------------------------------------------------------------------------------
+ * K8: the dense layers themselves.  Replaces, for 2-D f32 operands,
+ *     self.linear(feat) / self.linear1(feat) + self.linear2(ah)      module/layer.py:30, 38, 83, 92  (forward)
+ * and what autograd runs for them (grad_input = dY W, grad_weight = dY^T X) with hand-written tcgen05 kernels:
+ * kind::tf32 MMAs accumulating in TMEM, operands staged by TMA (SWIZZLE_128B), and the 3xTF32 operand split
+ * (hi = tf32(x), lo = x - hi; hi*hi + hi*lo + lo*hi) done in shared memory inside the pipeline, so the result is
+ * f32-accurate (~2^-21 relative per product) while every operand byte crosses HBM/L2 once (csrc/dense_tc.cuh).
+ *
+ * bns_dense_tn_3xtf32:  C[M, N] = A[M, K] * B[N, K]^T (+ bias[N]);  A, B, C row-major with leading dimensions
+ *   lda, ldb, ldc (floats).  Forward: A = X, B = weight.  Input gradient: A = dY, B = weight^T (a contiguous copy).
+ * bns_dense_nt_3xtf32:  C[N1, N2] = A[R, N1]^T * B[R, N2]  (contraction over the R rows, split across CTAs and
+ *   combined in split order -- deterministic).  Weight gradient: A = dY, B = X.  ws: at least
+ *   bns_dense_nt_workspace_bytes(R, N1, N2) bytes.
+ * All pointers 16-byte aligned, leading dimensions multiples of 4 (and N2 % 4 == 0); anything else returns
+ * BNS_E_INVALID and the caller uses the library GEMM.
+ * ----------------------------------------------------------------------------------------------*/
+int    bns_dense_tn_3xtf32(const float *A, int64_t lda, const float *B, int64_t ldb, const float *bias /*device [N] or NULL*/,
+                           float *C, int64_t ldc, int64_t M, int64_t N, int64_t K, void *stream);
+size_t bns_dense_nt_workspace_bytes(int64_t R, int64_t N1, int64_t N2);
+int    bns_dense_nt_3xtf32(const float *A, int64_t lda, const float *B, int64_t ldb, float *C, int64_t ldc,
+                           int64_t R, int64_t N1, int64_t N2, void *ws, size_t ws_bytes, void *stream);
+
+/* ------------------------------------------------------------------------------------------------
  * K10 (GAT, module/model.py:96-132 via dgl.nn.GATConv): the attention gradient.  For every entry k of row r:
  *     out[k * ldo] = < A[arow(r), :F], B[xrow(c_k), :F] >      (0 when the row or the entry is skipped)
  * arow / xrow as in bns_spmm_sum_f32 (row_map / col_map / n_direct).  F % 4 == 0, F <= 1024, 16-byte aligned rows.
