@@ -10,17 +10,19 @@
 // 128-byte swizzle pattern is untouched), then one thread issues the three MMAs per 8-wide k-step.  HBM/L2 see every
 // operand once; the library-composed variant (module/dense.py "3xtf32") needs a split pass plus three GEMMs.
 //
-// One CTA = one 128 x 128 output tile (x one slice of the contraction for the weight-gradient shape), 192 threads:
+// A work item = one 128 x 128 output tile (x one slice of the contraction for the weight-gradient shape); persistent CTAs
+// of 320 threads walk the items:
 //   warp 0      TMA producer (one lane)
 //   warp 1      TMEM allocator + MMA issuer (one lane)
-//   warps 2..5  split stage during the main loop, then the epilogue (tcgen05.ld -> +bias -> global)
+//   warps 2..5  split stage
+//   warps 6..9  epilogue (tcgen05.ld -> sum of the chains -> +bias -> global), overlapped with the next item's main loop
 // Pipeline barriers per stage: full (TMA -> split, transaction bytes), split (4 warps -> MMA), empty (tcgen05.commit
-// -> TMA); one accumulator barrier (last commit -> epilogue).
+// -> TMA); per TMEM buffer: acc_full (last commit -> epilogue), acc_empty (epilogue -> MMA).
 //
 // Accumulation chains.  The tensor core adds into the TMEM accumulator with truncation, so the error of one long
 // chain grows linearly (measured on B200: ~2.5e-7 of max|C| per 32-wide k-block, 2.6e-4 after 1040 k-blocks).  Two
-// counter-measures keep the result at cuBLAS-f32 level: k-blocks go round-robin into FOUR accumulators that the epilogue
-// adds in f32 (chains 4x shorter), and the weight-gradient contraction is cut into slices of <= 64 k-blocks whose
+// counter-measures keep the result at cuBLAS-f32 level: k-blocks go round-robin into kAcc accumulators that the epilogue
+// adds in f32 (shorter chains), and the weight-gradient contraction is cut into slices of <= kMaxChainKb k-blocks whose
 // partial tiles are summed by splitk_reduce_kernel in slice order (round-to-nearest f32, deterministic).
 //
 // Two operand layouts, through SWIZZLE_128B (K-major) / SWIZZLE_128B_ATOM_32B (MN-major) tensor maps:
@@ -39,11 +41,12 @@ constexpr int A_BYTES = BM * BK * 4;            // 16 KB
 constexpr int B_BYTES = BN * BK * 4;            // 16 KB
 constexpr int RAW_BYTES = A_BYTES + B_BYTES;    // TMA lands here; becomes the hi parts in place
 constexpr int STAGE_BYTES = 2 * RAW_BYTES;      // [A_hi | B_hi | A_lo | B_lo]
-constexpr int kThreadsTc = 192;
+constexpr int kThreadsTc = 320;                 // warp 0 TMA, warp 1 MMA, warps 2-5 split, warps 6-9 epilogue
 constexpr int kSplitThreads = 128;
-constexpr int kAcc = 4;                         // round-robin TMEM accumulators (see "accumulation chains" above)
-constexpr int kTmemCols = kAcc * BN;            // f32 accumulators: one column per output column each (all 512 columns)
-constexpr int kMaxChainKb = 64;                 // weight-gradient slices: at most this many k-blocks per CTA (16 per chain)
+constexpr int kEpiThreads = 128;
+constexpr int kAcc = 2;                         // round-robin TMEM accumulators per item (see "accumulation chains" above)
+constexpr int kTmemCols = 2 * kAcc * BN;        // 2 buffers x kAcc chains x one f32 column per output column = all 512
+constexpr int kMaxChainKb = 48;                 // weight-gradient slices: at most this many k-blocks per item (24 per chain)
 constexpr int BAR_BYTES = 256;
 constexpr int SMEM_BYTES = kStages * STAGE_BYTES + BAR_BYTES + 1024;   // + slack to align the stages to 1024
 constexpr int MN_BOX_BYTES = BK * 128;          // MN-major: one TMA box = BK rows x 32 floats
@@ -135,29 +138,32 @@ __device__ __forceinline__ float tf32_rna(float x) {
     return __uint_as_float(u);
 }
 
-template <bool kMN>
+// kTrunc: hi = x with the 13 low mantissa bits ignored BY THE TENSOR CORE (kind::tf32 reads the raw f32 words and drops
+// them -- verified on B200: same accuracy as the rounded variant), lo = x - trunc(x); saves the hi write-back, a third of
+// the split stage's shared-memory traffic.  Off (BNS_TC_TRUNC=0): hi = round-to-nearest TF32, written back in place.
+//
+// Persistent: gridDim.x = min(work items, SMs); a work item = (output tile, contraction slice).  All roles walk the same
+// item sequence; the shared-memory ring and its phases run on across items, and the accumulators are double-buffered in
+// TMEM (2 buffers x kAcc chains x 128 columns = all 512) so the epilogue of item i overlaps the main loop of item i+1.
+template <bool kMN, bool kTrunc>
 __global__ void __launch_bounds__(kThreadsTc, 1)
 gemm3x_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
               float *__restrict__ C, int64_t ldc, int64_t split_stride, const float *__restrict__ bias,
-              int M, int N, int num_kb, int tiles_n) {
+              int M, int N, int num_kb, int tiles_n, int tiles, int splits) {
     extern __shared__ uint8_t smem_raw[];
     const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
     uint8_t *base_ptr = smem_raw + (base - smem_u32(smem_raw));
     const uint32_t bars = base + kStages * STAGE_BYTES;
-    // barrier slots (8 bytes each): full[s], split[s], empty[s], accum; then the TMEM base address
+    // barrier slots (8 bytes each): full[s], split[s], empty[s], acc_full[2], acc_empty[2]; then the TMEM base address
     auto full_bar = [&](int s) { return bars + 8u * s; };
     auto split_bar = [&](int s) { return bars + 8u * (kStages + s); };
     auto empty_bar = [&](int s) { return bars + 8u * (2 * kStages + s); };
-    const uint32_t accum_bar = bars + 8u * (3 * kStages);
-    volatile uint32_t *tmem_slot = reinterpret_cast<volatile uint32_t *>(base_ptr + kStages * STAGE_BYTES + 8 * (3 * kStages + 1));
+    auto acc_full_bar = [&](int b) { return bars + 8u * (3 * kStages + b); };
+    auto acc_empty_bar = [&](int b) { return bars + 8u * (3 * kStages + 2 + b); };
+    volatile uint32_t *tmem_slot = reinterpret_cast<volatile uint32_t *>(base_ptr + kStages * STAGE_BYTES + 8 * (3 * kStages + 4));
 
-    const int tile = blockIdx.x;
-    const int m_t = tile / tiles_n, n_t = tile % tiles_n;
-    const int splits = gridDim.y;
-    const int kb0 = (int)(((int64_t)blockIdx.y * num_kb) / splits);
-    const int kb1 = (int)(((int64_t)(blockIdx.y + 1) * num_kb) / splits);
-    const int nkb = kb1 - kb0;
+    const int total_work = tiles * splits;
 
     if (warp == 0 && lane == 0) {
         asm volatile("prefetch.tensormap [%0];" ::"l"(&map_a) : "memory");
@@ -167,7 +173,10 @@ gemm3x_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__
             mbar_init(split_bar(s), kSplitThreads / 32);
             mbar_init(empty_bar(s), 1);
         }
-        mbar_init(accum_bar, 1);
+        for (int b = 0; b < 2; ++b) {
+            mbar_init(acc_full_bar(b), 1);
+            mbar_init(acc_empty_bar(b), kEpiThreads / 32);
+        }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     }
@@ -182,24 +191,34 @@ gemm3x_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
 
+    // work item w -> tile (m_t, n_t), contraction slice [kb0, kb1)
+#define BNS_TC_ITEM(w)                                                        \
+    const int split_ = (w) / tiles, tile_ = (w) % tiles;                      \
+    const int m_t = tile_ / tiles_n, n_t = tile_ % tiles_n;                   \
+    const int kb0 = (int)(((int64_t)split_ * num_kb) / splits);               \
+    const int nkb = (int)(((int64_t)(split_ + 1) * num_kb) / splits) - kb0;
+
     if (warp == 0) {
         if (lane == 0) {
             // ===== TMA producer =====
-            for (int i = 0; i < nkb; ++i) {
-                const int s = i % kStages;
-                const uint32_t ph = (uint32_t)(i / kStages) & 1u;
-                mbar_wait(empty_bar(s), ph ^ 1u);
-                mbar_expect_tx(full_bar(s), RAW_BYTES);
-                const uint32_t a_dst = base + s * STAGE_BYTES, b_dst = a_dst + A_BYTES;
-                const int kc = (kb0 + i) * BK;
-                if (!kMN) {
-                    tma_load_2d(a_dst, &map_a, full_bar(s), kc, m_t * BM);
-                    tma_load_2d(b_dst, &map_b, full_bar(s), kc, n_t * BN);
-                } else {
+            uint32_t g = 0;                                  // k-blocks issued so far (ring position)
+            for (int w = blockIdx.x; w < total_work; w += gridDim.x) {
+                BNS_TC_ITEM(w)
+                for (int i = 0; i < nkb; ++i, ++g) {
+                    const uint32_t s = g % kStages, ph = (g / kStages) & 1u;
+                    mbar_wait(empty_bar(s), ph ^ 1u);
+                    mbar_expect_tx(full_bar(s), RAW_BYTES);
+                    const uint32_t a_dst = base + s * STAGE_BYTES, b_dst = a_dst + A_BYTES;
+                    const int kc = (kb0 + i) * BK;
+                    if (!kMN) {
+                        tma_load_2d(a_dst, &map_a, full_bar(s), kc, m_t * BM);
+                        tma_load_2d(b_dst, &map_b, full_bar(s), kc, n_t * BN);
+                    } else {
 #pragma unroll
-                    for (int b = 0; b < BM / 32; ++b) tma_load_2d(a_dst + b * MN_BOX_BYTES, &map_a, full_bar(s), m_t * BM + 32 * b, kc);
+                        for (int b = 0; b < BM / 32; ++b) tma_load_2d(a_dst + b * MN_BOX_BYTES, &map_a, full_bar(s), m_t * BM + 32 * b, kc);
 #pragma unroll
-                    for (int b = 0; b < BN / 32; ++b) tma_load_2d(b_dst + b * MN_BOX_BYTES, &map_b, full_bar(s), n_t * BN + 32 * b, kc);
+                        for (int b = 0; b < BN / 32; ++b) tma_load_2d(b_dst + b * MN_BOX_BYTES, &map_b, full_bar(s), n_t * BN + 32 * b, kc);
+                    }
                 }
             }
         }
@@ -211,86 +230,115 @@ gemm3x_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__
                                    ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
             const uint32_t lbo = kMN ? (uint32_t)MN_BOX_BYTES : 0u, sbo = kMN ? 512u : 1024u, lay = kMN ? 1u : 2u;
             const uint32_t kstep = kMN ? 1024u : (uint32_t)(UMMA_K * 4);
-            for (int i = 0; i < nkb; ++i) {
-                const int s = i % kStages;
-                const uint32_t ph = (uint32_t)(i / kStages) & 1u;
-                mbar_wait(split_bar(s), ph);
+            uint32_t g = 0, it = 0;
+            for (int w = blockIdx.x; w < total_work; w += gridDim.x, ++it) {
+                BNS_TC_ITEM(w)
+                (void)m_t; (void)n_t; (void)kb0;
+                const uint32_t buf = it & 1u;
+                mbar_wait(acc_empty_bar(buf), ((it >> 1) & 1u) ^ 1u);      // epilogue has drained this buffer
                 tc_fence_after();
-                const uint32_t a_hi = base + s * STAGE_BYTES, b_hi = a_hi + A_BYTES;
-                const uint32_t a_lo = a_hi + RAW_BYTES, b_lo = a_lo + A_BYTES;
+                for (int i = 0; i < nkb; ++i, ++g) {
+                    const uint32_t s = g % kStages, ph = (g / kStages) & 1u;
+                    mbar_wait(split_bar(s), ph);
+                    tc_fence_after();
+                    const uint32_t a_hi = base + s * STAGE_BYTES, b_hi = a_hi + A_BYTES;
+                    const uint32_t a_lo = a_hi + RAW_BYTES, b_lo = a_lo + A_BYTES;
+                    const uint32_t d = tmem_base + (buf * kAcc + (uint32_t)(i % kAcc)) * BN;
 #pragma unroll
-                for (int k = 0; k < BK / UMMA_K; ++k) {
-                    const uint64_t dah = smem_desc(a_hi + k * kstep, lbo, sbo, lay), dbh = smem_desc(b_hi + k * kstep, lbo, sbo, lay);
-                    const uint64_t dal = smem_desc(a_lo + k * kstep, lbo, sbo, lay), dbl = smem_desc(b_lo + k * kstep, lbo, sbo, lay);
-                    const uint32_t d = tmem_base + (uint32_t)((i % kAcc) * BN);
-                    umma_tf32(d, dal, dbh, idesc, (i >= kAcc || k != 0) ? 1u : 0u);    // small terms first
-                    umma_tf32(d, dah, dbl, idesc, 1u);
-                    umma_tf32(d, dah, dbh, idesc, 1u);
+                    for (int k = 0; k < BK / UMMA_K; ++k) {
+                        const uint64_t dah = smem_desc(a_hi + k * kstep, lbo, sbo, lay), dbh = smem_desc(b_hi + k * kstep, lbo, sbo, lay);
+                        const uint64_t dal = smem_desc(a_lo + k * kstep, lbo, sbo, lay), dbl = smem_desc(b_lo + k * kstep, lbo, sbo, lay);
+                        umma_tf32(d, dal, dbh, idesc, (i >= kAcc || k != 0) ? 1u : 0u);    // small terms first
+                        umma_tf32(d, dah, dbl, idesc, 1u);
+                        umma_tf32(d, dah, dbh, idesc, 1u);
+                    }
+                    umma_commit(empty_bar(s));       // stage free once these MMAs have read it
                 }
-                umma_commit(empty_bar(s));       // stage free once these MMAs have read it
+                umma_commit(acc_full_bar(buf));      // this item's accumulators are complete
             }
-            umma_commit(accum_bar);              // accumulator complete
+        }
+    } else if (warp < 2 + kSplitThreads / 32) {
+        // ===== split warps =====
+        const int t = threadIdx.x - 64;
+        uint32_t g = 0;
+        for (int w = blockIdx.x; w < total_work; w += gridDim.x) {
+            BNS_TC_ITEM(w)
+            (void)m_t; (void)n_t; (void)kb0;
+            for (int i = 0; i < nkb; ++i, ++g) {
+                const uint32_t s = g % kStages, ph = (g / kStages) & 1u;
+                mbar_wait(full_bar(s), ph);
+                float4 *raw = reinterpret_cast<float4 *>(base_ptr + s * STAGE_BYTES);
+                float4 *lo = reinterpret_cast<float4 *>(base_ptr + s * STAGE_BYTES + RAW_BYTES);
+#pragma unroll 4
+                for (int j = 0; j < RAW_BYTES / 16 / kSplitThreads; ++j) {
+                    const int idx = t + j * kSplitThreads;
+                    const float4 x = raw[idx];
+                    float4 h, l;
+                    if (kTrunc) {
+                        h.x = __uint_as_float(__float_as_uint(x.x) & 0xffffe000u); h.y = __uint_as_float(__float_as_uint(x.y) & 0xffffe000u);
+                        h.z = __uint_as_float(__float_as_uint(x.z) & 0xffffe000u); h.w = __uint_as_float(__float_as_uint(x.w) & 0xffffe000u);
+                    } else {
+                        h.x = tf32_rna(x.x); h.y = tf32_rna(x.y); h.z = tf32_rna(x.z); h.w = tf32_rna(x.w);
+                        raw[idx] = h;
+                    }
+                    l.x = x.x - h.x; l.y = x.y - h.y; l.z = x.z - h.z; l.w = x.w - h.w;
+                    lo[idx] = l;
+                }
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic writes -> visible to the MMA's async reads
+                __syncwarp();
+                if (lane == 0) mbar_arrive(split_bar(s));
+            }
         }
     } else {
-        // ===== split warps, then epilogue =====
-        const int t = threadIdx.x - 64;
-        for (int i = 0; i < nkb; ++i) {
-            const int s = i % kStages;
-            const uint32_t ph = (uint32_t)(i / kStages) & 1u;
-            mbar_wait(full_bar(s), ph);
-            float4 *raw = reinterpret_cast<float4 *>(base_ptr + s * STAGE_BYTES);
-            float4 *lo = reinterpret_cast<float4 *>(base_ptr + s * STAGE_BYTES + RAW_BYTES);
-#pragma unroll 4
-            for (int j = 0; j < RAW_BYTES / 16 / kSplitThreads; ++j) {
-                const int idx = t + j * kSplitThreads;
-                const float4 x = raw[idx];
-                float4 h, l;
-                h.x = tf32_rna(x.x); h.y = tf32_rna(x.y); h.z = tf32_rna(x.z); h.w = tf32_rna(x.w);
-                l.x = x.x - h.x; l.y = x.y - h.y; l.z = x.z - h.z; l.w = x.w - h.w;
-                raw[idx] = h;
-                lo[idx] = l;
-            }
-            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic writes -> visible to the MMA's async reads
-            __syncwarp();
-            if (lane == 0) mbar_arrive(split_bar(s));
-        }
-        mbar_wait(accum_bar, 0);
-        tc_fence_after();
+        // ===== epilogue warps: TMEM -> (+ other chains, + bias) -> global =====
         const uint32_t q = warp & 3u;                    // TMEM lane quadrant this warp may read
-        const int nacc = nkb < kAcc ? nkb : kAcc;
-        const int row = m_t * BM + (int)(32 * q + lane);
-        float *Cout = C + (int64_t)blockIdx.y * split_stride + (int64_t)row * ldc;
+        uint32_t it = 0;
+        for (int w = blockIdx.x; w < total_work; w += gridDim.x, ++it) {
+            BNS_TC_ITEM(w)
+            (void)kb0;
+            const uint32_t buf = it & 1u;
+            mbar_wait(acc_full_bar(buf), (it >> 1) & 1u);
+            tc_fence_after();
+            const int nacc = nkb < kAcc ? nkb : kAcc;
+            const int row = m_t * BM + (int)(32 * q + lane);
+            float *Cout = C + (int64_t)split_ * split_stride + (int64_t)row * ldc;
+            const uint32_t tbase = tmem_base + ((32u * q) << 16) + buf * (uint32_t)(kAcc * BN);
 #pragma unroll 1
-        for (int c = 0; c < BN / 32; ++c) {
-            uint32_t v[32];
-            tmem_ld32(tmem_base + ((32u * q) << 16) + (uint32_t)(c * 32), v);
-            for (int a = 1; a < nacc; ++a) {            // the other accumulation chains, fixed order
-                uint32_t w[32];
-                tmem_ld32(tmem_base + ((32u * q) << 16) + (uint32_t)(a * BN + c * 32), w);
+            for (int c = 0; c < BN / 32; ++c) {
+                uint32_t v[32];
+                tmem_ld32(tbase + (uint32_t)(c * 32), v);
+                for (int a = 1; a < nacc; ++a) {            // the other accumulation chains, fixed order
+                    uint32_t u[32];
+                    tmem_ld32(tbase + (uint32_t)(a * BN + c * 32), u);
 #pragma unroll
-                for (int e = 0; e < 32; ++e) v[e] = __float_as_uint(__uint_as_float(v[e]) + __uint_as_float(w[e]));
-            }
-            const int col0 = n_t * BN + c * 32;
-            if (row < M) {
+                    for (int e = 0; e < 32; ++e) v[e] = __float_as_uint(__uint_as_float(v[e]) + __uint_as_float(u[e]));
+                }
+                const int col0 = n_t * BN + c * 32;
+                if (row < M) {
 #pragma unroll
-                for (int j = 0; j < 8; ++j) {
-                    const int col = col0 + 4 * j;
-                    if (col + 3 < N) {
-                        float4 o = make_float4(__uint_as_float(v[4 * j]), __uint_as_float(v[4 * j + 1]),
-                                               __uint_as_float(v[4 * j + 2]), __uint_as_float(v[4 * j + 3]));
-                        if (bias) {
-                            const float4 bb = __ldg(reinterpret_cast<const float4 *>(bias + col));
-                            o.x += bb.x; o.y += bb.y; o.z += bb.z; o.w += bb.w;
+                    for (int j = 0; j < 8; ++j) {
+                        const int col = col0 + 4 * j;
+                        if (col + 3 < N) {
+                            float4 o = make_float4(__uint_as_float(v[4 * j]), __uint_as_float(v[4 * j + 1]),
+                                                   __uint_as_float(v[4 * j + 2]), __uint_as_float(v[4 * j + 3]));
+                            if (bias) {
+                                const float4 bb = __ldg(reinterpret_cast<const float4 *>(bias + col));
+                                o.x += bb.x; o.y += bb.y; o.z += bb.z; o.w += bb.w;
+                            }
+                            *reinterpret_cast<float4 *>(Cout + col) = o;
+                        } else {
+                            for (int e = 0; e < 4; ++e)
+                                if (col + e < N) Cout[col + e] = __uint_as_float(v[4 * j + e]) + (bias ? bias[col + e] : 0.f);
                         }
-                        *reinterpret_cast<float4 *>(Cout + col) = o;
-                    } else {
-                        for (int e = 0; e < 4; ++e)
-                            if (col + e < N) Cout[col + e] = __uint_as_float(v[4 * j + e]) + (bias ? bias[col + e] : 0.f);
                     }
                 }
             }
+            tc_fence_before();                           // TMEM reads done -> the MMA issuer may overwrite this buffer
+            __syncwarp();
+            if (lane == 0) mbar_arrive(acc_empty_bar(buf));
         }
     }
+#undef BNS_TC_ITEM
 
     tc_fence_before();
     __syncthreads();
@@ -350,14 +398,23 @@ inline int make_map(CUtensorMap *m, const float *ptr, int64_t inner, int64_t row
 
 inline bool aligned16(const void *p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
 
-template <bool kMN>
+inline bool trunc_mode() {
+    static int v = -1;
+    if (v < 0) {
+        const char *e = getenv("BNS_TC_TRUNC");
+        v = (e && e[0] == '0') ? 0 : 1;
+    }
+    return v == 1;
+}
+
+template <bool kMN, bool kTrunc>
 int configure() {
     static bool done = false;      // per process; the attribute is per function, set once per device context in practice
     static int dev_done = -1;
     int dev = 0;
     BNS_CUDA(cudaGetDevice(&dev));
     if (!done || dev_done != dev) {
-        BNS_CUDA(cudaFuncSetAttribute(gemm3x_kernel<kMN>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+        BNS_CUDA(cudaFuncSetAttribute(gemm3x_kernel<kMN, kTrunc>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
         done = true;
         dev_done = dev;
     }
@@ -380,13 +437,21 @@ extern "C" int bns_dense_tn_3xtf32(const float *A, int64_t lda, const float *B, 
     if (rc) return rc;
     rc = tc::make_map(&mb, B, K, N, ldb, tc::BK, tc::BN);
     if (rc) return rc;
-    rc = tc::configure<false>();
+    const bool tr = tc::trunc_mode();
+    rc = tr ? tc::configure<false, true>() : tc::configure<false, false>();
     if (rc) return rc;
     const int tiles_m = (int)((M + tc::BM - 1) / tc::BM), tiles_n = (int)((N + tc::BN - 1) / tc::BN);
     const int num_kb = (int)((K + tc::BK - 1) / tc::BK);
-    dim3 grid((unsigned)(tiles_m * (int64_t)tiles_n), 1, 1);
-    tc::gemm3x_kernel<false><<<grid, tc::kThreadsTc, tc::SMEM_BYTES, as_stream(stream)>>>(ma, mb, C, ldc, 0, bias, (int)M, (int)N,
-                                                                                         num_kb, tiles_n);
+    const int64_t tiles64 = tiles_m * (int64_t)tiles_n;
+    BNS_REQUIRE(tiles64 < (1ll << 31), "bns_dense_tn_3xtf32: too many tiles");
+    const int tiles = (int)tiles64;
+    dim3 grid((unsigned)(tiles < sm_count() ? tiles : sm_count()), 1, 1);
+    if (tr)
+        tc::gemm3x_kernel<false, true><<<grid, tc::kThreadsTc, tc::SMEM_BYTES, as_stream(stream)>>>(ma, mb, C, ldc, 0, bias, (int)M,
+                                                                                                   (int)N, num_kb, tiles_n, tiles, 1);
+    else
+        tc::gemm3x_kernel<false, false><<<grid, tc::kThreadsTc, tc::SMEM_BYTES, as_stream(stream)>>>(ma, mb, C, ldc, 0, bias, (int)M,
+                                                                                                    (int)N, num_kb, tiles_n, tiles, 1);
     ++g_launches;
     BNS_CUDA(cudaGetLastError());
     return BNS_OK;
@@ -441,19 +506,27 @@ extern "C" int bns_dense_nt_3xtf32(const float *A, int64_t lda, const float *B, 
     if (rc) return rc;
     rc = tc::make_map(&mb, B, N2, R, ldb, 32, tc::BK, true);
     if (rc) return rc;
-    rc = tc::configure<true>();
+    const bool tr = tc::trunc_mode();
+    rc = tr ? tc::configure<true, true>() : tc::configure<true, false>();
     if (rc) return rc;
     const int tiles_m = (int)((N1 + tc::BM - 1) / tc::BM), tiles_n = (int)((N2 + tc::BN - 1) / tc::BN);
     const int num_kb = (int)((R + tc::BK - 1) / tc::BK);
-    dim3 grid((unsigned)(tiles_m * tiles_n), (unsigned)splits, 1);
+    const int tiles = tiles_m * tiles_n;
+    const int64_t work = (int64_t)tiles * splits;
+    BNS_REQUIRE(work < (1ll << 31), "bns_dense_nt_3xtf32: too many work items");
+    dim3 grid((unsigned)(work < sm_count() ? work : sm_count()), 1, 1);
     cudaStream_t st = as_stream(stream);
+    float *w = splits == 1 ? C : static_cast<float *>(ws);
+    const int64_t ldw = splits == 1 ? ldc : N2, slice = splits == 1 ? 0 : N1 * N2;
+    if (tr)
+        tc::gemm3x_kernel<true, true><<<grid, tc::kThreadsTc, tc::SMEM_BYTES, st>>>(ma, mb, w, ldw, slice, nullptr, (int)N1, (int)N2,
+                                                                                    num_kb, tiles_n, tiles, splits);
+    else
+        tc::gemm3x_kernel<true, false><<<grid, tc::kThreadsTc, tc::SMEM_BYTES, st>>>(ma, mb, w, ldw, slice, nullptr, (int)N1, (int)N2,
+                                                                                     num_kb, tiles_n, tiles, splits);
     if (splits == 1) {
-        tc::gemm3x_kernel<true><<<grid, tc::kThreadsTc, tc::SMEM_BYTES, st>>>(ma, mb, C, ldc, 0, nullptr, (int)N1, (int)N2, num_kb, tiles_n);
         ++g_launches;
     } else {
-        float *w = static_cast<float *>(ws);
-        tc::gemm3x_kernel<true><<<grid, tc::kThreadsTc, tc::SMEM_BYTES, st>>>(ma, mb, w, N2, N1 * N2, nullptr, (int)N1, (int)N2, num_kb,
-                                                                              tiles_n);
         const int64_t total4 = N1 * N2 / 4;
         tc::splitk_reduce_kernel<<<(unsigned)((total4 + 255) / 256), 256, 0, st>>>(reinterpret_cast<const float4 *>(w), total4, splits,
                                                                                    N2 / 4, C, ldc, total4);

@@ -1,19 +1,19 @@
 """Dense layers of the path (K8, module/layer.py:30, 38, 83, 92 of the reference are plain ``nn.Linear`` in fp32).
 
 The reference runs them as true-fp32 cuBLAS SGEMMs (torch 1.12: ``allow_tf32=False`` for matmul).  On B200 the fp32
-SIMT pipe gives ~45 TFLOP/s -- after the SpMM work it is the largest share of the epoch -- while one TF32 tensor-core
-pass would miss the 1e-4 parity bar (10-bit mantissa).  ``linear()`` below therefore uses the error-compensated
-**3xTF32** scheme: split every f32 operand into ``hi = tf32(x)`` and ``lo = x - hi`` (exact in f32) and accumulate
-``hi*hi + hi*lo + lo*hi`` in three tensor-core GEMMs with f32 accumulation; the dropped ``lo*lo`` term is 2^-22
-relative, i.e. f32-level accuracy.  The GEMMs themselves are library calls (cuBLAS TF32, what the contract allows for
-plain GEMMs); a hand-written tcgen05 kernel with the LayerNorm / ReLU / dropout epilogue fused is the SURVEY §8(f)
-rank-2 follow-up.
+SIMT pipe gives ~45-60 TFLOP/s -- after the SpMM work the largest share of the epoch -- while one TF32 tensor-core
+pass would miss the 1e-4 parity bar (10-bit mantissa).  ``linear()`` therefore uses the error-compensated **3xTF32**
+scheme: split every f32 operand into ``hi = tf32(x)`` and ``lo = x - hi`` (exact in f32) and accumulate
+``hi*hi + hi*lo + lo*hi`` on the tensor cores with f32 accumulation; the dropped ``lo*lo`` term is 2^-22 relative.
 
-``MODE`` (env BNS_DENSE): "auto" (default: 3xtf32 where K >= 512, i.e. the layer-0 GEMMs, fp32 cuBLAS elsewhere) |
-"fp32" (the literal reference precision everywhere) | "3xtf32" | "bf16x3".  tools/bench_dense.py on B200, M=232,965
-K=1204 N=256: fp32 2.37 ms, one TF32 GEMM 0.25 ms (585 TFLOP/s), fused split pass 0.5 ms.  First attempt, kept for the record:  Measured on B200 (round 1, Reddit
-shape, N=1): 3xtf32 built from three cuBLAS TF32 GEMMs + the split passes is SLOWER than fp32 SIMT cuBLAS (44.2 vs
-37.8 ms/epoch), so it is off by default; the win needs the split fused into a hand-written tcgen05 kernel.
+``MODE`` (env BNS_DENSE): "tc" (default) -- the hand-written tcgen05 kernels of csrc/dense_tc.cuh: 3xTF32 with the
+operand split fused into the TMA -> shared memory -> TMEM pipeline (forward, input gradient, split-K weight gradient);
+operands whose rows are not 16-byte multiples fall back to fp32 cuBLAS | "fp32" (cuBLAS SIMT, the literal reference
+precision) | "auto" (library-composed 3xtf32 where K >= 512) | "3xtf32" | "bf16x3".
+B200, M=232,965 K=1204 N=256 (tools/check_dense_tc.py perf): fp32 cuBLAS 2.37 ms fwd / 3.15 ms dW; tc 0.95 / 0.97 ms
+with max error 2.7e-6 / 3.5e-6 of max|C| against f64 (cuBLAS fp32: 1.9e-6 / 1.5e-6).  History: the library-composed
+3xtf32 (three cuBLAS TF32 GEMMs + a split pass) was slower than fp32 cuBLAS except at K >= 512, bf16x3 always slower
+(profiles/bench_n1_r01_*_negative_result.json).
 """
 import os
 
@@ -27,7 +27,7 @@ import threading
 # fp32 ones included (forward AND backward -- hence the custom fp32 Function below instead of F.linear).
 _GEMM_LOCK = threading.RLock()
 
-MODE = os.environ.get("BNS_DENSE", "auto")
+MODE = os.environ.get("BNS_DENSE", "tc")
 MIN_K_3X = 512       # "auto": 3xTF32 only where the GEMM is big enough to repay the split pass (layer 0: K = 2 * n_feat)
 
 
@@ -218,8 +218,20 @@ class _LinearTc(torch.autograd.Function):
 def linear(x: torch.Tensor, weight: torch.Tensor, bias=None) -> torch.Tensor:
     """Drop-in for ``F.linear`` on 2-D f32 CUDA inputs."""
     ok = x.is_cuda and x.dtype == torch.float32 and x.dim() == 2
-    if MODE == "tc" and ok and tc_eligible(x, weight, bias):
-        return _LinearTc.apply(x, weight, bias)
+    if MODE == "tc" and ok:
+        n = weight.shape[0]
+        pad = (-n) % 4
+        if pad == 0:
+            if tc_eligible(x, weight, bias):
+                return _LinearTc.apply(x, weight, bias)
+        elif weight.dim() == 2 and weight.is_cuda and weight.dtype == torch.float32:
+            # e.g. 41 classes: run 44 output columns (zero rows of W) so that every row stays 16-byte aligned for TMA
+            # and slice; autograd pads dY / slices dW accordingly
+            w = F.pad(weight, (0, 0, 0, pad))
+            b = F.pad(bias, (0, pad)) if bias is not None else None
+            if tc_eligible(x, w, b):
+                return _LinearTc.apply(x, w, b)[:, :n]
+        return _LinearFp32.apply(x, weight, bias)        # shapes TMA cannot address (rows not 16-byte multiples)
     if MODE == "bf16x3" and ok and x.numel() % 4 == 0 and weight.numel() % 4 == 0 and weight.shape[0] % 4 == 0:
         return _LinearBf16x3.apply(x, weight, bias)
     if ok and (MODE == "3xtf32" or (MODE == "auto" and x.shape[1] >= MIN_K_3X)):
