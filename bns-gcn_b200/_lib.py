@@ -49,8 +49,10 @@ SIGNATURES = {
                                             c_int64, c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),
     "bns_split_tf32_f32": (c_int, [c_void_p, c_int64, c_void_p, c_void_p, c_void_p]),
     "bns_split_bf16x3_f32": (c_int, [c_void_p, c_int64, c_void_p, c_void_p, c_void_p, c_void_p]),
-    "bns_dense_tn_3xtf32": (c_int, [c_void_p, c_int64, c_void_p, c_int64, c_void_p, c_void_p, c_int64, c_int64, c_int64,
-                                    c_int64, c_void_p]),
+    "bns_dense_tn_3xtf32": (c_int, [c_void_p, c_int64, c_void_p, c_int64, c_void_p, c_void_p, c_int64, c_void_p, c_int64,
+                                    c_int64, c_int64, c_int64, c_void_p]),
+    "bns_colsum_workspace_bytes": (c_size_t, [c_int64]),
+    "bns_colsum_f32": (c_int, [c_void_p, c_int64, c_int64, c_int64, c_void_p, c_void_p, c_size_t, c_void_p]),
     "bns_dense_nt_workspace_bytes": (c_size_t, [c_int64, c_int64, c_int64]),
     "bns_dense_nt_3xtf32": (c_int, [c_void_p, c_int64, c_void_p, c_int64, c_void_p, c_int64, c_int64, c_int64, c_int64,
                                     c_void_p, c_size_t, c_void_p]),

@@ -1284,6 +1284,80 @@ extern "C" int bns_ln_relu_dropout_bwd_f32(const float *dy, int64_t lddy, const 
 }
 
 // =================================================================================================
+// column sums (bias gradients of the dense layers: db = dY.sum(0)), deterministic two-pass
+// =================================================================================================
+namespace {
+
+constexpr int kColsumMaxCols = 1024;
+
+// block b sums rows b, b + gridDim.x, ... ; thread (rg, c) = (t / CV, t % CV) owns float4 column c of every RG-th of them
+__global__ void __launch_bounds__(kThreads) colsum_partial_kernel(const float *__restrict__ X, int64_t ld, int64_t rows, int CV,
+                                                                 float4 *__restrict__ partial) {
+    __shared__ float4 s_acc[kThreads];
+    const int RG = kThreads / CV;
+    const int rg = threadIdx.x / CV, c = threadIdx.x % CV;
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (rg < RG) {
+        // contiguous row range per block, rows interleaved over the row groups inside it
+        const int64_t per = (rows + gridDim.x - 1) / gridDim.x;
+        const int64_t r0 = (int64_t)blockIdx.x * per, r1 = r0 + per < rows ? r0 + per : rows;
+        for (int64_t r = r0 + rg; r < r1; r += RG) {
+            const float4 v = __ldg(reinterpret_cast<const float4 *>(X + r * ld) + c);
+            acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+        }
+    }
+    s_acc[threadIdx.x] = acc;
+    __syncthreads();
+    if (rg == 0) {
+        for (int g = 1; g < RG; ++g) {
+            const float4 v = s_acc[g * CV + c];
+            acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+        }
+        partial[(int64_t)blockIdx.x * CV + c] = acc;
+    }
+}
+
+__global__ void colsum_final_kernel(const float4 *__restrict__ partial, int n_part, int CV, float4 *__restrict__ out) {
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= CV) return;
+    float4 acc = partial[c];
+    for (int p = 1; p < n_part; ++p) {
+        const float4 v = partial[(int64_t)p * CV + c];
+        acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+    }
+    out[c] = acc;
+}
+
+inline int colsum_blocks() { return sm_count() * 4; }
+
+}  // namespace
+
+extern "C" size_t bns_colsum_workspace_bytes(int64_t cols) {
+    return cols > 0 ? (size_t)colsum_blocks() * (size_t)((cols + 3) / 4) * sizeof(float4) : 0;
+}
+
+extern "C" int bns_colsum_f32(const float *X, int64_t ld, int64_t rows, int64_t cols, float *out, void *ws, size_t ws_bytes,
+                              void *stream) {
+    BNS_REQUIRE(X && out, "bns_colsum_f32: NULL argument");
+    BNS_REQUIRE(rows > 0 && cols > 0 && cols % 4 == 0 && cols <= kColsumMaxCols, "bns_colsum_f32: need 0 < cols <= 1024, cols %% 4 == 0");
+    BNS_REQUIRE(ld >= cols && ld % 4 == 0 && (reinterpret_cast<uintptr_t>(X) & 15u) == 0 && (reinterpret_cast<uintptr_t>(out) & 15u) == 0,
+                "bns_colsum_f32: 16-byte aligned rows required");
+    const size_t need = bns_colsum_workspace_bytes(cols);
+    if (!ws || ws_bytes < need || (reinterpret_cast<uintptr_t>(ws) & 15u))
+        return fail(BNS_E_WORKSPACE, "bns_colsum_f32: workspace %zu bytes < %zu needed", ws_bytes, need);
+    const int CV = (int)(cols / 4);
+    int blocks = colsum_blocks();
+    if ((int64_t)blocks > rows) blocks = (int)rows;
+    cudaStream_t st = as_stream(stream);
+    colsum_partial_kernel<<<blocks, kThreads, 0, st>>>(X, ld, rows, CV, reinterpret_cast<float4 *>(ws));
+    colsum_final_kernel<<<(CV + 127) / 128, 128, 0, st>>>(reinterpret_cast<const float4 *>(ws), blocks, CV,
+                                                          reinterpret_cast<float4 *>(out));
+    g_launches += 2;
+    BNS_CUDA(cudaGetLastError());
+    return BNS_OK;
+}
+
+// =================================================================================================
 // f32 -> 3 x bf16 split (dense layers, module/dense.py "bf16x3"): x = b0 + b1 + b2 to 24 bits of mantissa
 // =================================================================================================
 namespace {

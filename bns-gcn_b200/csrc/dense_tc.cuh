@@ -149,7 +149,7 @@ template <bool kMN, bool kTrunc>
 __global__ void __launch_bounds__(kThreadsTc, 1)
 gemm3x_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
               float *__restrict__ C, int64_t ldc, int64_t split_stride, const float *__restrict__ bias,
-              int M, int N, int num_kb, int tiles_n, int tiles, int splits) {
+              const float *__restrict__ addend, int64_t ldadd, int M, int N, int num_kb, int tiles_n, int tiles, int splits) {
     extern __shared__ uint8_t smem_raw[];
     const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
@@ -302,6 +302,7 @@ gemm3x_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__
             const int nacc = nkb < kAcc ? nkb : kAcc;
             const int row = m_t * BM + (int)(32 * q + lane);
             float *Cout = C + (int64_t)split_ * split_stride + (int64_t)row * ldc;
+            const float *Add = addend ? addend + (int64_t)row * ldadd : nullptr;
             const uint32_t tbase = tmem_base + ((32u * q) << 16) + buf * (uint32_t)(kAcc * BN);
 #pragma unroll 1
             for (int c = 0; c < BN / 32; ++c) {
@@ -325,10 +326,15 @@ gemm3x_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__
                                 const float4 bb = __ldg(reinterpret_cast<const float4 *>(bias + col));
                                 o.x += bb.x; o.y += bb.y; o.z += bb.z; o.w += bb.w;
                             }
+                            if (Add) {
+                                const float4 aa = *reinterpret_cast<const float4 *>(Add + col);
+                                o.x += aa.x; o.y += aa.y; o.z += aa.z; o.w += aa.w;
+                            }
                             *reinterpret_cast<float4 *>(Cout + col) = o;
                         } else {
                             for (int e = 0; e < 4; ++e)
-                                if (col + e < N) Cout[col + e] = __uint_as_float(v[4 * j + e]) + (bias ? bias[col + e] : 0.f);
+                                if (col + e < N)
+                                    Cout[col + e] = __uint_as_float(v[4 * j + e]) + (bias ? bias[col + e] : 0.f) + (Add ? Add[col + e] : 0.f);
                         }
                     }
                 }
@@ -423,14 +429,15 @@ int configure() {
 
 }  // namespace tc
 
-// C[M, N] = A[M, K] * B[N, K]^T (+ bias[N])
-extern "C" int bns_dense_tn_3xtf32(const float *A, int64_t lda, const float *B, int64_t ldb, const float *bias, float *C,
-                                   int64_t ldc, int64_t M, int64_t N, int64_t K, void *stream) {
+// C[M, N] = A[M, K] * B[N, K]^T (+ bias[N]) (+ addend[M, N])
+extern "C" int bns_dense_tn_3xtf32(const float *A, int64_t lda, const float *B, int64_t ldb, const float *bias,
+                                   const float *addend, int64_t ldadd, float *C, int64_t ldc, int64_t M, int64_t N, int64_t K,
+                                   void *stream) {
     BNS_REQUIRE(A && B && C, "bns_dense_tn_3xtf32: NULL argument");
     BNS_REQUIRE(M > 0 && N > 0 && K > 0 && M < (1ll << 31) && N < (1ll << 31) && K < (1ll << 31), "bns_dense_tn_3xtf32: bad shape");
     BNS_REQUIRE(lda >= K && ldb >= K && ldc >= N, "bns_dense_tn_3xtf32: leading dimension smaller than the row");
     BNS_REQUIRE(lda % 4 == 0 && ldb % 4 == 0 && ldc % 4 == 0 && tc::aligned16(A) && tc::aligned16(B) && tc::aligned16(C) &&
-                    (!bias || tc::aligned16(bias)),
+                    (!bias || tc::aligned16(bias)) && (!addend || (tc::aligned16(addend) && ldadd % 4 == 0 && ldadd >= N)),
                 "bns_dense_tn_3xtf32: operands must be 16-byte aligned with leading dimensions that are multiples of 4");
     CUtensorMap ma, mb;
     int rc = tc::make_map(&ma, A, K, M, lda, tc::BK, tc::BM);
@@ -447,11 +454,11 @@ extern "C" int bns_dense_tn_3xtf32(const float *A, int64_t lda, const float *B, 
     const int tiles = (int)tiles64;
     dim3 grid((unsigned)(tiles < sm_count() ? tiles : sm_count()), 1, 1);
     if (tr)
-        tc::gemm3x_kernel<false, true><<<grid, tc::kThreadsTc, tc::SMEM_BYTES, as_stream(stream)>>>(ma, mb, C, ldc, 0, bias, (int)M,
-                                                                                                   (int)N, num_kb, tiles_n, tiles, 1);
+        tc::gemm3x_kernel<false, true><<<grid, tc::kThreadsTc, tc::SMEM_BYTES, as_stream(stream)>>>(ma, mb, C, ldc, 0, bias, addend, ldadd,
+                                                                                                   (int)M, (int)N, num_kb, tiles_n, tiles, 1);
     else
-        tc::gemm3x_kernel<false, false><<<grid, tc::kThreadsTc, tc::SMEM_BYTES, as_stream(stream)>>>(ma, mb, C, ldc, 0, bias, (int)M,
-                                                                                                    (int)N, num_kb, tiles_n, tiles, 1);
+        tc::gemm3x_kernel<false, false><<<grid, tc::kThreadsTc, tc::SMEM_BYTES, as_stream(stream)>>>(ma, mb, C, ldc, 0, bias, addend, ldadd,
+                                                                                                    (int)M, (int)N, num_kb, tiles_n, tiles, 1);
     ++g_launches;
     BNS_CUDA(cudaGetLastError());
     return BNS_OK;
@@ -519,11 +526,11 @@ extern "C" int bns_dense_nt_3xtf32(const float *A, int64_t lda, const float *B, 
     float *w = splits == 1 ? C : static_cast<float *>(ws);
     const int64_t ldw = splits == 1 ? ldc : N2, slice = splits == 1 ? 0 : N1 * N2;
     if (tr)
-        tc::gemm3x_kernel<true, true><<<grid, tc::kThreadsTc, tc::SMEM_BYTES, st>>>(ma, mb, w, ldw, slice, nullptr, (int)N1, (int)N2,
-                                                                                    num_kb, tiles_n, tiles, splits);
+        tc::gemm3x_kernel<true, true><<<grid, tc::kThreadsTc, tc::SMEM_BYTES, st>>>(ma, mb, w, ldw, slice, nullptr, nullptr, 0, (int)N1,
+                                                                                    (int)N2, num_kb, tiles_n, tiles, splits);
     else
-        tc::gemm3x_kernel<true, false><<<grid, tc::kThreadsTc, tc::SMEM_BYTES, st>>>(ma, mb, w, ldw, slice, nullptr, (int)N1, (int)N2,
-                                                                                     num_kb, tiles_n, tiles, splits);
+        tc::gemm3x_kernel<true, false><<<grid, tc::kThreadsTc, tc::SMEM_BYTES, st>>>(ma, mb, w, ldw, slice, nullptr, nullptr, 0, (int)N1,
+                                                                                     (int)N2, num_kb, tiles_n, tiles, splits);
     if (splits == 1) {
         ++g_launches;
     } else {

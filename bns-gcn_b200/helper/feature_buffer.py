@@ -258,6 +258,9 @@ class Buffer(object):
         F = grad.shape[1]
         if not grad.is_contiguous():
             grad = grad.contiguous()
+        trace = getattr(self, "trace", None)          # tests only: {name: tensor} of the gradients around the exchange
+        if trace is not None:
+            trace[f"grad_u{layer}"] = grad.detach().clone()
         main, cs = torch.cuda.current_stream(self._device), self._comm_stream
         start, done = torch.cuda.Event(), torch.cuda.Event()
         start.record(main)
@@ -298,6 +301,8 @@ class Buffer(object):
         for i in range(1, self._size):               # the reference's order: idx = left, i = 1 .. P-1 (:111-129)
             left = (self._rank - i + self._size) % self._size
             ops.scatter_add_div(inner, self._selected[left], recv[left], self._ratio[left])      # K5
+        if trace is not None:
+            trace[f"grad_h{layer}"] = inner.detach().clone()
         return inner
 
     def __del__(self):

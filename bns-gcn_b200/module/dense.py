@@ -169,16 +169,34 @@ def tc_eligible(x: torch.Tensor, weight: torch.Tensor, bias=None) -> bool:
                                   and bias.data_ptr() % 16 == 0)))
 
 
-def tc_mm_tn(a: torch.Tensor, b: torch.Tensor, bias=None) -> torch.Tensor:
-    """``a @ b.T (+ bias)``: a [M, K], b [N, K] (``bns_dense_tn_3xtf32``)."""
+def tc_mm_tn(a: torch.Tensor, b: torch.Tensor, bias=None, addend=None) -> torch.Tensor:
+    """``a @ b.T (+ bias) (+ addend)``: a [M, K], b [N, K], addend [M, >= N] (``bns_dense_tn_3xtf32``)."""
     from .._lib import check, lib
     M, K = a.shape
     N = b.shape[0]
     out = torch.empty((M, N), dtype=torch.float32, device=a.device)
     with torch.cuda.device(a.device):
         check(lib.bns_dense_tn_3xtf32(a.data_ptr(), a.stride(0), b.data_ptr(), b.stride(0),
-                                      None if bias is None else bias.data_ptr(), out.data_ptr(), out.stride(0), M, N, K,
+                                      None if bias is None else bias.data_ptr(),
+                                      None if addend is None else addend.data_ptr(),
+                                      0 if addend is None else addend.stride(0), out.data_ptr(), out.stride(0), M, N, K,
                                       torch.cuda.current_stream().cuda_stream), "bns_dense_tn_3xtf32")
+    return out
+
+
+def colsum(x: torch.Tensor) -> torch.Tensor:
+    """``x.sum(0)`` of a 2-D f32 CUDA matrix (bias gradients): ``bns_colsum_f32`` where the rows are 16-byte
+    multiples, torch otherwise."""
+    if not (_tc_operand(x) and x.shape[1] % 4 == 0 and x.shape[1] <= 1024):
+        return x.sum(0)
+    from .._lib import check, lib
+    rows, cols = x.shape
+    out = torch.empty(cols, dtype=torch.float32, device=x.device)
+    nbytes = lib.bns_colsum_workspace_bytes(cols)
+    ws = torch.empty(nbytes, dtype=torch.uint8, device=x.device)
+    with torch.cuda.device(x.device):
+        check(lib.bns_colsum_f32(x.data_ptr(), x.stride(0), rows, cols, out.data_ptr(), ws.data_ptr(), nbytes,
+                                 torch.cuda.current_stream().cuda_stream), "bns_colsum_f32")
     return out
 
 
@@ -198,12 +216,14 @@ def tc_mm_nt(a: torch.Tensor, b: torch.Tensor) -> torch.Tensor:
 
 
 class _LinearTc(torch.autograd.Function):
+    """``x @ W^T + b (+ addend)``; the addend (the other branch of ``linear1(feat) + linear2(ah)``) rides in the
+    epilogue and simply receives ``dY`` in backward."""
 
     @staticmethod
-    def forward(ctx, x, weight, bias):
+    def forward(ctx, x, weight, bias, addend):
         ctx.save_for_backward(x, weight)
         ctx.has_bias = bias is not None
-        return tc_mm_tn(x, weight, bias)
+        return tc_mm_tn(x, weight, bias, addend)
 
     @staticmethod
     def backward(ctx, dy):
@@ -211,27 +231,43 @@ class _LinearTc(torch.autograd.Function):
         dy = dy.contiguous()
         dx = tc_mm_tn(dy, weight.t().contiguous()) if ctx.needs_input_grad[0] else None     # dY @ W
         dw = tc_mm_nt(dy, x) if ctx.needs_input_grad[1] else None                            # dY^T @ X
-        db = dy.sum(0) if ctx.has_bias and ctx.needs_input_grad[2] else None
-        return dx, dw, db
+        db = colsum(dy) if ctx.has_bias and ctx.needs_input_grad[2] else None
+        da = dy if ctx.needs_input_grad[3] else None
+        return dx, dw, db, da
 
 
-def linear(x: torch.Tensor, weight: torch.Tensor, bias=None) -> torch.Tensor:
-    """Drop-in for ``F.linear`` on 2-D f32 CUDA inputs."""
+def linear(x: torch.Tensor, weight: torch.Tensor, bias=None, addend=None) -> torch.Tensor:
+    """Drop-in for ``F.linear`` on 2-D f32 CUDA inputs; ``addend`` ([M, >= out_features], extra columns ignored) is
+    added to the result -- inside the GEMM epilogue in "tc" mode (when it has exactly the padded output width)."""
+    n = weight.shape[0]
+    if addend is not None:
+        y = _linear(x, weight, bias, addend)
+        return y if y is not None else _linear(x, weight, bias, None) + addend[:, :n]
+    return _linear(x, weight, bias, None)
+
+
+def _linear(x, weight, bias, addend):
+    """Returns None when ``addend`` was given but cannot be fused (the caller adds it)."""
     ok = x.is_cuda and x.dtype == torch.float32 and x.dim() == 2
     if MODE == "tc" and ok:
         n = weight.shape[0]
         pad = (-n) % 4
+        add_ok = addend is None or (_tc_operand(addend) and addend.shape[0] == x.shape[0] and addend.shape[1] == n + pad)
         if pad == 0:
-            if tc_eligible(x, weight, bias):
-                return _LinearTc.apply(x, weight, bias)
-        elif weight.dim() == 2 and weight.is_cuda and weight.dtype == torch.float32:
+            if add_ok and tc_eligible(x, weight, bias):
+                return _LinearTc.apply(x, weight, bias, addend)
+        elif add_ok and weight.dim() == 2 and weight.is_cuda and weight.dtype == torch.float32:
             # e.g. 41 classes: run 44 output columns (zero rows of W) so that every row stays 16-byte aligned for TMA
             # and slice; autograd pads dY / slices dW accordingly
             w = F.pad(weight, (0, 0, 0, pad))
             b = F.pad(bias, (0, pad)) if bias is not None else None
             if tc_eligible(x, w, b):
-                return _LinearTc.apply(x, w, b)[:, :n]
+                return _LinearTc.apply(x, w, b, addend)[:, :n]
+        if addend is not None:
+            return None
         return _LinearFp32.apply(x, weight, bias)        # shapes TMA cannot address (rows not 16-byte multiples)
+    if addend is not None:
+        return None
     if MODE == "bf16x3" and ok and x.numel() % 4 == 0 and weight.numel() % 4 == 0 and weight.shape[0] % 4 == 0:
         return _LinearBf16x3.apply(x, weight, bias)
     if ok and (MODE == "3xtf32" or (MODE == "auto" and x.shape[1] >= MIN_K_3X)):

@@ -118,11 +118,12 @@ class GraphSAGELayer(nn.Module):
             num_dst = graph.num_nodes('_V')
             if AGGREGATE_AFTER_TRANSFORM and self.linear2.out_features < self.linear2.in_features:
                 t, out = _narrow_first(self.linear2.weight, feat)
-                ah = _aggregate(graph, t, graph.recip(in_norm))[:, :out]
-                res = self._lin(self.linear1, feat[0:num_dst]) + ah
+                ah = _aggregate(graph, t, graph.recip(in_norm))      # [n_in, out padded to 4]; the "+ ah" rides in
+                res = dense.linear(feat[0:num_dst], self.linear1.weight, self.linear1.bias, addend=ah)   # the epilogue
                 return res + self.linear2.bias if self.linear2.bias is not None else res
             ah = _aggregate(graph, feat, graph.recip(in_norm))                       # :85-91  (sum / degs)
-            return self._lin(self.linear1, feat[0:num_dst]) + self._lin(self.linear2, ah)  # :92
+            return dense.linear(feat[0:num_dst], self.linear1.weight, self.linear1.bias,
+                                addend=self._lin(self.linear2, ah))                  # :92, "+" fused into the epilogue
         degs = graph.in_degrees()                                                    # :94-102
         ah = _aggregate(graph, feat, 1.0 / degs.float())
         if self.use_pp:

@@ -323,7 +323,9 @@ class LnReluDropout(torch.autograd.Function):
         n, F = x.shape
         dx = torch.empty_like(x)
         dgamma, dbeta = torch.empty_like(gamma), torch.empty_like(beta)
-        key = (x.device, F)
+        # per (device, width, stream): ranks that live as threads of one process (tests, smoke) run their backward
+        # passes concurrently on their own streams and must not share the partial-sum scratch
+        key = (x.device, F, torch.cuda.current_stream(x.device).cuda_stream)
         ws = _LN_WS.get(key)
         if ws is None:
             ws = _LN_WS[key] = torch.empty(lib.bns_ln_bwd_workspace_bytes(F), dtype=torch.uint8, device=x.device)

@@ -125,8 +125,10 @@ int bns_split_tf32_f32(const float *x, int64_t n, float *hi, float *lo, void *st
  * (hi = tf32(x), lo = x - hi; hi*hi + hi*lo + lo*hi) done in shared memory inside the pipeline, so the result is
  * f32-accurate (~2^-21 relative per product) while every operand byte crosses HBM/L2 once (csrc/dense_tc.cuh).
  *
- * bns_dense_tn_3xtf32:  C[M, N] = A[M, K] * B[N, K]^T (+ bias[N]);  A, B, C row-major with leading dimensions
- *   lda, ldb, ldc (floats).  Forward: A = X, B = weight.  Input gradient: A = dY, B = weight^T (a contiguous copy).
+ * bns_dense_tn_3xtf32:  C[M, N] = A[M, K] * B[N, K]^T (+ bias[N]) (+ addend[M, N]);  A, B, C row-major with leading
+ *   dimensions lda, ldb, ldc (floats).  Forward: A = X, B = weight; `addend` fuses the "+" of
+ *   linear1(feat) + linear2(ah) (module/layer.py:92) into the epilogue.  Input gradient: A = dY, B = weight^T (a
+ *   contiguous copy).
  * bns_dense_nt_3xtf32:  C[N1, N2] = A[R, N1]^T * B[R, N2]  (contraction over the R rows, split across CTAs and
  *   combined in split order -- deterministic).  Weight gradient: A = dY, B = X.  ws: at least
  *   bns_dense_nt_workspace_bytes(R, N1, N2) bytes.
@@ -134,10 +136,16 @@ int bns_split_tf32_f32(const float *x, int64_t n, float *hi, float *lo, void *st
  * BNS_E_INVALID and the caller uses the library GEMM.
  * ----------------------------------------------------------------------------------------------*/
 int    bns_dense_tn_3xtf32(const float *A, int64_t lda, const float *B, int64_t ldb, const float *bias /*device [N] or NULL*/,
+                           const float *addend /*device [M, N] with leading dimension ldadd, or NULL*/, int64_t ldadd,
                            float *C, int64_t ldc, int64_t M, int64_t N, int64_t K, void *stream);
 size_t bns_dense_nt_workspace_bytes(int64_t R, int64_t N1, int64_t N2);
 int    bns_dense_nt_3xtf32(const float *A, int64_t lda, const float *B, int64_t ldb, float *C, int64_t ldc,
                            int64_t R, int64_t N1, int64_t N2, void *ws, size_t ws_bytes, void *stream);
+/* Bias gradient of the same layers (autograd's dY.sum(0)): out[c] = sum_r X[r, c], two deterministic passes.
+ * cols % 4 == 0, cols <= 1024, ld % 4 == 0, 16-byte aligned; ws >= bns_colsum_workspace_bytes(cols). */
+size_t bns_colsum_workspace_bytes(int64_t cols);
+int    bns_colsum_f32(const float *X, int64_t ld, int64_t rows, int64_t cols, float *out, void *ws, size_t ws_bytes,
+                      void *stream);
 
 /* ------------------------------------------------------------------------------------------------
  * K10 (GAT, module/model.py:96-132 via dgl.nn.GATConv): the attention gradient.  For every entry k of row r:

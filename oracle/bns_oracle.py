@@ -552,6 +552,8 @@ class _Exchange(torch.autograd.Function):
 
     @staticmethod
     def backward(ctx, grad):
+        if ctx.rk.trace is not None:
+            ctx.rk.trace[f"grad_u{ctx.layer}"] = grad.detach().clone()          # before the gradient exchange
         g = ctx.rk.exchange_backward(ctx.layer, grad)
         if ctx.rk.trace is not None:
             ctx.rk.trace[f"grad_h{ctx.layer}"] = g[:ctx.n_in].detach().clone()

@@ -33,6 +33,10 @@ CONFIGS = {
     "gcn": dict(shape="tiny", n_parts=2, model="gcn", n_layers=3, n_hidden=16, rate=0.5, epochs=3),
     "graphsage_bn": dict(shape="tiny", n_parts=2, model="graphsage", n_layers=3, n_hidden=16, rate=0.5, epochs=3,
                          norm="batch", graph_override={"train": 1.0}),   # whole_size == #nodes, as under --inductive
+    # 8 gloo processes, 7 peers per rank; "slim": keep every rank's index sets but only rank 0's tensors (the reduced
+    # gradients / weights are identical on all ranks) so that the fixture stays below 1 MB
+    "graphsage_small": dict(shape="small", n_parts=8, model="graphsage", n_layers=3, n_hidden=32, rate=0.5, epochs=2,
+                            slim=True),
 }
 
 
@@ -271,6 +275,16 @@ def worker(rank, world, cfg, port, out_dir):
 
     def select_node(boundary, send_size):
         sel = orig_select(boundary, send_size)
+        if cfg.get("philox_seed") is not None:
+            # draw the sets with the product's counter-based sampler instead of numpy (same distribution): pins the
+            # reference on exactly the index sets the CUDA path samples by itself
+            from oracle import philox
+            peers = [j for j in range(world) if j != rank]
+            drawn = philox.sample_boundary([boundary[j].numpy() for j in peers], [int(send_size[j]) for j in peers],
+                                           cfg["philox_seed"], len(rec["selected"]))
+            sel = [None] * world
+            for i, j in enumerate(peers):
+                sel[j] = torch.from_numpy(np.ascontiguousarray(drawn[i])).long()
         rec["selected"].append([None if s is None else s.clone() for s in sel])
         return sel
     ref_train.select_node = select_node
@@ -327,6 +341,10 @@ def main():
         with tempfile.TemporaryDirectory() as d:
             mp.spawn(worker, args=(cfg["n_parts"], cfg, 29600 + i, d), nprocs=cfg["n_parts"], join=True)
             ranks = [torch.load(os.path.join(d, f"rank{r}.pt")) for r in range(cfg["n_parts"])]
+        if cfg.get("slim"):
+            keep0 = ("selected", "boundary", "param_names", "logits", "layer_out", "params", "grads")
+            ranks = [{k: ([v[-1]] if k in ("logits", "layer_out") else v) for k, v in rk.items()
+                      if k in (keep0 if r == 0 else ("selected", "boundary", "param_names"))} for r, rk in enumerate(ranks)]
         out = os.path.join(HERE, f"ref_{name}_p{cfg['n_parts']}.pt")
         torch.save({"config": cfg, "ranks": ranks}, out)
         print("wrote", out, os.path.getsize(out), "bytes")

@@ -82,3 +82,26 @@ def test_rejects_unaligned_operands(dense):
         dense.tc_mm_tn(a, b)
     y = dense.linear(a, b)                          # linear() falls back to the library GEMM instead
     assert _rel(y, a.double() @ b.double().t()) < 1e-5
+
+
+def test_fused_addend_and_colsum(dense):
+    g = torch.Generator().manual_seed(7)
+    x = torch.randn(2500, 128, generator=g).cuda().requires_grad_()
+    w = (torch.randn(41, 128, generator=g) / 11).cuda().requires_grad_()
+    b = torch.randn(41, generator=g).cuda().requires_grad_()
+    add = torch.randn(2500, 44, generator=g).cuda().requires_grad_()      # padded width: fused into the epilogue
+    dy = torch.randn(2500, 41, generator=g).cuda()
+    y = dense.linear(x, w, b, addend=add)
+    y.backward(dy)
+    ref = x.detach().double() @ w.detach().double().t() + b.detach().double() + add.detach().double()[:, :41]
+    assert _rel(y.detach(), ref) < TOL
+    assert torch.equal(add.grad[:, :41], dy) and float(add.grad[:, 41:].abs().max()) == 0.0
+    assert _rel(b.grad, dy.double().sum(0)) < 1e-5
+    # unfusable width (40 columns for 41 outputs): same result through the plain add
+    add2 = torch.randn(2500, 41, generator=g).cuda()
+    y2 = dense.linear(x.detach(), w.detach(), b.detach(), addend=add2)
+    assert _rel(y2, x.detach().double() @ w.detach().double().t() + b.detach().double() + add2.double()) < TOL
+    big = torch.randn(100000, 256, generator=g).cuda()
+    s1, s2 = dense.colsum(big), dense.colsum(big)
+    assert torch.equal(s1, s2)
+    assert _rel(s1, big.double().sum(0)) < 1e-5

@@ -65,7 +65,7 @@ def _relerr(a, b):
     return ((a - b).norm() / b.norm().clamp(min=1e-30)).item()
 
 
-@pytest.mark.parametrize("F", [256, 128, 64, 4, 100, 602, 41, 1, 300])
+@pytest.mark.parametrize("F", [256, 128, 64, 4, 100, 602, 41, 1, 300, 44, 48, 40])
 def test_spmm_plain(built, F):
     from bns_gcn_b200 import ops
     dev = torch.device("cuda:0")
@@ -106,7 +106,7 @@ def test_spmm_roundtrip_csr_and_transpose(built):
     assert _relerr(dx, ref) < RTOL
 
 
-@pytest.mark.parametrize("F", [256, 128, 36, 7])
+@pytest.mark.parametrize("F", [256, 128, 36, 7, 44])
 def test_spmm_scales_maps_accumulate(built, F):
     """The per-epoch form: halo columns resolved through a slot map (-1 = unsampled), GCN-style col / row
     scales, accumulation on top of the inner-edge pass, and the row-mapped backward."""

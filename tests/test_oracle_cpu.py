@@ -134,3 +134,24 @@ def test_philox_sampler_properties():
     s2 = sample_boundary(b, k, seed=7, offset=4)
     assert not np.array_equal(s[0], s2[0])
     assert np.array_equal(s[0], sample_boundary(b, k, seed=7, offset=3)[0])
+
+
+def test_oracle_reproduces_reference_golden_eight_partitions():
+    """Same pin at 8 partitions (7 peers per rank, 6000-node graph, two epochs): the reference's own train.run on 8
+    gloo processes vs the oracle fed the index sets the reference drew."""
+    gold = torch.load(os.path.join(GOLD, "ref_graphsage_small_p8.pt"))
+    cfg, ranks = gold["config"], gold["ranks"]
+    sel = [[ranks[r]["selected"][e] for r in range(cfg["n_parts"])] for e in range(cfg["epochs"])]
+    out = _oracle_run(cfg, sel)
+    for r, rk in enumerate(out):
+        for j, b in enumerate(ranks[r]["boundary"]):
+            if b is not None:
+                assert torch.equal(rk.boundary[j], b)
+    g0 = ranks[0]
+    for i, lo in enumerate(g0["layer_out"][-1]):
+        assert _rel(out[0].trace[f"layer{i}"], lo) < 1e-5, i
+    assert _rel(out[0].trace["logits"], g0["logits"][-1]) < 1e-5
+    for r, rk in enumerate(out):
+        for p, gp, gg, nm in zip(rk.net.parameters(), g0["params"], g0["grads"], g0["param_names"]):
+            assert _rel(p.detach(), gp) < 1e-5, (r, nm)
+            assert _rel(p.grad, gg) < 1e-5, (r, nm)

@@ -34,6 +34,19 @@ def test_training_parity_small_both_transports(built, backend):
          chunk_nnz=64)
 
 
+@pytest.mark.parametrize("backend", ["nccl", "p2p"])
+def test_training_parity_eight_partitions(built, backend):
+    """8 partitions (the largest BASELINE rank count) as 8 in-process ranks: 7 peers per rank on both transports.
+
+    graph_seed=3 on purpose.  With graph_seed=0 this configuration has, in epoch 2, one LayerNorm output at -2.8e-6
+    (rank 0, row 64, feature 17): the f32 forward of the CUDA path lands on the other side of the ReLU kink, the
+    mask of that single entry flips and the gradients upstream differ by 1e-3 -- from the oracle AND from the
+    reference itself, which the oracle matches to 1e-7 there (tools/debug_p8.py localises it; the same inputs with
+    the sets the reference drew have no such entry and agree to 2e-5, see the golden test below)."""
+    _run(shape="small", n_parts=8, model="graphsage", sampling_rate=0.5, n_epochs=2, backend=backend, n_hidden=32,
+         graph_seed=3)
+
+
 def test_config0_two_partitions_rate1(built):
     """BASELINE.json configs[0]: 10K-node / 100K-edge random graph, 2 partitions, GraphSAGE, sampling rate 1.0."""
     _run(shape="synthetic-10k", n_parts=2, model="graphsage", sampling_rate=1.0, n_epochs=2, n_hidden=64)
@@ -98,6 +111,35 @@ def test_cuda_path_reproduces_reference_golden(built, name):
                 continue
             assert _relerr(p, gp) < TOL, (r, nm)
             assert _relerr(o["grads"][k], gg) < TOL, (r, nm)
+
+
+def test_cuda_path_reproduces_reference_golden_eight_partitions(built):
+    """The reference's own train.run on 8 gloo processes (tests/golden/make_golden.py, config graphsage_small):
+    6000-node graph, 7 peers per rank, sampling rate 0.5, two epochs.  Rank 0's layer outputs / logits and the
+    all-reduced gradients and updated weights (identical on every rank) are stored."""
+    import os
+    from tests.harness import make_args, run_product, _relerr
+    from bns_gcn_b200.data import make_graph, partition_graph
+    gold = torch.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "ref_graphsage_small_p8.pt"))
+    cfg, ranks = gold["config"], gold["ranks"]
+    fg = make_graph(cfg["shape"], seed=0)
+    parts = partition_graph(fg, cfg["n_parts"], "random", seed=0)
+    args = make_args(dataset=cfg["shape"], model=cfg["model"], sampling_rate=cfg["rate"], n_layers=cfg["n_layers"],
+                     n_hidden=cfg["n_hidden"], n_partitions=cfg["n_parts"])
+    sel = [[ranks[r]["selected"][e] for r in range(cfg["n_parts"])] for e in range(cfg["epochs"])]
+    out = run_product(parts, args, "cuda:0", cfg["epochs"], selected_per_epoch=sel)
+    for r, o in enumerate(out):
+        for j, b in enumerate(ranks[r]["boundary"]):
+            if b is not None:
+                assert torch.equal(o["boundary"][j], b)
+    g0, o = ranks[0], out[0]
+    for i, lo in enumerate(g0["layer_out"][-1]):
+        assert _relerr(o["layers"][f"layer{i}"], lo) < TOL, i
+    assert _relerr(o["logits"], g0["logits"][-1]) < TOL
+    for r, o in enumerate(out):
+        for k, (gp, gg) in enumerate(zip(g0["params"], g0["grads"])):
+            assert _relerr(o["params"][k], gp) < TOL, (r, g0["param_names"][k])
+            assert _relerr(o["grads"][k], gg) < TOL, (r, g0["param_names"][k])
 
 
 @pytest.mark.parametrize("model", ["graphsage", "gcn"])
