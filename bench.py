@@ -167,11 +167,15 @@ def run_ours(a):
         train.train_epoch(st, epoch)
         epoch += 1
 
+    from bns_gcn_b200.module import dense as dense_mod
+    dense_prof = []
+
     def timed(step_fn, n_steps, profile_spmm):
         """n_steps of step_fn between barriers; device time by CUDA events, max over ranks."""
         barrier()
         if profile_spmm:
             ops.PROFILE = []
+            dense_mod.PROFILE = []
         c0 = lib.bns_launch_count()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         barrier()
@@ -183,6 +187,9 @@ def run_ours(a):
         e1.record(torch.cuda.current_stream(dev))
         barrier()
         pr, ops.PROFILE = ops.PROFILE, None
+        if profile_spmm:
+            dense_prof[:] = dense_mod.PROFILE or []
+        dense_mod.PROFILE = None
         return max_over_ranks(e0.elapsed_time(e1)), lib.bns_launch_count() - c0, pr
 
     def eager_step():
@@ -224,6 +231,9 @@ def run_ours(a):
     spmm_ms = sum(s.elapsed_time(e) for s, e, *_ in prof)
     spmm_alg = sum(p[2] for p in prof)
     spmm_gather = sum(4 * p[3] + 4 * p[4] * p[5] for p in prof)        # p[5]: entries actually gathered (estimate)
+    gemm_ms = sum(s.elapsed_time(e) for s, e, *_ in dense_prof)
+    gemm_flops = sum(p[2] for p in dense_prof)
+    gemm_bytes = sum(p[3] for p in dense_prof)
     # ---------------- e2e: host-resident inputs, H2D + D2H inside the timed region -------------------
     feat_dev, lab_dev, mask_dev = st.feat, st.labels, st.train_mask
     feat_pin = feat_dev.cpu().pin_memory()
@@ -335,6 +345,26 @@ def run_ours(a):
                              "gather_GBs counts one 4F-byte row read per edge (what actually crosses L2->SM): that is the "
                              "binding resource on this degree-492 graph, see DESIGN.md"},
     }
+    if dense_prof and gemm_ms > 0:
+        # second kernel family of the step: the dense layers on tcgen05 (csrc/dense_tc.cuh).  3xTF32 issues three
+        # tensor-core products per useful f32 one; TF32 dense peak is taken as half the measured bf16 cuBLAS rate
+        # (MEASURED_PEAKS.json holds no TF32 figure; sustained, because the kernel runs inside a long step)
+        try:
+            with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+                pk = json.load(f)
+            tf32_peak, tf32_src = 0.5 * float(pk.get("bf16_tflops_sustained") or pk["bf16_tflops"]), "0.5 x measured sustained bf16 (MEASURED_PEAKS.json)"
+        except Exception:   # noqa: BLE001
+            tf32_peak, tf32_src = 0.5 * 1400.0, "0.5 x fallback sustained bf16 (B200_PROFILING.md)"
+        useful = gemm_flops / (gemm_ms * 1e-3) / 1e12
+        out["dense_roofline"] = {"bound": "tensor", "kernel": "gemm3x_kernel (bns_dense_tn_3xtf32 / bns_dense_nt_3xtf32)",
+                                 "achieved": 3.0 * useful, "peak": tf32_peak, "unit": "TFLOP/s", "frac": 3.0 * useful / tf32_peak,
+                                 "f32_equivalent_TFLOPs": useful, "peak_source": tf32_src, "launches_timed": len(dense_prof),
+                                 "share_of_step": gemm_ms / eager_ms if eager_ms else None,
+                                 "algorithmic_GBs": gemm_bytes / (gemm_ms * 1e-3) / 1e9,
+                                 "note": "achieved = 3 x useful f32 FLOPs (hi*hi + hi*lo + lo*hi) / CUDA-event time of the "
+                                         "launches in the eager pass; the kernel is shared-memory-bandwidth bound (ncu: tensor "
+                                         "pipe 46 %, LSU + tensor-core shared-memory wavefronts 53 % + 51 %), see "
+                                         "profiles/ncu_gemm3x_r01.md"}
     if world == 1 and not a.no_cpu_baseline:
         out["cpu_baseline"] = cpu_epochs_per_sec(a.shape, 1, steps=1, warmup=1)
     print(json.dumps(out))

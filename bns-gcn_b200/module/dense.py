@@ -28,6 +28,8 @@ import threading
 _GEMM_LOCK = threading.RLock()
 
 MODE = os.environ.get("BNS_DENSE", "tc")
+# bench.py sets this to a list to collect (start_event, end_event, useful_flops, algorithmic_bytes) per tcgen05 GEMM
+PROFILE = None
 MIN_K_3X = 512       # "auto": 3xTF32 only where the GEMM is big enough to repay the split pass (layer 0: K = 2 * n_feat)
 
 
@@ -175,12 +177,19 @@ def tc_mm_tn(a: torch.Tensor, b: torch.Tensor, bias=None, addend=None) -> torch.
     M, K = a.shape
     N = b.shape[0]
     out = torch.empty((M, N), dtype=torch.float32, device=a.device)
+    prof = PROFILE
+    if prof is not None:
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        ev0.record(torch.cuda.current_stream(a.device))
     with torch.cuda.device(a.device):
         check(lib.bns_dense_tn_3xtf32(a.data_ptr(), a.stride(0), b.data_ptr(), b.stride(0),
                                       None if bias is None else bias.data_ptr(),
                                       None if addend is None else addend.data_ptr(),
                                       0 if addend is None else addend.stride(0), out.data_ptr(), out.stride(0), M, N, K,
                                       torch.cuda.current_stream().cuda_stream), "bns_dense_tn_3xtf32")
+    if prof is not None:
+        ev1.record(torch.cuda.current_stream(a.device))
+        prof.append((ev0, ev1, 2.0 * M * N * K, 4.0 * (M * K + N * K + M * N * (2 if addend is not None else 1))))
     return out
 
 
@@ -208,10 +217,17 @@ def tc_mm_nt(a: torch.Tensor, b: torch.Tensor) -> torch.Tensor:
     out = torch.empty((N1, N2), dtype=torch.float32, device=a.device)
     nbytes = lib.bns_dense_nt_workspace_bytes(R, N1, N2)
     ws = torch.empty(max(nbytes, 16), dtype=torch.uint8, device=a.device)
+    prof = PROFILE
+    if prof is not None:
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        ev0.record(torch.cuda.current_stream(a.device))
     with torch.cuda.device(a.device):
         check(lib.bns_dense_nt_3xtf32(a.data_ptr(), a.stride(0), b.data_ptr(), b.stride(0), out.data_ptr(), out.stride(0),
                                       R, N1, N2, ws.data_ptr(), nbytes, torch.cuda.current_stream().cuda_stream),
               "bns_dense_nt_3xtf32")
+    if prof is not None:
+        ev1.record(torch.cuda.current_stream(a.device))
+        prof.append((ev0, ev1, 2.0 * R * N1 * N2, 4.0 * (R * N1 + R * N2 + N1 * N2)))
     return out
 
 
