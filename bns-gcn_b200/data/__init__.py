@@ -1,3 +1,4 @@
 from .synthetic import FullGraph, SHAPES, make_graph
 from .partition import (NID, GraphPartitionBook, LocalGraph, Partition, partition_graph, extract_partition,
                         assign_parts, relabel, induced_subgraph)
+from .store import graph_partition, load_partition, load_as_partition, save_partition, default_graph_name

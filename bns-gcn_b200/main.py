@@ -1,5 +1,6 @@
-"""Launcher with the reference's flags (main.py:10-64): generate (instead of download) the graph, partition it,
-start one process per partition / GPU and run ``train.run`` in each.
+"""Launcher with the reference's flags (main.py:10-64): generate (instead of download) the graph, partition it into
+the on-disk store (``data/store.py``: ``graph_partition`` unless ``--skip-partition``), start one process per
+partition / GPU; each loads its part (``load_partition``) and runs ``train.run``.
 
     python -m bns_gcn_b200.main --dataset reddit --n-partitions 4 --model graphsage --n-layers 3 --n-hidden 256 \
         --sampling-rate 0.1 --use-pp --partition-method random --n-epochs 50 --no-eval
@@ -14,7 +15,7 @@ import torch
 import torch.distributed as dist
 import torch.multiprocessing as mp
 
-from .data import make_graph, partition_graph
+from .data.store import default_graph_name, graph_partition, load_partition
 from .helper.parser import create_parser
 
 
@@ -27,15 +28,12 @@ def init_processes(rank, size, args):
     torch.cuda.set_device(local)
     dev = torch.device('cuda', local)
     dist.init_process_group('nccl', rank=rank, world_size=size, device_id=dev)
-    fg = make_graph(args.dataset, seed=0, device=dev)
-    part = partition_graph(fg, size, args.partition_method, seed=0, inductive=args.inductive, ranks=[rank],
-                           device=dev)[0]
-    del fg
-    args.n_feat, args.n_class, args.n_train = part.meta['n_feat'], part.meta['n_class'], part.meta['n_train']
-    if args.eval:
-        warnings.warn('evaluation / checkpointing (train.py:427-456) is not on the rebuilt path; running --no-eval')
-        args.eval = False
-    train.run(part.graph, part.node_dict, part.gpb, args, dev)
+    if getattr(args, '_partition_in_job', False):          # torchrun: nobody partitioned before the ranks started
+        if rank == 0:
+            graph_partition(args, device=dev)
+        dist.barrier()
+    g, node_dict, gpb = load_partition(args, rank)          # train.py:469 (fills args.n_feat / n_class / n_train)
+    train.run(g, node_dict, gpb, args, dev)
     dist.destroy_process_group()
 
 
@@ -48,8 +46,16 @@ def main(argv=None):
     if args.backend in ('gloo', 'mpi'):
         warnings.warn(f'--backend {args.backend}: host-staged transports are what this build replaces; using nccl')
         args.backend = 'nccl'
+    if args.graph_name == '':                               # main.py:17-23
+        args.graph_name = default_graph_name(args)
+    under_torchrun = 'RANK' in os.environ and 'WORLD_SIZE' in os.environ
+    if not args.skip_partition:                             # main.py:25-30
+        if under_torchrun:
+            args._partition_in_job = True
+        elif args.node_rank == 0:
+            graph_partition(args)
     print(args)
-    if 'RANK' in os.environ and 'WORLD_SIZE' in os.environ:
+    if under_torchrun:
         init_processes(int(os.environ['RANK']), int(os.environ['WORLD_SIZE']), args)
         return
     mp.set_start_method('spawn', force=True)

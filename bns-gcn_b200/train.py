@@ -422,11 +422,25 @@ class GraphedEpoch:
         return self.loss
 
 
-def run(graph, node_dict, gpb, args, device=None):
-    """train.py:300-456 without the evaluation / checkpoint branch (not on the throughput path, README.md:110)."""
+def run(graph, node_dict, gpb, args, device=None, full_graph=None):
+    """train.py:300-456.  With ``args.eval`` rank 0 also runs the evaluation / checkpoint branch (:308-321, 427-456)
+    through ``evaluate.Evaluator`` -- on the GPU with the same kernels, synchronously, instead of a CPU thread pool;
+    ``full_graph``: the un-partitioned ``FullGraph`` to evaluate on (default: regenerated from ``args.dataset``)."""
     rank, size = _rank_size()
     st = setup(graph, node_dict, gpb, args, device)
     dev = st.feat.device
+    evaluator = None
+    if getattr(args, 'eval', False) and rank == 0:
+        if args.model == 'gat':
+            import warnings
+            warnings.warn('--eval: the full-graph GAT forward (dgl.nn.GATConv on a homogeneous graph) is not rebuilt; '
+                          'training runs without the evaluation branch')
+        else:
+            from .data import make_graph
+            from .evaluate import Evaluator
+            fg = full_graph if full_graph is not None else make_graph(args.dataset, seed=getattr(args, 'graph_seed', 0),
+                                                                      device=dev)
+            evaluator = Evaluator(args, fg, dev)
     train_dur, comm_dur, reduce_dur = [], [], []
     torch.cuda.reset_peak_memory_stats(dev)
     print(f'Process {rank} start training')
@@ -445,6 +459,10 @@ def run(graph, node_dict, gpb, args, device=None):
                 rank, epoch, np.mean(train_dur) if train_dur else float('nan'),
                 np.mean(comm_dur) if comm_dur else float('nan'),
                 np.mean(reduce_dur) if reduce_dur else float('nan'), loss.item() / max(st.part_train, 1)))
+            if evaluator is not None:                                       # train.py:427-442
+                evaluator.after_epoch(st.model, epoch)
     print_memory("memory stats")
+    if evaluator is not None:                                               # train.py:446-456
+        evaluator.finish(st.model)
     return st, {"time": train_dur, "comm": comm_dur, "reduce": reduce_dur,
                 "loss": None if loss is None else loss.item()}

@@ -246,3 +246,38 @@ def test_gat_training_parity(built, kw):
     shape = kw.pop("shape", "tiny-ml")
     kw.setdefault("n_layers", 2)
     _run(shape=shape, model="gat", n_epochs=2, multilabel=(shape == "tiny-ml"), **kw)
+
+
+def test_run_with_eval_writes_checkpoints_and_results(built, tmp_path, monkeypatch):
+    """train.run with --eval (train.py:427-456): every log_every epochs rank 0 saves a checkpoint, evaluates on the full
+    graph with the same kernels and appends the result line; at the end the best model is saved and tested."""
+    import argparse
+    import os
+    from tests.harness import make_args
+    from bns_gcn_b200 import train
+    from bns_gcn_b200.data import make_graph, partition_graph
+    from bns_gcn_b200.evaluate import checkpoint_path, load_checkpoint, result_file_name
+    from bns_gcn_b200.helper.comm import run_threads
+    monkeypatch.chdir(tmp_path)
+    fg = make_graph("tiny", seed=0)
+    parts = partition_graph(fg, 2, "random", seed=0)
+    args = make_args(dataset="tiny", model="graphsage", sampling_rate=0.5, n_hidden=16, n_partitions=2, n_epochs=4,
+                     log_every=2, eval=True, graph_name="tiny-2-random-vol-trans")
+
+    def fn(comm, r):
+        a = argparse.Namespace(**vars(args))
+        p = parts[r]
+        a.n_feat, a.n_class, a.n_train = p.meta["n_feat"], p.meta["n_class"], p.meta["n_train"]
+        st, stats = train.run(p.graph, p.node_dict, p.gpb, a, "cuda:0", full_graph=fg)
+        return st.model if r == 0 else None
+
+    model = run_threads(2, fn, device="cuda:0")[0]
+    with open(result_file_name(args)) as f:
+        lines = f.read().strip().splitlines()
+    assert len(lines) == 2 and all("Validation Accuracy" in ln and "Test Accuracy" in ln for ln in lines)
+    for e in (1, 3):
+        assert os.path.exists(checkpoint_path(args, e))
+    assert os.path.exists(checkpoint_path(args))
+    load_checkpoint(model, checkpoint_path(args, 3))          # the last periodic checkpoint is the final weights
+    sd = torch.load(checkpoint_path(args, 3))
+    assert list(sd.keys()) == [k for k, _ in model.named_parameters()]
