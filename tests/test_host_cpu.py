@@ -79,7 +79,7 @@ def test_partition_contract(method):
     assert n_edges == fg.n_edges
 
 
-def _gloo_worker(rank, world, port, out_dir):
+def _gloo_worker(rank, world, port, out_dir, use_store=False):
     os.environ["MASTER_ADDR"], os.environ["MASTER_PORT"] = "127.0.0.1", str(port)
     sys.path.insert(0, ROOT)
     import torch.distributed as dist
@@ -90,7 +90,19 @@ def _gloo_worker(rank, world, port, out_dir):
     from bns_gcn_b200.helper import context as ctx
     from bns_gcn_b200.helper.utils import TransferTag, data_transfer, get_boundary
     fg = make_graph("tiny", seed=0, device=torch.device("cpu"))
-    p = partition_graph(fg, world, "random", seed=0, device=torch.device("cpu"))[rank]
+    if use_store:
+        # main.py's flow under torchrun: rank 0 writes the partition store, everybody loads its own part from disk
+        import argparse
+        from bns_gcn_b200.data import graph_partition, load_as_partition
+        a = argparse.Namespace(dataset="tiny", n_partitions=world, partition_method="random", partition_obj="vol",
+                               inductive=False, part_path=os.path.join(out_dir, "partition"), graph_name="")
+        if rank == 0:
+            graph_partition(a, fg=fg, device=torch.device("cpu"))
+        dist.barrier()
+        p = load_as_partition(a, rank)
+        assert (a.n_feat, a.n_class, a.n_train) == (fg.n_feat, fg.n_class, int(fg.train_mask.sum()))
+    else:
+        p = partition_graph(fg, world, "random", seed=0, device=torch.device("cpu"))[rank]
     assert ctx.comm().kind == "dist" and ctx.comm().backend == "gloo"
     boundary = get_boundary(p.node_dict, p.gpb)
     pos = train.get_pos(p.node_dict, p.gpb)
@@ -107,9 +119,10 @@ def _gloo_worker(rank, world, port, out_dir):
     dist.destroy_process_group()
 
 
-def test_exchange_metadata_gloo_world2(tmp_path):
+@pytest.mark.parametrize("use_store", [False, True])
+def test_exchange_metadata_gloo_world2(tmp_path, use_store):
     import torch.multiprocessing as mp
-    mp.spawn(_gloo_worker, args=(2, 29650, str(tmp_path)), nprocs=2, join=True)
+    mp.spawn(_gloo_worker, args=(2, 29650 + int(use_store), str(tmp_path), use_store), nprocs=2, join=True)
     r = [torch.load(os.path.join(tmp_path, f"r{i}.pt")) for i in range(2)]
     gold = torch.load(os.path.join(ROOT, "tests", "golden", "ref_graphsage_p2.pt"))["ranks"]
     for me, other in ((0, 1), (1, 0)):
