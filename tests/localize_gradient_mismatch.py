@@ -3,7 +3,7 @@
 ``OracleRank.trace`` on the oracle side.  The default arguments reproduce the ReLU-kink case documented in
 tests/test_parity_gpu.py::test_training_parity_eight_partitions (graph_seed 0: rank 0, row 64).
 
-    python tools/debug_p8.py [--parts 8] [--graph-seed 0] [--rate 0.5] [--hidden 32] [--epochs 2]
+    python tests/localize_gradient_mismatch.py [--parts 8] [--graph-seed 0] [--rate 0.5] [--hidden 32] [--epochs 2]
 """
 import argparse
 import os

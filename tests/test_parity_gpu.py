@@ -41,7 +41,7 @@ def test_training_parity_eight_partitions(built, backend):
     graph_seed=3 on purpose.  With graph_seed=0 this configuration has, in epoch 2, one LayerNorm output at -2.8e-6
     (rank 0, row 64, feature 17): the f32 forward of the CUDA path lands on the other side of the ReLU kink, the
     mask of that single entry flips and the gradients upstream differ by 1e-3 -- from the oracle AND from the
-    reference itself, which the oracle matches to 1e-7 there (tools/debug_p8.py localises it; the same inputs with
+    reference itself, which the oracle matches to 1e-7 there (tests/localize_gradient_mismatch.py localises it; the same inputs with
     the sets the reference drew have no such entry and agree to 2e-5, see the golden test below)."""
     _run(shape="small", n_parts=8, model="graphsage", sampling_rate=0.5, n_epochs=2, backend=backend, n_hidden=32,
          graph_seed=3)
