@@ -325,6 +325,8 @@ class OracleRank:
             self.in_norm = inp.in_deg                                                        # train.py:380
         self.selected: List[Optional[torch.Tensor]] = [None] * self.size
         self.trace: Dict[str, torch.Tensor] = {}
+        self.relu_masks: Optional[Dict[int, torch.Tensor]] = None
+        self.kink = {"flips": 0, "max_abs_z": 0.0}
         self.comm_bytes = 0
 
     # ---- helper/utils.py:150-184 ---------------------------------------------------------
@@ -498,9 +500,16 @@ class OracleRank:
 
     # ---- train.py:385-425 ---------------------------------------------------------------------
     def epoch(self, selected: Optional[list] = None, rng: Optional[np.random.RandomState] = None,
-              step: bool = True, trace: bool = False) -> float:
-        """One training epoch; returns the local (sum-reduced) loss.  ``selected`` injects the sampled sets."""
+              step: bool = True, trace: bool = False, relu_masks: Optional[Dict[int, torch.Tensor]] = None) -> float:
+        """One training epoch; returns the local (sum-reduced) loss.  ``selected`` injects the sampled sets.
+
+        ``relu_masks`` ({norm index i: bool [n_in, F]}): the active set another implementation of the SAME forward took
+        at the ReLU after norm i.  Gradient parity is only defined on a common active set: where a pre-activation sits
+        within f32 rounding of zero the two forwards may land on different sides of the kink (tests/harness.py).  The
+        given mask then replaces ``z > 0``; ``self.kink`` counts the entries where it differed and how far from zero
+        the furthest of them was (a large distance means a real forward disagreement, not a kink)."""
         self.trace = {} if trace else None
+        self.relu_masks = relu_masks
         if selected is None:
             selected = self.select_node(rng if rng is not None else np.random)
         self.selected = selected
@@ -720,8 +729,22 @@ class GNNRef(nn.Module):
             if i < self.n_layers - 1:
                 if self.use_norm:
                     h = self.norm[i](h)
-                h = F.relu(h)
+                h = _relu_on_active_set(h, rk, i)
         return h
+
+
+def _relu_on_active_set(z, rk, i):
+    """``F.relu(z)``, or ``z * mask`` when the caller prescribed the active set (``OracleRank.epoch(relu_masks=...)``)."""
+    if rk is not None and rk.trace is not None:
+        rk.trace[f"z{i}"] = z.detach().clone()
+    m = rk.relu_masks.get(i) if (rk is not None and rk.relu_masks) else None
+    if m is None:
+        return F.relu(z)
+    d = (z.detach() > 0) != m
+    if bool(d.any()):
+        rk.kink["flips"] += int(d.sum())
+        rk.kink["max_abs_z"] = max(rk.kink["max_abs_z"], float(z.detach()[d].abs().max()))
+    return z * m.to(z.dtype)
 
 
 class GATConvRef(nn.Module):

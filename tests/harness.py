@@ -24,8 +24,10 @@ def _relerr(a: torch.Tensor, b: torch.Tensor) -> float:
     return ((a - b).norm() / b.norm().clamp(min=1e-30)).item()
 
 
-def run_product(parts, args, device, n_epochs, selected_per_epoch=None, capture=True):
-    """Train ``n_epochs`` on the CUDA path with one in-process rank per partition.  Returns per-rank dicts."""
+def run_product(parts, args, device, n_epochs, selected_per_epoch=None, capture=True, capture_masks=False):
+    """Train ``n_epochs`` on the CUDA path with one in-process rank per partition.  Returns per-rank dicts.
+    ``capture_masks``: also record, per epoch, the active set of every inter-layer ReLU (``{norm index: bool [n_in, F]}``,
+    read off the input of the following layer: with dropout 0 it is positive exactly where the pre-activation was)."""
     from bns_gcn_b200 import train
     from bns_gcn_b200.helper.comm import run_threads
 
@@ -41,7 +43,17 @@ def run_product(parts, args, device, n_epochs, selected_per_epoch=None, capture=
                 hooks.append(layer.register_forward_hook(
                     lambda m, inp, out, i=i: outs.__setitem__(
                         f"layer{i}", (out.mean(1) if out.dim() == 3 else out).detach().clone())))
-        losses, sel_log, hops_log = [], [], []
+        losses, sel_log, hops_log, mask_log, cur_masks = [], [], [], [], {}
+        if capture_masks:
+            n_in = p.graph.n_in
+            for i, layer in enumerate(st.model.layers):
+                if i == 0:
+                    continue
+
+                def pre(m, inp, i=i):
+                    h = inp[1] if len(inp) > 1 else inp[0]
+                    cur_masks[i - 1] = (h[:n_in] > 0).detach().cpu()
+                hooks.append(layer.register_forward_pre_hook(pre))
         for e in range(n_epochs):
             inj = None
             if selected_per_epoch is not None:
@@ -50,10 +62,12 @@ def run_product(parts, args, device, n_epochs, selected_per_epoch=None, capture=
             losses.append(loss.item())
             sel_log.append([None if s is None else s.cpu().clone() for s in st.selected])
             hops_log.append([None if s is None else s.cpu().clone() for s in st.one_hops])
+            mask_log.append(dict(cur_masks))
+            cur_masks.clear()
         torch.cuda.synchronize()
         for h in hooks:
             h.remove()
-        return {"loss": losses, "selected": sel_log, "one_hops": hops_log,
+        return {"loss": losses, "selected": sel_log, "one_hops": hops_log, "relu_masks": mask_log,
                 "layers": {k: v.cpu() for k, v in outs.items()},
                 "logits": st.last_logits.detach().cpu(),
                 "grads": [p_.grad.detach().cpu().clone() for p_ in st.model.parameters()],
@@ -64,8 +78,9 @@ def run_product(parts, args, device, n_epochs, selected_per_epoch=None, capture=
     return run_threads(len(parts), fn, device=device)
 
 
-def run_oracle(parts, args, n_epochs, selected_per_epoch):
-    """The same run on the CPU oracle (P threads, injected index sets)."""
+def run_oracle(parts, args, n_epochs, selected_per_epoch, relu_masks_per_epoch=None):
+    """The same run on the CPU oracle (P threads, injected index sets).  ``relu_masks_per_epoch[e][r]``: the active
+    sets the CUDA run took (``OracleRank.epoch(relu_masks=...)``)."""
     from oracle import bns_oracle as O
 
     def fn(comm, r):
@@ -78,8 +93,10 @@ def run_oracle(parts, args, n_epochs, selected_per_epoch):
         losses = []
         for e in range(n_epochs):
             sel = None if selected_per_epoch is None else selected_per_epoch[e][r]
-            losses.append(rk.epoch(selected=sel, trace=True))
-        return {"loss": losses, "layers": {k: v for k, v in rk.trace.items() if k.startswith("layer")},
+            rm = None if relu_masks_per_epoch is None else relu_masks_per_epoch[e][r]
+            losses.append(rk.epoch(selected=sel, trace=True, relu_masks=rm))
+        return {"loss": losses, "kink": dict(rk.kink),
+                "layers": {k: v for k, v in rk.trace.items() if k.startswith("layer")},
                 "logits": rk.trace["logits"], "grads": [q.grad.detach().clone() for q in rk.net.parameters()],
                 "params": [q.detach().clone() for q in rk.net.parameters()],
                 "boundary": rk.boundary, "send_size": rk.send_size, "one_hops": rk.one_hops, "feat0": rk.feat}
@@ -104,22 +121,23 @@ def run_parity_case(shape="tiny", n_parts=2, model="graphsage", sampling_rate=0.
     prod = run_product(parts, args, device, n_epochs)
     selected = [[prod[r]["selected"][e] for r in range(n_parts)] for e in range(n_epochs)]
     orc = run_oracle(parts, args, n_epochs, selected if n_parts > 1 else None)
-    worst, detail = 0.0, {}
-    for r in range(n_parts):
-        for k in list(prod[r]["layers"].keys()) + ["logits", "feat0"]:
-            a = prod[r]["layers"][k] if k.startswith("layer") else prod[r][k]
-            b = orc[r]["layers"][k] if k.startswith("layer") else orc[r][k]
-            e = _relerr(a, b)
-            detail[f"r{r}/{k}"] = e
-            worst = max(worst, e)
-        for i, (a, b) in enumerate(zip(prod[r]["grads"], orc[r]["grads"])):
-            e = _relerr(a, b)
-            detail[f"r{r}/grad{i}"] = e
-            worst = max(worst, e)
-        for i, (a, b) in enumerate(zip(prod[r]["params"], orc[r]["params"])):
-            e = _relerr(a, b)
-            detail[f"r{r}/param{i}"] = e
-            worst = max(worst, e)
+    worst, detail = _compare(prod, orc, n_parts)
+    # ReLU kinks.  Where a pre-activation lies within f32 rounding of zero the CUDA forward and the CPU forward can land
+    # on different sides, the masks of those entries differ and the gradients upstream differ by ~1e-3 although both
+    # are right (DESIGN.md "ReLU kinks").  Gradient parity is defined on a common active set: on a mismatch, re-run the
+    # CUDA path recording its active sets and the oracle on exactly those; accept the comparison only if every entry
+    # that had to be switched sat within KINK_MARGIN of zero in the oracle's own forward.
+    kink = None
+    if worst >= KINK_TRIGGER and model in ("graphsage", "gcn"):
+        sel_in = selected if n_parts > 1 else None
+        prod2 = run_product(parts, args, device, n_epochs, selected_per_epoch=sel_in, capture_masks=True)
+        masks = [[prod2[r]["relu_masks"][e] for r in range(n_parts)] for e in range(n_epochs)]
+        orc2 = run_oracle(parts, args, n_epochs, sel_in, relu_masks_per_epoch=masks)
+        kink = {"flips": sum(o["kink"]["flips"] for o in orc2), "max_abs_z": max(o["kink"]["max_abs_z"] for o in orc2),
+                "max_rel_err_before": worst}
+        if kink["flips"] > 0 and kink["max_abs_z"] < KINK_MARGIN:
+            prod, orc = prod2, orc2
+            worst, detail = _compare(prod, orc, n_parts)
     # exactness of the integer side
     index_ok = True
     for r in range(n_parts):
@@ -141,4 +159,28 @@ def run_parity_case(shape="tiny", n_parts=2, model="graphsage", sampling_rate=0.
     loss_p = [sum(prod[r]["loss"][e] for r in range(n_parts)) for e in range(n_epochs)]
     loss_o = [sum(orc[r]["loss"][e] for r in range(n_parts)) for e in range(n_epochs)]
     return {"max_rel_err": worst, "detail": detail, "index_sets_equal": bool(index_ok), "loss": loss_p,
-            "loss_oracle": loss_o}
+            "loss_oracle": loss_o, "kink": kink}
+
+
+KINK_TRIGGER = 1e-4      # the parity bar: a result below it needs no second look
+KINK_MARGIN = 1e-4       # |z| (LayerNorm / BatchNorm output, O(1) scale) below which a sign disagreement is a kink
+
+
+def _compare(prod, orc, n_parts):
+    worst, detail = 0.0, {}
+    for r in range(n_parts):
+        for k in list(prod[r]["layers"].keys()) + ["logits", "feat0"]:
+            a = prod[r]["layers"][k] if k.startswith("layer") else prod[r][k]
+            b = orc[r]["layers"][k] if k.startswith("layer") else orc[r][k]
+            e = _relerr(a, b)
+            detail[f"r{r}/{k}"] = e
+            worst = max(worst, e)
+        for i, (a, b) in enumerate(zip(prod[r]["grads"], orc[r]["grads"])):
+            e = _relerr(a, b)
+            detail[f"r{r}/grad{i}"] = e
+            worst = max(worst, e)
+        for i, (a, b) in enumerate(zip(prod[r]["params"], orc[r]["params"])):
+            e = _relerr(a, b)
+            detail[f"r{r}/param{i}"] = e
+            worst = max(worst, e)
+    return worst, detail

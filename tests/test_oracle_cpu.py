@@ -155,3 +155,113 @@ def test_oracle_reproduces_reference_golden_eight_partitions():
         for p, gp, gg, nm in zip(rk.net.parameters(), g0["params"], g0["grads"], g0["param_names"]):
             assert _rel(p.detach(), gp) < 1e-5, (r, nm)
             assert _rel(p.grad, gg) < 1e-5, (r, nm)
+
+
+def test_oracle_active_set_override():
+    """``OracleRank.epoch(relu_masks=...)`` (the kink-aware leg of tests/harness.py): prescribing the oracle's OWN
+    active sets changes nothing; flipping the entry closest to the kink is counted, its distance from zero reported,
+    and moves the gradients -- which is exactly the disagreement a forward 1e-6 away can produce."""
+    import bns_gcn_b200  # noqa: F401
+    from bns_gcn_b200.data import make_graph, partition_graph
+    from oracle import bns_oracle as O
+    fg = make_graph("tiny", seed=0, device=torch.device("cpu"))
+    parts = partition_graph(fg, 2, "random", seed=0, device=torch.device("cpu"))
+    E = 2
+
+    def run(masks_per_epoch):
+        def fn(comm, r):
+            rk = O.OracleRank(O.RankInput.from_partition(parts[r]), comm, model="graphsage", n_layers=3, n_hidden=16,
+                              sampling_rate=0.5, dropout=0.0, seed=0)
+            zs = []
+            for e in range(E):
+                rm = None if masks_per_epoch is None else masks_per_epoch[e][r]
+                rk.epoch(rng=np.random.RandomState(100 * e + r), trace=True, relu_masks=rm)
+                zs.append({i: rk.trace[f"z{i}"] for i in range(2)})
+            return zs, [p.grad.clone() for p in rk.net.parameters()], dict(rk.kink)
+        return O.run_threads(2, fn)
+
+    base = run(None)
+    own = [[{i: base[r][0][e][i] > 0 for i in range(2)} for r in range(2)] for e in range(E)]
+    same = run(own)
+    assert all(s[2]["flips"] == 0 for s in same)
+    for a, b in zip(base[0][1], same[0][1]):
+        assert _rel(a, b) < 1e-6
+    # flip the entry of epoch 0 / rank 0 / norm 0 that is closest to zero
+    z = base[0][0][0][0]
+    k = int(z.abs().argmin())
+    flipped = [[{i: m.clone() for i, m in own[e][r].items()} for r in range(2)] for e in range(E)]
+    flipped[0][0][0].view(-1)[k] = ~flipped[0][0][0].view(-1)[k]
+    # later epochs: keep the oracle's own (then current) sign except that the prescription must stay self-consistent,
+    # so only epoch 0 is prescribed
+    flipped = [flipped[0]] + [[None, None] for _ in range(E - 1)]
+    moved = run(flipped)
+    assert moved[0][2]["flips"] == 1 and moved[1][2]["flips"] == 0
+    assert abs(moved[0][2]["max_abs_z"] - float(z.abs().min())) < 1e-12
+    assert max(_rel(a, b) for a, b in zip(moved[0][1], base[0][1])) > 1e-7          # the kink matters
+
+
+def test_harness_kink_retry_logic_with_a_stub_product(monkeypatch):
+    """tests/harness.run_parity_case's kink-aware leg, exercised on the CPU: the CUDA run is replaced by a stub that
+    computes the oracle's math but takes the OTHER side of the kink at the pre-activation closest to zero (what a
+    forward that differs in the last bits does).  The first comparison must fail, the retry on the stub's active sets
+    must bring the error back under the bar, and the report must say one entry was switched, at that distance."""
+    import bns_gcn_b200  # noqa: F401
+    from oracle import bns_oracle as O, philox
+    from tests import harness as H
+
+    state = {}
+
+    def stub_run_product(parts, args, device, n_epochs, selected_per_epoch=None, capture=True, capture_masks=False):
+        P = len(parts)
+
+        def once(masks_per_epoch):
+            def fn(comm, r):
+                rk = O.OracleRank(O.RankInput.from_partition(parts[r]), comm, model=args.model, n_layers=args.n_layers,
+                                  n_hidden=args.n_hidden, sampling_rate=args.sampling_rate, dropout=0.0, seed=args.seed)
+                peers = [j for j in range(P) if j != r]
+                losses, sel_log, hop_log, z_log = [], [], [], []
+                for e in range(n_epochs):
+                    drawn = philox.sample_boundary([rk.boundary[j].numpy() for j in peers],
+                                                   [rk.send_size[j] for j in peers], args.sampler_seed, e)
+                    sel = [None] * P
+                    for i, j in enumerate(peers):
+                        sel[j] = torch.from_numpy(np.ascontiguousarray(drawn[i])).long()
+                    rm = None if masks_per_epoch is None else masks_per_epoch[e][r]
+                    losses.append(rk.epoch(selected=sel, trace=True, relu_masks=rm))
+                    sel_log.append(sel)
+                    hop_log.append(list(rk.one_hops))
+                    z_log.append({i: rk.trace[f"z{i}"] for i in range(args.n_layers - 1)})
+                return {"loss": losses, "selected": sel_log, "one_hops": hop_log, "z": z_log,
+                        "layers": {k: v for k, v in rk.trace.items() if k.startswith("layer")},
+                        "logits": rk.trace["logits"], "grads": [q.grad.detach().clone() for q in rk.net.parameters()],
+                        "params": [q.detach().clone() for q in rk.net.parameters()], "boundary": rk.boundary,
+                        "send_size": rk.send_size, "feat0": rk.feat}
+            return O.run_threads(P, fn)
+
+        plain = once(None)
+        z = plain[0]["z"][0][0]
+        k = int(z.abs().argmin())
+        state["abs_z"] = float(z.abs().min())
+        first = [{i: (plain[r]["z"][0][i] > 0) for i in plain[r]["z"][0]} for r in range(P)]
+        first[0][0] = first[0][0].clone()
+        first[0][0].view(-1)[k] = ~first[0][0].view(-1)[k]
+        out = once([first] + [[None] * P for _ in range(n_epochs - 1)])
+        for r in range(P):       # the active sets this "implementation" actually took
+            out[r]["relu_masks"] = [first[r]] + [{i: out[r]["z"][e][i] > 0 for i in out[r]["z"][e]}
+                                                 for e in range(1, n_epochs)]
+        state["calls"] = state.get("calls", 0) + 1
+        return out
+
+    monkeypatch.setattr(H, "run_product", stub_run_product)
+    monkeypatch.setattr(H, "KINK_MARGIN", 1e-3)      # the 600-node graph's closest entry sits at ~1e-4, not ~1e-6
+    res = H.run_parity_case(shape="tiny", n_parts=2, model="graphsage", sampling_rate=0.5, n_epochs=2, device="cpu")
+    assert state["calls"] == 2, "the mismatch must trigger the second, mask-recording run"
+    assert res["kink"] is not None and res["kink"]["flips"] == 1
+    assert abs(res["kink"]["max_abs_z"] - state["abs_z"]) < 1e-9 and res["kink"]["max_abs_z"] < H.KINK_MARGIN
+    assert res["kink"]["max_rel_err_before"] >= H.KINK_TRIGGER > res["max_rel_err"]
+    assert res["index_sets_equal"]
+    # a sign disagreement FAR from zero is a real forward error: with the margin below this entry's distance the retry
+    # must not paper over it
+    monkeypatch.setattr(H, "KINK_MARGIN", 1e-5)
+    res = H.run_parity_case(shape="tiny", n_parts=2, model="graphsage", sampling_rate=0.5, n_epochs=2, device="cpu")
+    assert res["kink"]["flips"] == 1 and res["max_rel_err"] >= H.KINK_TRIGGER

@@ -113,6 +113,21 @@ def test_cuda_path_reproduces_reference_golden(built, name):
             assert _relerr(o["grads"][k], gg) < TOL, (r, nm)
 
 
+@pytest.mark.xfail(strict=False, reason="kink-aware retry: harness logic is CPU-tested with a stub product "
+                                       "(tests/test_oracle_cpu.py); its CUDA-side mask capture was written after the "
+                                       "round's GPU budget ended and has not run on hardware yet")
+def test_training_parity_through_a_relu_kink(built):
+    """The graph_seed=0 twin of the test above: epoch 2 has one LayerNorm output at -2.8e-6 on rank 0 and the CUDA
+    forward takes the other side of the ReLU kink.  run_parity_case must notice the mismatch, re-run both sides on the
+    CUDA path's active sets, find exactly that kind of entry (|z| < 1e-4) and then agree within the bar."""
+    from tests.harness import run_parity_case
+    res = run_parity_case(shape="small", n_parts=8, model="graphsage", sampling_rate=0.5, n_epochs=2, n_hidden=32,
+                          graph_seed=0)
+    assert res["kink"] is not None and res["kink"]["flips"] >= 1 and res["kink"]["max_abs_z"] < 1e-4, res["kink"]
+    assert res["max_rel_err"] < TOL, {k: v for k, v in res["detail"].items() if v >= TOL}
+    assert res["index_sets_equal"]
+
+
 def test_cuda_path_reproduces_reference_golden_eight_partitions(built):
     """The reference's own train.run on 8 gloo processes (tests/golden/make_golden.py, config graphsage_small):
     6000-node graph, 7 peers per rank, sampling rate 0.5, two epochs.  Rank 0's layer outputs / logits and the
