@@ -37,6 +37,11 @@ CONFIGS = {
     # gradients / weights are identical on all ranks) so that the fixture stays below 1 MB
     "graphsage_small": dict(shape="small", n_parts=8, model="graphsage", n_layers=3, n_hidden=32, rate=0.5, epochs=2,
                             slim=True),
+    # GCN on the 6000-node graph over 4 ranks at a low sampling rate; GraphSAGE with a trailing nn.Linear layer
+    # (--n-linear 1) on the inductive (train-nodes-only) graph over 3 ranks
+    "gcn_small": dict(shape="small", n_parts=4, model="gcn", n_layers=3, n_hidden=32, rate=0.1, epochs=2, slim=True),
+    "graphsage_nlin_induc": dict(shape="tiny", n_parts=3, model="graphsage", n_layers=3, n_hidden=16, rate=0.5, epochs=3,
+                                 n_linear=1, inductive=True, slim=True),
 }
 
 
@@ -252,7 +257,8 @@ def worker(rank, world, cfg, port, out_dir):
     import argparse
 
     fg = make_graph(cfg["shape"], seed=0, device=torch.device("cpu"), **cfg.get("graph_override", {}))
-    part = partition_graph(fg, world, "random", seed=0, device=torch.device("cpu"))[rank]
+    part = partition_graph(fg, world, "random", seed=0, inductive=cfg.get("inductive", False),
+                           device=torch.device("cpu"))[rank]
     lg = part.graph
     v = torch.repeat_interleave(torch.arange(lg.n_in), lg.indptr[1:] - lg.indptr[:-1])
     subg = FakeGraph(lg.indices.clone(), v, lg.n_in + lg.n_halo)
@@ -264,8 +270,8 @@ def worker(rank, world, cfg, port, out_dir):
 
     args = argparse.Namespace(dataset="synthetic", model=cfg["model"], dropout=0.0, lr=1e-2, sampling_rate=cfg["rate"],
                               heads=1, n_epochs=cfg["epochs"], n_partitions=world, n_hidden=cfg["n_hidden"],
-                              n_layers=cfg["n_layers"], log_every=1, weight_decay=0.0, norm=cfg.get("norm", "layer"), n_linear=0,
-                              use_pp=True, inductive=False, seed=0, backend="gloo", eval=False,
+                              n_layers=cfg["n_layers"], log_every=1, weight_decay=0.0, norm=cfg.get("norm", "layer"),
+                              n_linear=cfg.get("n_linear", 0), use_pp=True, inductive=cfg.get("inductive", False), seed=0, backend="gloo", eval=False,
                               graph_name="golden", n_feat=part.meta["n_feat"], n_class=part.meta["n_class"],
                               n_train=part.meta["n_train"])
     rec = {"selected": [], "logits": [], "layer_out": [], "loss": []}
@@ -337,7 +343,10 @@ def worker(rank, world, cfg, port, out_dir):
 def main():
     import tempfile
     import torch.multiprocessing as mp
+    only = set(sys.argv[1:])                      # optional: names of the configs to (re)generate
     for i, (name, cfg) in enumerate(CONFIGS.items()):
+        if only and name not in only:
+            continue
         with tempfile.TemporaryDirectory() as d:
             mp.spawn(worker, args=(cfg["n_parts"], cfg, 29600 + i, d), nprocs=cfg["n_parts"], join=True)
             ranks = [torch.load(os.path.join(d, f"rank{r}.pt")) for r in range(cfg["n_parts"])]

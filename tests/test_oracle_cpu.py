@@ -20,12 +20,13 @@ def _oracle_run(cfg, selected_per_epoch):
     from bns_gcn_b200.data import make_graph, partition_graph
     from oracle import bns_oracle as O
     fg = make_graph(cfg["shape"], seed=0, device=torch.device("cpu"), **cfg.get("graph_override", {}))
-    parts = partition_graph(fg, cfg["n_parts"], "random", seed=0, device=torch.device("cpu"))
+    parts = partition_graph(fg, cfg["n_parts"], "random", seed=0, inductive=cfg.get("inductive", False),
+                            device=torch.device("cpu"))
 
     def fn(comm, r):
         rk = O.OracleRank(O.RankInput.from_partition(parts[r]), comm, model=cfg["model"], n_layers=cfg["n_layers"],
                           n_hidden=cfg["n_hidden"], sampling_rate=cfg["rate"], dropout=0.0, seed=0,
-                          norm=cfg.get("norm", "layer"))
+                          norm=cfg.get("norm", "layer"), n_linear=cfg.get("n_linear", 0))
         for e in range(cfg["epochs"]):
             rk.epoch(selected=selected_per_epoch[e][r], trace=True)
         return rk
@@ -136,10 +137,13 @@ def test_philox_sampler_properties():
     assert np.array_equal(s[0], sample_boundary(b, k, seed=7, offset=3)[0])
 
 
-def test_oracle_reproduces_reference_golden_eight_partitions():
-    """Same pin at 8 partitions (7 peers per rank, 6000-node graph, two epochs): the reference's own train.run on 8
-    gloo processes vs the oracle fed the index sets the reference drew."""
-    gold = torch.load(os.path.join(GOLD, "ref_graphsage_small_p8.pt"))
+@pytest.mark.parametrize("fixture", ["graphsage_small_p8", "gcn_small_p4", "graphsage_nlin_induc_p3"])
+def test_oracle_reproduces_reference_golden_slim(fixture):
+    """The same pin on wider configurations (slim fixtures: every rank's index sets, rank 0's tensors): 8 partitions
+    (7 peers per rank, 6000-node graph); GCN over 4 ranks at sampling rate 0.1; GraphSAGE with a trailing nn.Linear
+    (--n-linear 1) on the inductive graph over 3 ranks.  The reference's own train.run on gloo vs the oracle fed the
+    index sets the reference drew."""
+    gold = torch.load(os.path.join(GOLD, f"ref_{fixture}.pt"))
     cfg, ranks = gold["config"], gold["ranks"]
     sel = [[ranks[r]["selected"][e] for r in range(cfg["n_parts"])] for e in range(cfg["epochs"])]
     out = _oracle_run(cfg, sel)
