@@ -138,3 +138,20 @@ def test_exchange_metadata_gloo_world2(tmp_path, use_store):
         # merged out-degree vector == full-graph out-degree of [inner | halo]
         # (node ids were relabelled by the partitioner, so compare through the relabelled full graph)
         assert a["out_deg"].numel() == a["nid"].numel()
+
+
+def test_dense_split_k_plan_is_sane_without_a_gpu(built):
+    """``bns_dense_nt_workspace_bytes`` is pure host arithmetic (SM count falls back to 148 without a device): the
+    weight-gradient contraction is cut into slices of at most 48 k-blocks of 32 rows (accumulation-chain bound,
+    csrc/dense_tc.cuh), never more slices than k-blocks, and no workspace when one slice suffices."""
+    from bns_gcn_b200 import _lib
+    f = _lib.lib.bns_dense_nt_workspace_bytes
+    assert f(32, 128, 128) == 0 and f(0, 128, 128) == 0 and f(100, 0, 8) == 0
+    for R, n1, n2 in [(232965, 256, 1204), (232965, 256, 256), (58242, 256, 1204), (29121, 44, 256), (1000, 136, 100)]:
+        b = f(R, n1, n2)
+        assert b % (n1 * n2 * 4) == 0
+        splits = b // (n1 * n2 * 4) if b else 1
+        kb = (R + 31) // 32
+        assert 1 <= splits <= kb
+        assert (kb + splits - 1) // splits <= 48 + 5, (R, n1, n2, splits)      # <= 48 up to the -10 % wave rounding
+    assert _lib.lib.bns_colsum_workspace_bytes(256) == 148 * 4 * 64 * 16
