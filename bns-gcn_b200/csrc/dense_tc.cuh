@@ -4,11 +4,12 @@
 //
 // Why not one TF32 GEMM: the parity bar is 1e-4 on layer outputs (f32 in the reference: torch 1.12 has
 // allow_tf32 = False for matmul); a 10-bit mantissa misses it.  The kernel therefore computes the error-compensated
-// 3xTF32 product  A*B ~= A_hi*B_hi + A_hi*B_lo + A_lo*B_hi  (hi = x rounded to TF32, lo = x - hi, exact in f32; the
-// dropped lo*lo term is ~2^-22 relative) with the operand split done INSIDE the pipeline: TMA lands the raw f32 tile
-// in shared memory, four "split" warps rewrite it in place as hi and write lo beside it (element-wise, so the
-// 128-byte swizzle pattern is untouched), then one thread issues the three MMAs per 8-wide k-step.  HBM/L2 see every
-// operand once; the library-composed variant (module/dense.py "3xtf32") needs a split pass plus three GEMMs.
+// 3xTF32 product  A*B ~= A_hi*B_hi + A_hi*B_lo + A_lo*B_hi  (hi = the TF32 part of x, lo = x - hi, exact in f32; the
+// dropped lo*lo term is ~2^-20 relative) with the operand split done INSIDE the pipeline: TMA lands the raw f32 tile
+// in shared memory, four "split" warps write lo beside it (element-wise, so the 128-byte swizzle pattern is
+// untouched; hi is the raw tile itself, see kTrunc below), then one thread issues the three MMAs per 8-wide k-step.
+// HBM/L2 see every operand once; the library-composed variant (module/dense.py "3xtf32") needs a split pass plus
+// three GEMMs.
 //
 // A work item = one 128 x 128 output tile (x one slice of the contraction for the weight-gradient shape); persistent CTAs
 // of 320 threads walk the items:
@@ -29,7 +30,7 @@
 //   kMN = false  A [M, K], B [N, K] row-major: contraction contiguous ("K-major").  forward  Y = X W^T + b  and the
 //                input gradient  dX = dY (W^T)^T  (the caller passes a transposed copy of the small weight).
 //   kMN = true   A [R, M], B [R, N] row-major: contraction over the R rows ("MN-major").  weight gradient
-//                dW = dY^T X, contraction = the node dimension, split over blockIdx.y with a deterministic reduce.
+//                dW = dY^T X, contraction = the node dimension, cut into slices (work items) with a deterministic reduce.
 #include <cuda.h>   // CUtensorMap + enums only; cuTensorMapEncodeTiled is fetched through cudaGetDriverEntryPoint
 
 namespace tc {
@@ -39,7 +40,7 @@ constexpr int UMMA_K = 8;                       // kind::tf32: 8 elements (32 by
 constexpr int kStages = 3;
 constexpr int A_BYTES = BM * BK * 4;            // 16 KB
 constexpr int B_BYTES = BN * BK * 4;            // 16 KB
-constexpr int RAW_BYTES = A_BYTES + B_BYTES;    // TMA lands here; becomes the hi parts in place
+constexpr int RAW_BYTES = A_BYTES + B_BYTES;    // TMA lands here: the hi parts (the tensor core drops the low bits)
 constexpr int STAGE_BYTES = 2 * RAW_BYTES;      // [A_hi | B_hi | A_lo | B_lo]
 constexpr int kThreadsTc = 320;                 // warp 0 TMA, warp 1 MMA, warps 2-5 split, warps 6-9 epilogue
 constexpr int kSplitThreads = 128;
