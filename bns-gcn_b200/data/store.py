@@ -80,7 +80,8 @@ def graph_partition(args, fg: Optional[FullGraph] = None, device: Optional[torch
     os.makedirs(graph_dir, exist_ok=True)
     if not os.path.exists(part_config):                    # utils.py:86
         parts = partition_graph(fg, args.n_partitions, args.partition_method, seed=getattr(args, 'graph_seed', 0),
-                                inductive=args.inductive, device=device)
+                                inductive=args.inductive, device=device,
+                                objective=getattr(args, 'partition_obj', 'vol'))
         cfg = {"format_version": FORMAT_VERSION, "graph_name": args.graph_name, "num_parts": args.n_partitions,
                "part_method": args.partition_method, "inductive": bool(args.inductive),
                "node_map": [int(x) for x in parts[0].gpb.ranges.tolist()],

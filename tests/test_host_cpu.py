@@ -155,3 +155,48 @@ def test_dense_split_k_plan_is_sane_without_a_gpu(built):
         assert 1 <= splits <= kb
         assert (kb + splits - 1) // splits <= 48 + 5, (R, n1, n2, splits)      # <= 48 up to the -10 % wave rounding
     assert _lib.lib.bns_colsum_workspace_bytes(256) == 148 * 4 * 64 * 16
+
+
+def _planted_partition_graph(n, P, deg_in, deg_out, seed=0):
+    """Symmetric stochastic-block-model graph with one self loop per node (the generator's contract) and its blocks."""
+    from bns_gcn_b200.data import FullGraph
+    g = torch.Generator().manual_seed(seed)
+    blk = torch.randint(0, P, (n,), generator=g)
+    order = torch.argsort(blk)
+    starts, sizes = torch.searchsorted(blk[order], torch.arange(P)), torch.bincount(blk, minlength=P)
+    m_in, m_out = n * deg_in // 2, n * deg_out // 2
+    u = torch.randint(0, n, (m_in,), generator=g)
+    v = order[starts[blk[u]] + (torch.rand(m_in, generator=g) * sizes[blk[u]]).long().clamp(max=sizes[blk[u]] - 1)]
+    a = torch.cat([u, torch.randint(0, n, (m_out,), generator=g)])
+    b = torch.cat([v, torch.randint(0, n, (m_out,), generator=g)])
+    keep = a != b
+    lo, hi = torch.minimum(a[keep], b[keep]), torch.maximum(a[keep], b[keep])
+    key = torch.unique(lo * n + hi)
+    lo, hi, loops = key // n, key % n, torch.arange(n)
+    dst, src = torch.cat([lo, hi, loops]), torch.cat([hi, lo, loops])
+    o = torch.argsort(dst * n + src)
+    dst, src = dst[o], src[o]
+    indptr = torch.zeros(n + 1, dtype=torch.int64)
+    indptr[1:] = torch.cumsum(torch.bincount(dst, minlength=n), 0)
+    z = torch.zeros(n, dtype=torch.bool)
+    return FullGraph(n, indptr, src, torch.zeros(n, 1), torch.zeros(n, dtype=torch.int64), z, z, z, 2), blk
+
+
+@pytest.mark.parametrize("objective", ["cut", "vol"])
+def test_metis_standin_finds_planted_structure(objective):
+    """``--partition-method metis`` (RCM blocks + balanced label propagation on ``--partition-obj``): on a graph with
+    4 planted communities it must land near the planted cut -- far below what ``random`` gives -- within the size cap,
+    and the refinement must never return something worse than it was given."""
+    import bns_gcn_b200  # noqa: F401
+    from bns_gcn_b200.data import assign_parts, partition_quality, refine_label_propagation
+    fg, blk = _planted_partition_graph(8000, 4, 16, 2)
+    planted = partition_quality(fg, blk, 4)
+    rnd = partition_quality(fg, assign_parts(fg, 4, "random", 0), 4)
+    part = assign_parts(fg, 4, "metis", 0, objective)
+    q = partition_quality(fg, part, 4)
+    assert q[objective] <= 1.5 * planted[objective] and q[objective] < 0.5 * rnd[objective], (q, planted, rnd)
+    assert q["max_size"] <= int(1.03 * 8000 / 4) + 1 and q["min_size"] > 0
+    # monotone: refining a random assignment never makes it worse
+    start = assign_parts(fg, 4, "random", 1)
+    better = refine_label_propagation(fg, start, 4, objective)
+    assert partition_quality(fg, better, 4)[objective] <= partition_quality(fg, start, 4)[objective]
