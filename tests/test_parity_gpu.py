@@ -263,6 +263,10 @@ def test_gat_training_parity(built, kw):
     _run(shape=shape, model="gat", n_epochs=2, multilabel=(shape == "tiny-ml"), **kw)
 
 
+@pytest.mark.xfail(strict=False, reason="written after the round's GPU budget ended: the host pieces (checkpoint names / "
+                                       "keys, accuracy, result lines) are CPU-tested in tests/test_store_eval_cpu.py and "
+                                       "the full-graph forward by test_eval_branch_full_graph; this end-to-end wiring "
+                                       "has not run on hardware yet -- drop the marker once it has")
 def test_run_with_eval_writes_checkpoints_and_results(built, tmp_path, monkeypatch):
     """train.run with --eval (train.py:427-456): every log_every epochs rank 0 saves a checkpoint, evaluates on the full
     graph with the same kernels and appends the result line; at the end the best model is saved and tested."""
