@@ -94,7 +94,8 @@ def refine_label_propagation(fg: FullGraph, part: torch.Tensor, n_parts: int, ob
                              rounds: int = 24, imbalance: float = 0.03, seed: int = 0, device=None) -> torch.Tensor:
     """Balanced label propagation: every round each node looks at the owners of its neighbours, the nodes that would
     gain most by joining the majority owner move -- as many as the target part has room for under the size cap
-    ``(1 + imbalance) N / P``, and only a random half of them per round (simultaneous moves of neighbours can undo
+    ``(1 + imbalance) N / P`` (and the source part above the floor ``(1 - imbalance) N / P``), and only a random half of
+    them per round (simultaneous moves of neighbours can undo
     each other).  A round that does not improve ``objective`` ("cut" | "vol") is rolled back (three in a row end the
     refinement), so the result is never worse than the input.  Pure torch (sorting / unique / scatter): runs on
     ``device``."""
@@ -108,6 +109,7 @@ def refine_label_propagation(fg: FullGraph, part: torch.Tensor, n_parts: int, ob
     src, dst = src_all[keep], dst_all[keep]
     part = part.to(dev).clone()
     cap = int((1.0 + imbalance) * n / P) + 1
+    floor = max(int((1.0 - imbalance) * n / P), 1)
 
     def score(p):
         ps, pd = p[src], p[dst]
@@ -145,6 +147,14 @@ def refine_label_propagation(fg: FullGraph, part: torch.Tensor, n_parts: int, ob
         rank = torch.arange(cand.numel(), device=dev) - first[tgt]
         ok = rank < room[tgt]
         movers, to = cand[ok], tgt[ok]
+        if movers.numel():                                           # nor may a part shrink below the floor
+            frm = part[movers]
+            o2 = torch.argsort(frm, stable=True)                     # keeps the gain order inside each source part
+            movers, to, frm = movers[o2], to[o2], frm[o2]
+            first2 = torch.searchsorted(frm, torch.arange(P, device=dev))
+            rank2 = torch.arange(movers.numel(), device=dev) - first2[frm]
+            ok2 = rank2 < (sizes - floor).clamp(min=0)[frm]
+            movers, to = movers[ok2], to[ok2]
         if movers.numel() == 0:
             break
         trial = part.clone()

@@ -195,7 +195,7 @@ def test_metis_standin_finds_planted_structure(objective):
     part = assign_parts(fg, 4, "metis", 0, objective)
     q = partition_quality(fg, part, 4)
     assert q[objective] <= 1.5 * planted[objective] and q[objective] < 0.5 * rnd[objective], (q, planted, rnd)
-    assert q["max_size"] <= int(1.03 * 8000 / 4) + 1 and q["min_size"] > 0
+    assert q["max_size"] <= int(1.03 * 8000 / 4) + 1 and q["min_size"] >= int(0.97 * 8000 / 4)
     # monotone: refining a random assignment never makes it worse
     start = assign_parts(fg, 4, "random", 1)
     better = refine_label_propagation(fg, start, 4, objective)
