@@ -46,23 +46,30 @@ def _aggregate(graph, feat, rs, cs_u=None):
     raise TypeError(f"unsupported graph handle {type(graph).__name__}")
 
 
+def _uniform_init(*linears):
+    """``reset_parameters`` of the reference's layers (module/layer.py:20-24, 65-77): every weight, then every bias,
+    from U(-1/sqrt(fan_in), 1/sqrt(fan_in)) of the FIRST linear -- the draw order fixes the weights under a seed."""
+    bound = 1. / math.sqrt(linears[0].weight.size(1))
+    for t in [lin.weight for lin in linears] + [lin.bias for lin in linears if lin.bias is not None]:
+        t.data.uniform_(-bound, bound)
+
+
+def _apply(lin, x, addend=None):
+    return dense.linear(x, lin.weight, lin.bias, addend=addend)
+
+
 class GCNLayer(nn.Module):
 
     def __init__(self, in_feats, out_feats, bias=True, use_pp=False):
-        super(GCNLayer, self).__init__()
+        super().__init__()
         self.use_pp = use_pp
         self.linear = nn.Linear(in_feats, out_feats, bias=bias)
         self.reset_parameters()
 
     def reset_parameters(self):
-        stdv = 1. / math.sqrt(self.linear.weight.size(1))
-        self.linear.weight.data.uniform_(-stdv, stdv)
-        if self.linear.bias is not None:
-            self.linear.bias.data.uniform_(-stdv, stdv)
+        _uniform_init(self.linear)
 
-    @staticmethod
-    def _lin(lin, x):
-        return dense.linear(x, lin.weight, lin.bias)
+    _lin = staticmethod(_apply)
 
     def forward(self, graph, feat, in_norm, out_norm):
         """``out_norm``: sqrt(out_deg) of every *local* node (inner then halo, static) -- the reference rebuilds a
@@ -82,11 +89,13 @@ class GCNLayer(nn.Module):
 
 
 class GraphSAGELayer(nn.Module):
+    """Parameters ``linear`` (precomputed layer 0: input ``[x | mean_nbr(x)]``) or ``linear1`` (self) + ``linear2``
+    (neighbours), named as in the reference."""
 
     def __init__(self, in_feats, out_feats, bias=True, use_pp=False):
-        super(GraphSAGELayer, self).__init__()
+        super().__init__()
         self.use_pp = use_pp
-        if self.use_pp:
+        if use_pp:
             self.linear = nn.Linear(2 * in_feats, out_feats, bias=bias)
         else:
             self.linear1 = nn.Linear(in_feats, out_feats, bias=bias)
@@ -94,22 +103,9 @@ class GraphSAGELayer(nn.Module):
         self.reset_parameters()
 
     def reset_parameters(self):
-        if self.use_pp:
-            stdv = 1. / math.sqrt(self.linear.weight.size(1))
-            self.linear.weight.data.uniform_(-stdv, stdv)
-            if self.linear.bias is not None:
-                self.linear.bias.data.uniform_(-stdv, stdv)
-        else:
-            stdv = 1. / math.sqrt(self.linear1.weight.size(1))
-            self.linear1.weight.data.uniform_(-stdv, stdv)
-            self.linear2.weight.data.uniform_(-stdv, stdv)
-            if self.linear1.bias is not None:
-                self.linear1.bias.data.uniform_(-stdv, stdv)
-                self.linear2.bias.data.uniform_(-stdv, stdv)
+        _uniform_init(*([self.linear] if self.use_pp else [self.linear1, self.linear2]))
 
-    @staticmethod
-    def _lin(lin, x):
-        return dense.linear(x, lin.weight, lin.bias)
+    _lin = staticmethod(_apply)
 
     def forward(self, graph, feat, in_norm):
         if self.training:

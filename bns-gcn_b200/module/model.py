@@ -1,5 +1,7 @@
-"""``GCN`` / ``GraphSAGE`` layer stacks with the reference's constructor and ``forward`` signatures
-(module/model.py:7-93).  ``GAT`` and ``--norm batch`` are SURVEY.md §8(f) "next" rows."""
+"""Layer stacks ``GCN`` / ``GraphSAGE`` / ``GAT`` behind the reference's constructors and ``forward`` signatures
+(module/model.py:7-132).  What is an interface is kept -- class and attribute names (``layers``, ``norm``,
+``dropout``: they are the state-dict keys), argument order, the order in which sub-modules are created (it fixes the
+initial weights under a given seed) -- the rest is organised around one builder and one inter-layer step."""
 import torch.nn.functional as F
 from torch import nn
 
@@ -12,68 +14,77 @@ from .layer import GCNLayer, GraphSAGELayer
 FUSE_NORM_ACT_DROPOUT = True
 
 
+def _make_norm(kind, width, train_size):
+    if kind == 'layer':
+        return nn.LayerNorm(width, elementwise_affine=True)
+    if kind == 'batch':
+        from .sync_bn import SyncBatchNorm
+        return SyncBatchNorm(width, train_size)
+    return None
+
+
 class GNNBase(nn.Module):
 
     def __init__(self, layer_size, activation, use_pp=False, dropout=0.5, norm='layer', n_linear=0):
-        super(GNNBase, self).__init__()
-        self.n_layers = len(layer_size) - 1
-        self.layers = nn.ModuleList()
-        self.activation = activation
-        self.use_pp = use_pp
-        self.n_linear = n_linear
-        if norm is None:
-            self.use_norm = False
-        else:
-            self.use_norm = True
+        super().__init__()
+        self.n_layers, self.n_linear = len(layer_size) - 1, n_linear
+        self.activation, self.use_pp = activation, use_pp
+        self.layers = nn.ModuleList()              # registered before `norm`: parameter order of the reference
+        self.use_norm = norm is not None
+        if self.use_norm:
             self.norm = nn.ModuleList()
         self.dropout = nn.Dropout(p=dropout)
 
-    def _build(self, layer_cls, layer_size, use_pp, norm, train_size):
-        for i in range(self.n_layers):
-            if i < self.n_layers - self.n_linear:
-                self.layers.append(layer_cls(layer_size[i], layer_size[i + 1], use_pp=use_pp))
-            else:
-                self.layers.append(nn.Linear(layer_size[i], layer_size[i + 1]))
-            if i < self.n_layers - 1 and self.use_norm:
-                if norm == 'layer':
-                    self.norm.append(nn.LayerNorm(layer_size[i + 1], elementwise_affine=True))
-                elif norm == 'batch':
-                    from .sync_bn import SyncBatchNorm
-                    self.norm.append(SyncBatchNorm(layer_size[i + 1], train_size))
-            use_pp = False                                   # model.py:40, 75: only layer 0 is precomputed
+    @property
+    def n_conv(self) -> int:
+        """Graph layers come first, ``n_linear`` plain ``nn.Linear`` layers close the stack."""
+        return self.n_layers - self.n_linear
+
+    def _populate(self, layer_size, conv, norm, train_size):
+        """``conv(i, n_in, n_out)`` makes graph layer ``i``.  Layer ``i`` is created before the norm that follows it."""
+        for i, (n_in, n_out) in enumerate(zip(layer_size[:-1], layer_size[1:])):
+            self.layers.append(conv(i, n_in, n_out) if i < self.n_conv else nn.Linear(n_in, n_out))
+            if self.use_norm and i < self.n_layers - 1:
+                nm = _make_norm(norm, n_out, train_size)
+                if nm is not None:
+                    self.norm.append(nm)
+
+    def _between(self, i, h, may_fuse):
+        """norm -> activation after layer ``i``.  Returns ``(h, dropped)``: with ``may_fuse`` and LayerNorm + ReLU the
+        fused kernel also applies the NEXT layer's input dropout."""
+        nm = self.norm[i] if self.use_norm else None
+        if (may_fuse and FUSE_NORM_ACT_DROPOUT and isinstance(nm, nn.LayerNorm) and self.activation is F.relu
+                and nm.elementwise_affine and ops.ln_relu_dropout_supported(h, h.shape[1])):
+            p = self.dropout.p if self.training else 0.0
+            return ops.LnReluDropout.apply(h, nm.weight, nm.bias, nm.eps, p, ops.RNG["seed"] + 7919 * (i + 1)), True
+        if nm is not None:
+            h = nm(h)
+        return self.activation(h), False
 
     def _forward(self, g, feat, *norms):
-        h = feat
-        dropped = False                      # this layer's input dropout was already applied by the fused op
-        for i in range(self.n_layers):
+        """GCN / GraphSAGE (module/model.py:42-58, 77-93): dropout -> [exchange] -> layer -> norm -> activation."""
+        h, dropped = feat, False               # dropped: this layer's input dropout was applied by the fused step
+        for i, layer in enumerate(self.layers):
             if not dropped:
                 h = self.dropout(h)
-            dropped = False
-            if i < self.n_layers - self.n_linear:
+            if i >= self.n_conv:
+                h = layer(h)
+            else:
                 if self.training and (i > 0 or not self.use_pp):
                     h = ctx.buffer.update(i, h, overlap=True)          # model.py:47-48, 82-83
-                h = self.layers[i](g, h, *norms)
-            else:
-                h = self.layers[i](h)
+                h = layer(g, h, *norms)
+            dropped = False
             if i < self.n_layers - 1:
-                nm = self.norm[i] if self.use_norm else None
-                if (FUSE_NORM_ACT_DROPOUT and isinstance(nm, nn.LayerNorm) and self.activation is F.relu
-                        and nm.elementwise_affine and ops.ln_relu_dropout_supported(h, h.shape[1])):
-                    p = self.dropout.p if self.training else 0.0
-                    h = ops.LnReluDropout.apply(h, nm.weight, nm.bias, nm.eps, p, ops.RNG["seed"] + 7919 * (i + 1))
-                    dropped = True
-                else:
-                    if self.use_norm:
-                        h = nm(h)
-                    h = self.activation(h)
+                h, dropped = self._between(i, h, True)
         return h
 
 
 class GCN(GNNBase):
 
     def __init__(self, layer_size, activation, use_pp, dropout=0.5, norm='layer', train_size=None, n_linear=0):
-        super(GCN, self).__init__(layer_size, activation, use_pp, dropout, norm, n_linear)
-        self._build(GCNLayer, layer_size, use_pp, norm, train_size)
+        super().__init__(layer_size, activation, use_pp, dropout, norm, n_linear)
+        # only layer 0 consumes precomputed features (model.py:40)
+        self._populate(layer_size, lambda i, a, b: GCNLayer(a, b, use_pp=use_pp and i == 0), norm, train_size)
 
     def forward(self, g, feat, in_norm=None, out_norm=None):
         return self._forward(g, feat, in_norm, out_norm)
@@ -82,50 +93,35 @@ class GCN(GNNBase):
 class GraphSAGE(GNNBase):
 
     def __init__(self, layer_size, activation, use_pp, dropout=0.5, norm='layer', train_size=None, n_linear=0):
-        super(GraphSAGE, self).__init__(layer_size, activation, use_pp, dropout, norm, n_linear)
-        self._build(GraphSAGELayer, layer_size, use_pp, norm, train_size)
+        super().__init__(layer_size, activation, use_pp, dropout, norm, n_linear)
+        self._populate(layer_size, lambda i, a, b: GraphSAGELayer(a, b, use_pp=use_pp and i == 0), norm, train_size)   # :75
 
     def forward(self, g, feat, in_norm=None):
         return self._forward(g, feat, in_norm)
 
 
 class GAT(GNNBase):
-    """module/model.py:96-132."""
+    """module/model.py:96-132: attention layers take the ``(source rows, destination rows)`` pair, heads are averaged,
+    dropout sits inside the attention layers (and before the closing linear layers only)."""
 
     def __init__(self, layer_size, activation, use_pp, heads=1, dropout=0.5, norm='layer', train_size=None, n_linear=0):
-        super(GAT, self).__init__(layer_size, activation, use_pp, dropout, norm, n_linear)
+        super().__init__(layer_size, activation, use_pp, dropout, norm, n_linear)
         from .gat import GATConv
-        for i in range(self.n_layers):
-            if i < self.n_layers - self.n_linear:
-                self.layers.append(GATConv(layer_size[i], layer_size[i + 1], heads, dropout, dropout))
-            else:
-                self.layers.append(nn.Linear(layer_size[i], layer_size[i + 1]))
-            if i < self.n_layers - 1 and self.use_norm:
-                if norm == 'layer':
-                    self.norm.append(nn.LayerNorm(layer_size[i + 1], elementwise_affine=True))
-                elif norm == 'batch':
-                    from .sync_bn import SyncBatchNorm
-                    self.norm.append(SyncBatchNorm(layer_size[i + 1], train_size))
+        self._populate(layer_size, lambda i, a, b: GATConv(a, b, heads, dropout, dropout), norm, train_size)
 
     def forward(self, g, feat):
         h = feat
-        for i in range(self.n_layers):
-            if i < self.n_layers - self.n_linear:
-                if self.training:
-                    if i > 0 or not self.use_pp:
-                        h1 = ctx.buffer.update(i, h, overlap=True)                # model.py:117-118
-                    else:
-                        h1 = h
-                        h = h[0:g.num_nodes('_V')]                                # :120-121
-                    h = self.layers[i](g, (h1, h))
-                else:
-                    h = self.layers[i](g, h)
-                h = h.mean(1)
+        for i, layer in enumerate(self.layers):
+            if i >= self.n_conv:
+                h = layer(self.dropout(h))
+            elif not self.training:
+                h = layer(g, h).mean(1)
             else:
-                h = self.dropout(h)
-                h = self.layers[i](h)
+                if i == 0 and self.use_pp:
+                    src, dst = h, h[0:g.num_nodes('_V')]                # :120-121: layer 0 holds the stored halo rows
+                else:
+                    src, dst = ctx.buffer.update(i, h, overlap=True), h  # :117-118
+                h = layer(g, (src, dst)).mean(1)
             if i < self.n_layers - 1:
-                if self.use_norm:
-                    h = self.norm[i](h)
-                h = self.activation(h)
+                h, _ = self._between(i, h, False)
         return h

@@ -1,10 +1,10 @@
 """``SyncBatchNorm`` (``--norm batch``; reference: module/sync_bn.py:7-56): batch statistics over ALL partitions.
 
-Same arithmetic as the reference, including its conventions: sums run over every inner node of every rank but are
-divided by ``whole_size`` (= the global number of TRAIN nodes, model.py:39), and the returned dweight / dbias are
-already global sums (the Reducer then divides by n_train and all-reduces them once more, like any other parameter).
-The reference issues 4 all-reduces of ``[F]`` per layer (2 forward, 2 backward, :17-18, :35-36); here each pair
-travels as one ``[2F]`` message."""
+The arithmetic and its conventions are the reference's: sums run over every inner node of every rank but are divided
+by ``whole_size`` (= the global number of TRAIN nodes, model.py:39); the returned d(weight) / d(bias) are already
+global sums (the Reducer then divides by n_train and all-reduces them once more, like any other parameter).  What
+differs is the traffic: the reference issues four ``[F]`` all-reduces per layer and step (sync_bn.py:17-18, :35-36);
+here the two moments travel as one ``[2F]`` message forward and the two gradient sums as one backward."""
 import torch
 from torch import nn
 from torch.autograd import Function
@@ -12,21 +12,28 @@ from torch.autograd import Function
 from ..helper import context as ctx
 
 
+def _global_column_sums(comm, first: torch.Tensor, second: torch.Tensor):
+    """Column sums of two ``[n, F]`` matrices over all ranks, one all-reduce for both."""
+    width = first.shape[1]
+    packed = torch.cat([first.sum(dim=0), second.sum(dim=0)])
+    comm.all_reduce_sum(packed)
+    return packed[:width], packed[width:]
+
+
 class SyncBatchNormFunc(Function):
+    """y = (x - mean) / sqrt(var + eps) * weight + bias with ``mean = S1 / n``, ``var = (S2 - mean * S1) / n``,
+    ``S1 = sum x``, ``S2 = sum x^2`` over every rank, ``n = whole_size``."""
 
     @staticmethod
     def forward(ctx_, x, weight, bias, whole_size, running_mean, running_var, training, momentum, eps, comm):
-        if not training:
-            mean, var = running_mean, running_var
+        if training:
+            s1, s2 = _global_column_sums(comm, x, x ** 2)
+            mean = s1 / whole_size
+            var = (s2 - mean * s1) / whole_size
+            for running, batch in ((running_mean, mean), (running_var, var)):
+                running.mul_(1 - momentum).add_(batch * momentum)
         else:
-            F = x.shape[1]
-            s = torch.cat([x.sum(dim=0), (x ** 2).sum(dim=0)])
-            comm.all_reduce_sum(s)                                   # sync_bn.py:17-18 in one message
-            sum_x, sum_x2 = s[:F], s[F:]
-            mean = sum_x / whole_size
-            var = (sum_x2 - mean * sum_x) / whole_size
-            running_mean.mul_(1 - momentum).add_(mean * momentum)
-            running_var.mul_(1 - momentum).add_(var * momentum)
+            mean, var = running_mean, running_var
         std = torch.sqrt(var + eps)
         x_hat = (x - mean) / std
         if training:
@@ -37,24 +44,21 @@ class SyncBatchNormFunc(Function):
     @staticmethod
     def backward(ctx_, grad):
         x_hat, weight, std = ctx_.saved_tensors
-        F = grad.shape[1]
-        d = torch.cat([grad.sum(dim=0), (grad * x_hat).sum(dim=0)])
-        ctx_.comm.all_reduce_sum(d)                                  # sync_bn.py:35-36 in one message
-        dbias, dweight = d[:F], d[F:]
+        d_bias, d_weight = _global_column_sums(ctx_.comm, grad, grad * x_hat)
         n = ctx_.whole_size
-        dx = (weight / n) / std * (n * grad - dbias - x_hat * dweight)
-        return dx, dweight, dbias, None, None, None, None, None, None, None
+        d_x = (weight / n) / std * (n * grad - d_bias - x_hat * d_weight)
+        return (d_x, d_weight, d_bias) + (None,) * 7
 
 
 class SyncBatchNorm(nn.Module):
+    """Parameters ``weight`` / ``bias`` and buffers ``running_mean`` / ``running_var`` as in the reference, so that
+    state dicts are interchangeable."""
 
     def __init__(self, num_features, whole_size, eps=1e-5, momentum=0.1):
-        super(SyncBatchNorm, self).__init__()
-        self.register_buffer('running_mean', torch.zeros(num_features))
-        self.register_buffer('running_var', torch.ones(num_features))
-        self.whole_size = whole_size
-        self.eps = eps
-        self.momentum = momentum
+        super().__init__()
+        self.whole_size, self.eps, self.momentum = whole_size, eps, momentum
+        for name, init in (('running_mean', torch.zeros), ('running_var', torch.ones)):
+            self.register_buffer(name, init(num_features))
         self.weight = nn.Parameter(torch.ones(num_features))
         self.bias = nn.Parameter(torch.zeros(num_features))
 

@@ -111,3 +111,32 @@ def test_checkpoint_keys_are_the_references_and_round_trip(tmp_path):
     torch.save({k: v for k, v in zip(r0["param_names"], r0["params"])}, os.path.join(tmp_path, "ref.pth.tar"))
     load_checkpoint(m2, os.path.join(tmp_path, "ref.pth.tar"))
     assert all(torch.equal(p, q) for p, q in zip(m2.parameters(), r0["params"]))
+
+
+@pytest.mark.parametrize("kind", ["graphsage", "gcn", "gat"])
+def test_model_mirrors_start_from_the_references_weights(kind):
+    """Under ``torch.manual_seed(seed)`` (train.py:331-333) the reference's initial weights are a function of the order
+    in which sub-modules are created and re-initialised.  The oracle restates that order (and is pinned to the
+    reference by the golden vectors); the product's mirrors must reproduce it: same names, same tensors."""
+    import torch.nn.functional as F
+    import bns_gcn_b200  # noqa: F401
+    from bns_gcn_b200.module.model import GAT, GCN, GraphSAGE
+    from oracle import bns_oracle as O
+    for use_pp in (False, True):
+        for norm in ("layer", "batch"):
+            for n_linear in (0, 1):
+                if kind == "gat" and not use_pp:
+                    continue                                   # the reference's GAT path requires --use-pp
+                layer_size = [12, 16, 16, 5]
+                torch.manual_seed(4)
+                if kind == "gat":
+                    ours = GAT(layer_size, F.relu, use_pp, heads=2, dropout=0.1, norm=norm, train_size=33, n_linear=n_linear)
+                else:
+                    ours = (GraphSAGE if kind == "graphsage" else GCN)(layer_size, F.relu, use_pp, dropout=0.1, norm=norm,
+                                                                         train_size=33, n_linear=n_linear)
+                torch.manual_seed(4)
+                ref = O.build_model(kind, layer_size, use_pp, 0.1, norm, 33, n_linear, 2)
+                a, b = dict(ours.named_parameters()), dict(ref.named_parameters())
+                assert list(a) == list(b), (use_pp, norm, n_linear)
+                for k in a:
+                    assert torch.equal(a[k], b[k]), (k, use_pp, norm, n_linear)
