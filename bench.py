@@ -9,6 +9,9 @@ features, 41 classes), vertex-partitioned over the N GPUs (random partition).  A
 boundary sampling -> id exchange -> forward (feature exchange + SpMM + dense) -> loss -> backward (SpMM^T +
 gradient exchange) -> weight-gradient all-reduce -> Adam.  The graph is fixed, so more GPUs = less work per GPU
 ("scaling": "strong").  value = epochs/sec of the whole job (max over ranks of the device-timed region).
+Besides the contract keys the line carries `roofline` (the SpMM, the dominant kernel: algorithmic bytes / CUDA-event
+time per launch, measured in an eager pass of the same step), `dense_roofline` (the tcgen05 GEMM family), `e2e`
+(inputs copied from pinned host memory every epoch, loss read back), `cpu_baseline` (N=1), `exchange`, `clocks`.
 
 `--impl reference` times the CPU restatement of the reference (oracle/: torch CPU fp32 + C/OpenMP SpMM, P in-process
 ranks for N>1) on the host cores with the same config; the real reference cannot run here (needs DGL + CUDA 11.3
