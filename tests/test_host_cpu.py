@@ -119,25 +119,29 @@ def _gloo_worker(rank, world, port, out_dir, use_store=False):
     dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("use_store", [False, True])
-def test_exchange_metadata_gloo_world2(tmp_path, use_store):
+@pytest.mark.parametrize("world,use_store", [(2, False), (2, True), (4, False)])
+def test_exchange_metadata_gloo(tmp_path, world, use_store):
+    """get_boundary / get_pos / send-recv sizes / data_transfer over torch.distributed gloo, ``world`` processes."""
     import torch.multiprocessing as mp
-    mp.spawn(_gloo_worker, args=(2, 29650 + int(use_store), str(tmp_path), use_store), nprocs=2, join=True)
-    r = [torch.load(os.path.join(tmp_path, f"r{i}.pt")) for i in range(2)]
-    gold = torch.load(os.path.join(ROOT, "tests", "golden", "ref_graphsage_p2.pt"))["ranks"]
-    for me, other in ((0, 1), (1, 0)):
-        a, b = r[me], r[other]
-        assert torch.equal(a["boundary"][other], gold[me]["boundary"][other])         # == the reference's get_boundary
-        assert a["send"][other] == b["recv"][me] == int(0.5 * a["boundary"][other].numel())
-        assert abs(a["ratio"][other] - a["send"][other] / a["boundary"][other].numel()) < 1e-12
-        assert torch.equal(b["hops"][me], a["sel"][other])                            # exchange exactness
-        # pos maps the sender's local ids onto my halo slots: the global ids agree
-        mine = b["pos"][me][a["sel"][other]]
-        assert torch.all(mine >= b["n_in"])
-        assert torch.equal(b["nid"][mine], a["sel"][other] + int(a["ranges"][me]))
-        # merged out-degree vector == full-graph out-degree of [inner | halo]
-        # (node ids were relabelled by the partitioner, so compare through the relabelled full graph)
-        assert a["out_deg"].numel() == a["nid"].numel()
+    mp.spawn(_gloo_worker, args=(world, 29650 + 2 * world + int(use_store), str(tmp_path), use_store), nprocs=world, join=True)
+    r = [torch.load(os.path.join(tmp_path, f"r{i}.pt")) for i in range(world)]
+    gold = torch.load(os.path.join(ROOT, "tests", "golden", "ref_graphsage_p2.pt"))["ranks"] if world == 2 else None
+    for me in range(world):
+        for other in range(world):
+            if other == me:
+                continue
+            a, b = r[me], r[other]
+            if gold is not None:
+                assert torch.equal(a["boundary"][other], gold[me]["boundary"][other])     # == the reference's get_boundary
+            assert a["send"][other] == b["recv"][me] == int(0.5 * a["boundary"][other].numel())
+            assert abs(a["ratio"][other] - a["send"][other] / a["boundary"][other].numel()) < 1e-12
+            assert torch.equal(b["hops"][me], a["sel"][other])                            # exchange exactness
+            # pos maps the sender's local ids onto my halo slots: the global ids agree
+            mine = b["pos"][me][a["sel"][other]]
+            assert torch.all(mine >= b["n_in"])
+            assert torch.equal(b["nid"][mine], a["sel"][other] + int(a["ranges"][me]))
+        # merged out-degree vector covers [inner | halo]
+        assert r[me]["out_deg"].numel() == r[me]["nid"].numel()
 
 
 def test_dense_split_k_plan_is_sane_without_a_gpu(built):
