@@ -140,3 +140,29 @@ def test_model_mirrors_start_from_the_references_weights(kind):
                 assert list(a) == list(b), (use_pp, norm, n_linear)
                 for k in a:
                     assert torch.equal(a[k], b[k]), (k, use_pp, norm, n_linear)
+
+
+@pytest.mark.parametrize("kind", ["graphsage", "gcn"])
+def test_all_linear_stack_runs_on_the_cpu_and_matches_the_oracle(kind):
+    """With ``n_linear == n_layers`` the stack holds no graph layer, so the product's ``_forward`` / inter-layer step
+    run on plain ATen CPU ops: dropout -> Linear -> norm -> activation must equal the oracle's (reference's) loop,
+    in training mode too (same dropout draws)."""
+    import torch.nn.functional as F
+    import bns_gcn_b200  # noqa: F401
+    from bns_gcn_b200.module.model import GCN, GraphSAGE
+    from oracle import bns_oracle as O
+    layer_size = [12, 16, 16, 5]
+    for p in (0.0, 0.4):
+        torch.manual_seed(4)
+        ours = (GraphSAGE if kind == "graphsage" else GCN)(layer_size, F.relu, False, dropout=p, norm="layer", n_linear=3)
+        torch.manual_seed(4)
+        ref = O.build_model(kind, layer_size, False, p, "layer", None, 3, 1)
+        x = torch.randn(40, 12)
+        for training in (False, True):
+            ours.train(training)
+            ref.train(training)
+            torch.manual_seed(8)
+            a = ours(None, x)
+            torch.manual_seed(8)
+            b = ref(None, x)
+            assert torch.equal(a, b), (p, training)
