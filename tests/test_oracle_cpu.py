@@ -269,3 +269,32 @@ def test_harness_kink_retry_logic_with_a_stub_product(monkeypatch):
     monkeypatch.setattr(H, "KINK_MARGIN", 1e-5)
     res = H.run_parity_case(shape="tiny", n_parts=2, model="graphsage", sampling_rate=0.5, n_epochs=2, device="cpu")
     assert res["kink"]["flips"] == 1 and res["max_rel_err"] >= H.KINK_TRIGGER
+
+
+def test_c_spmm_property_random_shapes_vs_dense():
+    """SURVEY §4 pin 4 as a property test (hypothesis): the oracle's C SpMM (oracle/spmm_ref.c, DGL's
+    ``update_all(copy_u, sum)``) and its transpose against a dense 0/1-count matrix product, over random shapes
+    including empty rows, empty graphs, duplicate edges and width-1 features."""
+    from hypothesis import given, settings, strategies as st
+    from oracle import bns_oracle as O
+
+    @settings(max_examples=40, deadline=None)
+    @given(n_src=st.integers(1, 40), n_dst=st.integers(1, 30), n_edges=st.integers(0, 300), width=st.integers(1, 9),
+           seed=st.integers(0, 10 ** 6))
+    def prop(n_src, n_dst, n_edges, width, seed):
+        g = torch.Generator().manual_seed(seed)
+        u = torch.randint(0, n_src, (n_edges,), generator=g)
+        v = torch.randint(0, n_dst, (n_edges,), generator=g)
+        x = torch.randn(n_src, width, generator=g, dtype=torch.float64).float().requires_grad_()
+        a = torch.zeros(n_dst, n_src, dtype=torch.float64)
+        a.index_put_((v, u), torch.ones(n_edges, dtype=torch.float64), accumulate=True)       # multi-edges count
+        y = O.CopyUSum.apply(O.EdgeList(u, v, n_src, n_dst), x)
+        want = a @ x.detach().double()
+        assert y.shape == (n_dst, width)
+        assert (y.detach().double() - want).abs().max() <= 1e-5 * (1 + want.abs().max())
+        w = torch.randn(n_dst, width, generator=g)
+        (y * w).sum().backward()
+        want_g = a.t() @ w.double()
+        assert (x.grad.double() - want_g).abs().max() <= 1e-5 * (1 + want_g.abs().max())
+
+    prop()
