@@ -44,6 +44,14 @@ def METRIC():
     return f"epochs/sec ({WORKLOAD['n_layers']}-layer {WORKLOAD['model']}, {WORKLOAD['shape']}-shape graph)"
 
 
+def workload_string(gstats: dict, world: int) -> str:
+    """`config.workload`, identical in both arms (our CUDA path and `--impl reference`)."""
+    head = "BASELINE configs[1]: " if (WORKLOAD["shape"], WORKLOAD["model"]) == ("reddit", "graphsage") else ""
+    return (f"{head}{WORKLOAD['shape']}-shape synthetic power-law graph, {gstats['n_nodes']} nodes, {gstats['n_edges']} edges, "
+            f"{gstats['n_feat']} feat; {WORKLOAD['model']} {WORKLOAD['n_layers']}-layer hidden {WORKLOAD['n_hidden']} --use-pp, "
+            f"sampling-rate {WORKLOAD['sampling_rate']}, dropout {WORKLOAD['dropout']}, {world} random partition(s)")
+
+
 def load_peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -165,6 +173,16 @@ def run_ours(a):
     # one device per process: run backward on this thread (no hand-off to autograd's device thread; it also keeps
     # the NVTX range below around the backward kernels for the ncu launch list)
     torch.autograd.set_multithreading_enabled(False)
+    # ---------------- parity probe (correctness carried by every bench line, N = 8 included) ------------------
+    # The forward loss of epoch 0 at the initial weights with dropout off, summed over ranks, against (N = 1) the CPU
+    # oracle's value and (N > 1) the same ranks run as threads of one process on rank 0's GPU -- the arrangement
+    # tests/ pins to the oracle, bench shape included (tests/test_bench_shape_gpu.py).
+    probe = None
+    if not a.no_probe:
+        lp = train.probe_loss(st, 0).double().reshape(1)
+        if world > 1:
+            dist.all_reduce(lp)
+        probe = {"loss_epoch0_dropout_off": float(lp.item())}
     epoch = 0
     for _ in range(W):                                   # untimed warm-up
         train.train_epoch(st, epoch)
@@ -195,10 +213,15 @@ def run_ours(a):
         dense_mod.PROFILE = None
         return max_over_ranks(e0.elapsed_time(e1)), lib.bns_launch_count() - c0, pr
 
+    comm_log, reduce_log = [], []
+
     def eager_step():
         nonlocal epoch
         train.train_epoch(st, epoch)
         epoch += 1
+        if world > 1:                                    # Comm(s) / Reduce(s) of EVERY eager epoch (train.py:415-418)
+            comm_log.append(comm_timer.tot_time())
+            reduce_log.append(ctx.reducer.last_reduce_seconds())
 
     # ---------------- eager pass: per-kernel CUDA events (roofline), Comm(s)/Reduce(s) -----------------------
     clocks = ClockSampler(local)
@@ -206,8 +229,9 @@ def run_ours(a):
         clocks.start()
     K_eager = K if a.mode == "eager" else min(K, 5)
     eager_ms, eager_launches, prof = timed(eager_step, K_eager, True)
-    comm_last = max_over_ranks(comm_timer.tot_time()) if world > 1 else 0.0     # Comm(s) of the last epoch
-    reduce_last = max_over_ranks(ctx.reducer.last_reduce_seconds()) if world > 1 else 0.0
+    # Comm(s) / Reduce(s) per epoch: mean over the eager epochs of this rank, then the max over ranks
+    comm_last = max_over_ranks(sum(comm_log) / len(comm_log)) if world > 1 and comm_log else 0.0
+    reduce_last = max_over_ranks(sum(reduce_log) / len(reduce_log)) if world > 1 and reduce_log else 0.0
     launches_per_step = eager_launches / K_eager
     mode = "eager"
     dev_ms, n_launch = eager_ms * K / K_eager, eager_launches * K // K_eager
@@ -258,25 +282,38 @@ def run_ours(a):
 
     for i in range(2):
         consumed[i].record(torch.cuda.current_stream(dev))
+    # the step's result (the loss) goes to pinned host memory with an async copy and is READ one step late: the host
+    # never stalls the queue, every loss is still read inside the timed region (the last one before the clock stops)
+    loss_pin = [torch.zeros(1, dtype=torch.float32).pin_memory() for _ in range(2)]
+    loss_ev = [torch.cuda.Event(), torch.cuda.Event()]
+    losses_read = []
     barrier()
     t0 = time.perf_counter()
     prefetch(0)
     for i in range(K):
         if i + 1 < K:
             prefetch(i + 1)                              # next step's inputs stream in behind this step's compute
-        torch.cuda.current_stream(dev).wait_event(ready[i % 2])
+        cur = torch.cuda.current_stream(dev)
+        cur.wait_event(ready[i % 2])
         if mode == "cuda-graph":                         # the graph reads fixed addresses: stage -> device copy
             feat_dev.copy_(bufs[i % 2][0]); lab_dev.copy_(bufs[i % 2][1]); mask_dev.copy_(bufs[i % 2][2])
-            consumed[i % 2].record(torch.cuda.current_stream(dev))
+            consumed[i % 2].record(cur)
             loss = step_fn()
         else:
             st.feat, st.labels, st.train_mask = bufs[i % 2]
             loss = train.train_epoch(st, epoch)
-            consumed[i % 2].record(torch.cuda.current_stream(dev))
+            consumed[i % 2].record(cur)
             epoch += 1
-        _ = loss.item()                                  # D2H read of the step's result
+        loss_pin[i % 2].copy_(loss.reshape(1), non_blocking=True)      # D2H of the step's result
+        loss_ev[i % 2].record(cur)
+        if i > 0:
+            loss_ev[(i - 1) % 2].synchronize()
+            losses_read.append(float(loss_pin[(i - 1) % 2][0]))
+    loss_ev[(K - 1) % 2].synchronize()
+    losses_read.append(float(loss_pin[(K - 1) % 2][0]))
     barrier()
     e2e_s = max_over_ranks(time.perf_counter() - t0)
+    assert len(losses_read) == K
     st.feat, st.labels, st.train_mask = feat_dev, lab_dev, mask_dev
 
     if a.profile and rank == 0:                            # diagnosis only (kineto); never a reported number
@@ -298,11 +335,27 @@ def run_ours(a):
     host_ms = (time.perf_counter() - th) / 5 * 1e3
     barrier()
 
+    # ---------------- parity probe, reference side (N > 1): the same ranks as threads of ONE process ------------
+    if probe is not None and world > 1:
+        if rank == 0:
+            try:
+                ref = inprocess_probe_loss(a.shape, world, dev)
+                probe.update({"reference": "same ranks as threads of one process on rank 0's GPU (staged transport), "
+                                           "the arrangement tests/ pins to the CPU oracle",
+                              "loss_reference": ref,
+                              "rel_err": abs(probe["loss_epoch0_dropout_off"] - ref) / max(abs(ref), 1e-30)})
+                probe["ok"] = bool(probe["rel_err"] < 1e-5)
+            except Exception as e:                       # noqa: BLE001
+                probe.update({"reference": f"in-process run failed: {type(e).__name__}: {e}", "ok": None})
+        barrier()
     if rank != 0:
         _leave(world)
         return
     peak, peak_src = load_peaks()
     n_spmm = max(len(prof), 1)
+    feat_mb = st.feat.numel() * 4 / 2 ** 20
+    csr_mb = part.graph.num_edges() * 4 * 2 / 2 ** 20
+    ws_mb = feat_mb + csr_mb + 8 * part.graph.n_in * WORKLOAD["n_hidden"] * 4 / 2 ** 20
     # boundary exchange (per rank, per epoch): rows sent forward + gradient rows returned, on every communicating layer
     n_comm_layers = max(WORKLOAD["n_layers"] - 1, 0)
     ex_bytes = 4 * WORKLOAD["n_hidden"] * (sum(st.send_size) + sum(st.recv_size)) * n_comm_layers if world > 1 else 0
@@ -317,16 +370,16 @@ def run_ours(a):
         "metric": METRIC(), "value": K / (dev_ms * 1e-3),
         "unit": "epochs/s", "n_gpus": world, "steps": K, "warmup": W, "ms_per_step": dev_ms / K,
         "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": f"{'BASELINE configs[1]: ' if (WORKLOAD['shape'], WORKLOAD['model']) == ('reddit', 'graphsage') else ''}"
-                               f"{WORKLOAD['shape']}-shape synthetic power-law graph, {gstats['n_nodes']} nodes, "
-                               f"{gstats['n_edges']} edges, {gstats['n_feat']} feat; {WORKLOAD['model']} "
-                               f"{WORKLOAD['n_layers']}-layer hidden {WORKLOAD['n_hidden']} --use-pp, sampling-rate "
-                               f"{WORKLOAD['sampling_rate']}, dropout {WORKLOAD['dropout']}, {world} random partition(s); "
-                               "per-rank inputs exceed L2, no flush needed",
+        "config": {"workload": workload_string(gstats, world),
+                   "l2": f"no flush between timed epochs: one epoch of rank 0 streams {ws_mb:.0f} MB (features "
+                         f"{feat_mb:.0f} MB + CSR and transposes {csr_mb:.0f} MB + activations), L2 is 126 MB",
                    "parallelism": f"partition-parallel x{world}", "exchange": a.backend, "execution": mode,
                    "n_in_rank0": part.graph.n_in, "n_halo_rank0": part.graph.n_halo,
                    "local_edges_rank0": part.graph.num_edges()},
-        "comm_s_per_epoch": comm_last, "reduce_s_per_epoch": reduce_last, "host_enqueue_ms_per_step": host_ms,
+        "comm_s_per_epoch": comm_last, "reduce_s_per_epoch": reduce_last,
+        "comm_note": f"mean over the {K_eager} eager epochs of this run (CUDA events on the comm / reduce streams), max over "
+                     "ranks; the replayed graph runs the same kernels but cannot be timed from inside",
+        "host_enqueue_ms_per_step": host_ms,
         "eager_ms_per_step": eager_ms / K_eager,
         "e2e": {"value": K / e2e_s, "unit": "epochs/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": 4,
                 "note": "features+labels+mask copied from pinned host memory every epoch (prefetched one step ahead on "
@@ -368,7 +421,16 @@ def run_ours(a):
                                          "pipe 46 %, LSU + tensor-core shared-memory wavefronts 53 % + 51 %), see "
                                          "profiles/ncu_gemm3x_r01.md"}
     if world == 1 and not a.no_cpu_baseline:
-        out["cpu_baseline"] = cpu_epochs_per_sec(a.shape, 1, steps=1, warmup=1)
+        out["cpu_baseline"] = cpu_epochs_per_sec(a.shape, 1, steps=1, warmup=1, probe=probe is not None)
+        out["cpu_baseline"].pop("gstats", None)
+        if probe is not None and "probe_loss" in out["cpu_baseline"]:
+            ref = out["cpu_baseline"].pop("probe_loss")
+            probe.update({"reference": "CPU oracle (oracle/bns_oracle.py), forward at the initial weights, dropout off",
+                          "loss_reference": ref,
+                          "rel_err": abs(probe["loss_epoch0_dropout_off"] - ref) / max(abs(ref), 1e-30)})
+            probe["ok"] = bool(probe["rel_err"] < 1e-4)
+    if probe is not None:
+        out["parity_probe"] = probe
     print(json.dumps(out))
     _leave(world)
 
@@ -383,53 +445,159 @@ def _leave(world: int) -> None:
         os._exit(0)
 
 
+def inprocess_probe_loss(shape: str, world: int, dev) -> float:
+    """`train.probe_loss` of epoch 0 with the `world` ranks as threads of this process on `dev` (ThreadComm, staged
+    transport), summed over ranks."""
+    import contextlib
+    from bns_gcn_b200 import train
+    from bns_gcn_b200.data import make_graph, partition_graph
+    from bns_gcn_b200.helper.comm import run_threads
+    fg = make_graph(shape, seed=0, device=dev)
+    parts = partition_graph(fg, world, WORKLOAD["partition"], seed=0, device=dev)
+    del fg
+
+    def fn(comm, r):
+        p = parts[r]
+        args = make_args(world, "nccl", {"n_feat": p.meta["n_feat"], "n_class": p.meta["n_class"],
+                                         "n_train": p.meta["n_train"], "dataset": shape})
+        with contextlib.redirect_stdout(sys.stderr):
+            st = train.setup(p.graph, p.node_dict, p.gpb, args, dev)
+        return float(train.probe_loss(st, 0).double().item())
+
+    return float(sum(run_threads(world, fn, device=str(dev))))
+
+
 # =====================================================================================================
 # CPU arm (the oracle as the reference's stand-in)
 # =====================================================================================================
-def cpu_epochs_per_sec(shape: str, n_parts: int, steps: int, warmup: int, budget_s: float = 150.0) -> dict:
+def _oracle_rank(part, comm):
+    from oracle import bns_oracle as O
+    return O.OracleRank(O.RankInput.from_partition(part), comm, model=WORKLOAD["model"], n_layers=WORKLOAD["n_layers"],
+                        n_hidden=WORKLOAD["n_hidden"], sampling_rate=WORKLOAD["sampling_rate"], use_pp=True,
+                        dropout=WORKLOAD["dropout"], norm=WORKLOAD["norm"], lr=WORKLOAD["lr"], seed=0,
+                        multilabel=(WORKLOAD["shape"] == "yelp"))
+
+
+def _cpu_rank_loop(rk, comm, r, per_rank, steps, warmup, budget_s, probe):
+    """The timed loop of one CPU rank: `warmup` + up to `steps` full epochs between barriers, stopped early (after at
+    least one timed epoch) once `budget_s` is spent.  Returns (per-epoch seconds, probe loss or None)."""
+    import numpy as np
+    torch.set_num_threads(per_rank)          # OpenMP's thread count is per calling thread
+    probe_loss = None
+    if probe:                                # forward at the initial weights, dropout off, the epoch-0 Philox sets
+        sel = None
+        if comm.size > 1:
+            from oracle import philox
+            peers = [j for j in range(comm.size) if j != r]
+            ref = philox.sample_boundary([rk.boundary[j].numpy() for j in peers], [rk.send_size[j] for j in peers], 0, 0)
+            sel = [None] * comm.size
+            for i, j in enumerate(peers):
+                sel[j] = torch.from_numpy(ref[i])
+        probe_loss = rk.epoch(selected=sel, forward_only=True)
+    rng = np.random.RandomState(1234 + r)
+    times = []
+    t_begin = time.perf_counter()
+    for e in range(warmup + steps):
+        comm.barrier()
+        t0 = time.perf_counter()
+        rk.epoch(rng=rng)
+        comm.barrier()
+        dt = time.perf_counter() - t0
+        if e >= warmup:
+            times.append(dt)
+        stop = torch.tensor([1.0 if (time.perf_counter() - t_begin > budget_s and e >= warmup) else 0.0])
+        comm.all_reduce_sum(stop)
+        if float(stop) > 0:
+            break
+    return times, probe_loss
+
+
+def cpu_worker(a):
+    """One gloo process of the CPU arm (spawned by cpu_epochs_per_sec for P > 1): loads its partition from the
+    hand-over directory, joins the gloo group on 127.0.0.1 and runs the timed loop."""
+    import torch.distributed as dist
+    from oracle import bns_oracle as O
+    d = a.cpu_worker
+    with open(os.path.join(d, "job.json")) as f:
+        job = json.load(f)
+    WORKLOAD.update(job["workload"])
+    r, P = a.cpu_rank, job["world"]
+    torch.set_num_threads(job["per_rank"])
+    O.set_threads(job["per_rank"])
+    dist.init_process_group("gloo", init_method=f"tcp://127.0.0.1:{job['port']}", rank=r, world_size=P)
+    part = torch.load(os.path.join(d, f"part{r}.pt"), weights_only=False)
+    comm = O.GlooComm()
+    rk = _oracle_rank(part, comm)
+    times, pl = _cpu_rank_loop(rk, comm, r, job["per_rank"], job["steps"], job["warmup"], job["budget_s"], job["probe"])
+    with open(os.path.join(d, f"out{r}.json"), "w") as f:
+        json.dump({"times": times, "probe_loss": pl}, f)
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def cpu_epochs_per_sec(shape: str, n_parts: int, steps: int, warmup: int, budget_s: float = 150.0,
+                       probe: bool = False) -> dict:
+    """The CPU restatement of the reference (oracle/) on the host cores: P = 1 in this process, P > 1 as P gloo
+    processes on 127.0.0.1 with floor(cores / P) threads each, full epochs of the same workload."""
+    import shutil
+    import tempfile
     from bns_gcn_b200.data import make_graph, partition_graph
     from oracle import bns_oracle as O
-    import numpy as np
     cores = os.cpu_count() or 1
     per_rank = max(1, cores // n_parts)
     torch.set_num_threads(per_rank)          # torchrun exports OMP_NUM_THREADS=1: set both pools explicitly
     O.set_threads(per_rank)
     fg = make_graph(shape, seed=0, device=torch.device("cuda") if torch.cuda.is_available() else None)
+    gstats = {"n_nodes": fg.n_nodes, "n_edges": fg.n_edges, "n_feat": fg.n_feat}
     parts = partition_graph(fg, n_parts, WORKLOAD["partition"], seed=0)
     del fg
-    times = [[] for _ in range(n_parts)]
-
-    def fn(comm, r):
-        torch.set_num_threads(per_rank)      # OpenMP's thread count is per calling thread: set it in every rank thread
-        rk = O.OracleRank(O.RankInput.from_partition(parts[r]), comm, model=WORKLOAD["model"],
-                          n_layers=WORKLOAD["n_layers"], n_hidden=WORKLOAD["n_hidden"],
-                          sampling_rate=WORKLOAD["sampling_rate"], use_pp=True, dropout=WORKLOAD["dropout"],
-                          norm=WORKLOAD["norm"], lr=WORKLOAD["lr"], seed=0, multilabel=(WORKLOAD["shape"] == "yelp"))
-        rng = np.random.RandomState(1234 + r)
-        t_begin = time.perf_counter()
-        for e in range(warmup + steps):
-            comm.barrier()
-            t0 = time.perf_counter()
-            rk.epoch(rng=rng)
-            comm.barrier()
-            dt = time.perf_counter() - t0
-            if e >= warmup:
-                times[r].append(dt)
-            # stay inside the time budget: a bounded sample of full epochs
-            stop = torch.tensor([1.0 if (time.perf_counter() - t_begin > budget_s and e >= warmup) else 0.0])
-            comm.all_reduce_sum(stop)
-            if float(stop) > 0:
-                break
-        return len(times[r])
-
-    done = O.run_threads(n_parts, fn)[0]
-    per_epoch = [max(times[r][i] for r in range(n_parts)) for i in range(done)]
+    if n_parts == 1:
+        comm = O.SoloComm()
+        per_rank_times, pl = _cpu_rank_loop(_oracle_rank(parts[0], comm), comm, 0, per_rank, steps, warmup, budget_s, probe)
+        all_times, probe_loss, how = [per_rank_times], pl, "this process"
+    else:
+        d = tempfile.mkdtemp(prefix="bns_cpu_arm_")
+        try:
+            for r, p_ in enumerate(parts):
+                torch.save(p_, os.path.join(d, f"part{r}.pt"))
+            del parts
+            import socket
+            with socket.socket() as sk:
+                sk.bind(("127.0.0.1", 0))
+                port = sk.getsockname()[1]
+            with open(os.path.join(d, "job.json"), "w") as f:
+                json.dump({"world": n_parts, "per_rank": per_rank, "steps": steps, "warmup": warmup, "budget_s": budget_s,
+                           "probe": probe, "port": port, "workload": WORKLOAD}, f)
+            env = {k: v for k, v in os.environ.items()
+                   if k not in ("RANK", "LOCAL_RANK", "WORLD_SIZE", "MASTER_ADDR", "MASTER_PORT", "TORCHELASTIC_RUN_ID",
+                                "OMP_NUM_THREADS", "GROUP_RANK", "ROLE_RANK", "LOCAL_WORLD_SIZE")}
+            env["OMP_NUM_THREADS"] = str(per_rank)
+            env["CUDA_VISIBLE_DEVICES"] = ""             # the CPU arm never touches a GPU
+            procs = [subprocess.Popen([sys.executable, os.path.abspath(__file__), "--cpu-worker", d, "--cpu-rank", str(r)],
+                                      env=env, stdout=sys.stderr, stderr=sys.stderr) for r in range(n_parts)]
+            rcs = [p_.wait() for p_ in procs]
+            if any(rcs):
+                raise RuntimeError(f"CPU arm: worker exit codes {rcs}")
+            outs = []
+            for r in range(n_parts):
+                with open(os.path.join(d, f"out{r}.json")) as f:
+                    outs.append(json.load(f))
+            all_times = [o["times"] for o in outs]
+            probe_loss = sum(o["probe_loss"] for o in outs) if probe else None
+            how = f"{n_parts} gloo processes on 127.0.0.1"
+        finally:
+            shutil.rmtree(d, ignore_errors=True)
+    done = min(len(t) for t in all_times)
+    per_epoch = [max(t[i] for t in all_times) for i in range(done)]
     mean = sum(per_epoch) / len(per_epoch)
-    return {"value": 1.0 / mean, "unit": "epochs/s", "cores": cores, "kind": "port",
-            "sample": f"{done} full epoch(s) of the same workload ({n_parts} partition(s) as in-process ranks) after "
-                      f"{warmup} warm-up, oracle/bns_oracle.py + oracle/spmm_ref.c (OpenMP), {cores} host threads "
-                      f"({per_rank} per rank)",
-            "seconds_per_epoch": mean}
+    res = {"value": 1.0 / mean, "unit": "epochs/s", "cores": cores, "kind": "port",
+           "sample": f"{done} full epoch(s) of the same workload ({how}) after {warmup} warm-up, oracle/bns_oracle.py + "
+                     f"oracle/spmm_ref.c (OpenMP), {cores} host threads ({per_rank} per rank)",
+           "seconds_per_epoch": mean, "epochs_timed": done, "seconds_per_epoch_min": min(per_epoch),
+           "seconds_per_epoch_median": statistics.median(per_epoch), "gstats": gstats}
+    if probe_loss is not None:
+        res["probe_loss"] = probe_loss
+    return res
 
 
 def run_reference(a):
@@ -438,12 +606,16 @@ def run_reference(a):
         return
     K, W = a.steps, a.warmup
     res = cpu_epochs_per_sec(a.shape, a.gpus, steps=K, warmup=min(W, 1))
+    gstats = res.pop("gstats")
+    done = res["epochs_timed"]
     out = {"impl": "reference", "metric": METRIC(), "value": res["value"],
-           "unit": "epochs/s", "n_gpus": a.gpus, "steps": K, "warmup": W, "ms_per_step": 1e3 * res["seconds_per_epoch"],
+           "unit": "epochs/s", "n_gpus": a.gpus, "steps": done, "steps_requested": K, "warmup": min(W, 1),
+           "ms_per_step": 1e3 * res["seconds_per_epoch"],
            "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-           "config": {"workload": f"BASELINE configs[1] on host cores: Reddit-shape synthetic graph, GraphSAGE 3-layer "
-                                  f"hidden 256 --use-pp, sampling-rate 0.1, dropout 0.5, {a.gpus} random partition(s)",
-                      "parallelism": f"{a.gpus} in-process rank(s), OpenMP SpMM"},
+           "config": {"workload": workload_string(gstats, a.gpus),
+                      "parallelism": f"host cores: {a.gpus} rank(s), OpenMP SpMM + torch CPU f32",
+                      "note": "steps = epochs actually timed inside the 150 s budget (each epoch is a full pass of the "
+                              "same workload); steps_requested = --steps"},
            "cpu_baseline": res,
            "e2e": {"value": res["value"], "unit": "epochs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(out))
@@ -469,7 +641,13 @@ def main():
     ap.add_argument("--n-hidden", type=int, default=None)
     ap.add_argument("--rate", type=float, default=None)
     ap.add_argument("--dropout", type=float, default=None)
+    ap.add_argument("--no-probe", action="store_true", help="skip the parity probe")
+    ap.add_argument("--cpu-worker", default="", help=argparse.SUPPRESS)      # internal: one gloo process of the CPU arm
+    ap.add_argument("--cpu-rank", type=int, default=0, help=argparse.SUPPRESS)
     a = ap.parse_args()
+    if a.cpu_worker:
+        cpu_worker(a)
+        return
     for k, v in (("model", a.model), ("n_layers", a.n_layers), ("n_hidden", a.n_hidden), ("sampling_rate", a.rate),
                  ("dropout", a.dropout), ("shape", a.shape)):
         if v is not None:

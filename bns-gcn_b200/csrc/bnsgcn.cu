@@ -53,17 +53,29 @@ constexpr int kWarps = kThreads / 32;
 constexpr int kDefaultChunk = 256;   // B200 sweep (profiles/spmm_chunk_sweep_r1.txt): 256 -> 7.39 ms, 512 -> 7.58, 1024 -> 8.34, 2048 -> 9.27
 
 std::atomic<unsigned long long> g_launches{0};   // kernels of this library enqueued so far (bench.py gpu_launches)
-int g_sm_count = 0;
+
+// Per-DEVICE properties (ranks that live as threads of one process may sit on different GPUs).
+constexpr int kMaxDevices = 64;
+struct DeviceProps {
+    std::atomic<int> sms{0};
+    std::atomic<long long> l2{0};
+};
+DeviceProps g_dev[kMaxDevices];
+
+int current_device() {
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= kMaxDevices) dev = 0;
+    return dev;
+}
+
 int sm_count() {
-    if (g_sm_count == 0) {
-        int dev = 0, n = 0;
-        if (cudaGetDevice(&dev) == cudaSuccess &&
-            cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) == cudaSuccess && n > 0)
-            g_sm_count = n;
-        else
-            g_sm_count = 148;
+    const int dev = current_device();
+    int n = g_dev[dev].sms.load(std::memory_order_relaxed);
+    if (n == 0) {
+        if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) n = 148;
+        g_dev[dev].sms.store(n, std::memory_order_relaxed);
     }
-    return g_sm_count;
+    return n;
 }
 
 }  // namespace
@@ -272,7 +284,10 @@ extern "C" int bns_graph_create(bns_graph_t **out, int64_t n_rows, int64_t n_col
         cudaMemcpyAsync(&ends[0], g->indptr, sizeof(int64_t), cudaMemcpyDeviceToHost, st);
         cudaMemcpyAsync(&ends[1], g->indptr + n_rows, sizeof(int64_t), cudaMemcpyDeviceToHost, st);
         int *bad = nullptr, hbad = 0;
-        cudaMalloc(&bad, sizeof(int));
+        if (cudaMalloc(&bad, sizeof(int)) != cudaSuccess) {
+            rc = fail(BNS_E_CUDA, "bns_graph_create: cudaMalloc failed: %s", cudaGetErrorString(cudaGetLastError()));
+            break;
+        }
         cudaMemsetAsync(bad, 0, sizeof(int), st);
         if (nnz) check_indices_kernel<<<(unsigned)((nnz + 255) / 256), 256, 0, st>>>(g->indices, nnz, n_cols, bad);
         cudaMemcpyAsync(&hbad, bad, sizeof(int), cudaMemcpyDeviceToHost, st);
@@ -619,13 +634,16 @@ __global__ void __launch_bounds__(kThreads) spmm_fixup_kernel(SpmmArgs a) {
 
 template <int W, int G, int NV, bool MAP, bool CSCALE, bool GUARD>
 int launch_spmm(SpmmArgs a, cudaStream_t st) {
-    static int blocks_per_sm = 0;
+    static std::atomic<int> occ[kMaxDevices];            // per device, per instantiation
+    const int dev = current_device();
+    int blocks_per_sm = occ[dev].load(std::memory_order_relaxed);
     if (blocks_per_sm == 0) {
         int n = 0;
         if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, spmm_kernel<W, G, NV, MAP, CSCALE, GUARD>, kThreads, 0) !=
                 cudaSuccess || n < 1)
             n = 2;
         blocks_per_sm = n;
+        occ[dev].store(n, std::memory_order_relaxed);
     }
     constexpr int SLAB = G * W * NV;
     a.n_tiles = (a.F + SLAB - 1) / SLAB;
@@ -666,17 +684,15 @@ int dispatch_flags(const SpmmArgs &a, cudaStream_t st) {
 
 inline int64_t ws_ld(int64_t F) { return (F + 3) / 4 * 4; }
 
-int64_t g_l2_bytes = 0;
 int64_t l2_bytes() {
-    if (g_l2_bytes == 0) {
-        int dev = 0, v = 0;
-        if (cudaGetDevice(&dev) == cudaSuccess && cudaDeviceGetAttribute(&v, cudaDevAttrL2CacheSize, dev) == cudaSuccess &&
-            v > 0)
-            g_l2_bytes = v;
-        else
-            g_l2_bytes = 126ll << 20;
+    const int dev = current_device();
+    long long v = g_dev[dev].l2.load(std::memory_order_relaxed);
+    if (v == 0) {
+        int b = 0;
+        v = (cudaDeviceGetAttribute(&b, cudaDevAttrL2CacheSize, dev) == cudaSuccess && b > 0) ? b : (126ll << 20);
+        g_dev[dev].l2.store(v, std::memory_order_relaxed);
     }
-    return g_l2_bytes;
+    return v;
 }
 
 // Widest column slab (in floats: 256, 128, 64 or 32) whose source slab  x_rows * slab * 4 B  fits the L2 budget.
@@ -1667,7 +1683,7 @@ extern "C" int bns_p2p_put_rows_f32(bns_p2p_t *p, int32_t peer, size_t remote_of
     BNS_REQUIRE(p->peer_slab[peer] && p->peer_flags[peer], "bns_p2p_put_rows_f32: peer %d not connected", peer);
     BNS_REQUIRE(flag_index >= 0 && flag_index < p->n_flags, "bns_p2p_put_rows_f32: bad flag index");
     BNS_REQUIRE(k >= 0 && F > 0 && ldh >= F && ld_remote >= F, "bns_p2p_put_rows_f32: bad shape");
-    BNS_REQUIRE(div != 0.f, "bns_p2p_put_rows_f32: division by zero");
+    BNS_REQUIRE(k == 0 || div != 0.f, "bns_p2p_put_rows_f32: division by zero");   // k == 0 still publishes the flag
     BNS_REQUIRE(remote_off % 16 == 0 && remote_off + (size_t)k * ld_remote * 4 <= p->peer_slab_bytes[peer],
                 "bns_p2p_put_rows_f32: remote range [%zu, +%lld rows) outside peer %d's slab (%zu bytes)", remote_off,
                 (long long)k, peer, p->peer_slab_bytes[peer]);

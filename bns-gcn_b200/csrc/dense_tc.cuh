@@ -416,14 +416,11 @@ inline bool trunc_mode() {
 
 template <bool kMN, bool kTrunc>
 int configure() {
-    static bool done = false;      // per process; the attribute is per function, set once per device context in practice
-    static int dev_done = -1;
-    int dev = 0;
-    BNS_CUDA(cudaGetDevice(&dev));
-    if (!done || dev_done != dev) {
+    static std::atomic<int> done[kMaxDevices];      // the attribute is per function AND per device
+    const int dev = current_device();
+    if (!done[dev].load(std::memory_order_acquire)) {
         BNS_CUDA(cudaFuncSetAttribute(gemm3x_kernel<kMN, kTrunc>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
-        done = true;
-        dev_done = dev;
+        done[dev].store(1, std::memory_order_release);
     }
     return BNS_OK;
 }

@@ -36,12 +36,14 @@ class PartitionGraph:
 
     def recip(self, t: torch.Tensor) -> torch.Tensor:
         """``1 / t`` as f32, cached per source tensor (degree / norm vectors are static)."""
-        key = (t.data_ptr(), t.numel(), t.dtype)
-        r = self._recip.get(key)
-        if r is None:
-            r = (1.0 / t.to(torch.float32)).contiguous()
-            self._recip[key] = r
-        return r
+        # keyed on the tensor OBJECT (kept alive here, so its id cannot be recycled) and its in-place version counter:
+        # a freed-and-reallocated buffer at the same address, or a norm updated in place, never returns a stale value
+        key = id(t)
+        hit = self._recip.get(key)
+        if hit is None or hit[0] is not t or hit[1] != t._version:
+            hit = (t, t._version, (1.0 / t.to(torch.float32)).contiguous())
+            self._recip[key] = hit
+        return hit[2]
 
 
 class FullGraphHandle:

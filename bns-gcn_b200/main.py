@@ -28,6 +28,12 @@ def init_processes(rank, size, args):
     torch.cuda.set_device(local)
     dev = torch.device('cuda', local)
     dist.init_process_group('nccl', rank=rank, world_size=size, device_id=dev)
+    # Without --fix-seed every process drew its own args.seed (main(): random.randint).  The weights are created from
+    # it on every rank and never broadcast (only gradients are all-reduced), so the replicas must agree on it:
+    # rank 0's seed wins.  (The mp.spawn path pickles one args object to all ranks; under torchrun each rank ran main().)
+    seed = [int(args.seed)]
+    dist.broadcast_object_list(seed, src=0)
+    args.seed = int(seed[0])
     if getattr(args, '_partition_in_job', False):          # torchrun: nobody partitioned before the ranks started
         if rank == 0:
             graph_partition(args, device=dev)

@@ -291,7 +291,32 @@ def halo_slot_update(pos: torch.Tensor, one_hops: torch.Tensor, n_in: int, slab_
 # ---- fused LayerNorm -> ReLU -> dropout --------------------------------------------------------------------------
 # Philox stream of the dropout masks: (seed, offset [+ *offset_dev]); train.train_epoch sets it once per epoch
 # (offset = epoch index; under CUDA-graph replay the epoch index comes from the device counter).
-RNG = {"seed": 0, "offset": 0, "offset_dev": None}
+class _ThreadLocalRng:
+    """dict-like, one instance per thread: ranks that live as threads of one process (tests, smoke, 1-GPU emulation)
+    each set their own (seed, offset) in train.train_epoch and must not see each other's."""
+    _DEFAULT = {"seed": 0, "offset": 0, "offset_dev": None}
+
+    def __init__(self):
+        import threading
+        self._tls = threading.local()
+
+    def _d(self):
+        d = getattr(self._tls, "d", None)
+        if d is None:
+            d = self._tls.d = dict(self._DEFAULT)
+        return d
+
+    def __getitem__(self, k):
+        return self._d()[k]
+
+    def __setitem__(self, k, v):
+        self._d()[k] = v
+
+    def update(self, **kw):
+        self._d().update(kw)
+
+
+RNG = _ThreadLocalRng()
 _LN_WS: Dict[tuple, torch.Tensor] = {}
 
 

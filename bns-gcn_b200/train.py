@@ -333,9 +333,8 @@ def setup(graph: LocalGraph, node_dict, gpb, args, device=None) -> TrainState:
                       train_idx=torch.nonzero(node_dict['train_mask'], as_tuple=True)[0])
 
 
-def train_epoch(st: TrainState, epoch: int, selected: Optional[list] = None) -> torch.Tensor:
-    """One pass of the epoch body (train.py:388-413).  Returns the local sum-reduced loss (device scalar).
-    ``selected`` injects the sampled sets (parity runs); by default they come from the Philox sampler."""
+def _forward_logits(st: TrainState, epoch: int, selected: Optional[list] = None) -> torch.Tensor:
+    """train.py:388-402: sample the boundary, exchange the ids, refresh the graph, run the model (training mode)."""
     rank, size = _rank_size()
     args = st.args
     st.epoch_dev.add_(1)
@@ -362,13 +361,18 @@ def train_epoch(st: TrainState, epoch: int, selected: Optional[list] = None) -> 
     g = construct_graph(st.part, None, st.pos, one_hops)                                        # K7
     st.model.train()
     if args.model == 'gcn':
-        logits = st.model(g, st.feat, st.in_norm, st.out_norm)
+        return st.model(g, st.feat, st.in_norm, st.out_norm)
     elif args.model == 'graphsage':
-        logits = st.model(g, st.feat, st.in_norm)
+        return st.model(g, st.feat, st.in_norm)
     elif args.model == 'gat':
-        logits = st.model(g, construct_feat(g.num_nodes('_V'), st.feat, st.pos, one_hops))     # train.py:401-402
-    else:
-        raise NotImplementedError
+        return st.model(g, construct_feat(g.num_nodes('_V'), st.feat, st.pos, one_hops))        # train.py:401-402
+    raise NotImplementedError
+
+
+def train_epoch(st: TrainState, epoch: int, selected: Optional[list] = None) -> torch.Tensor:
+    """One pass of the epoch body (train.py:388-413).  Returns the local sum-reduced loss (device scalar).
+    ``selected`` injects the sampled sets (parity runs); by default they come from the Philox sampler."""
+    logits = _forward_logits(st, epoch, selected)
     # train.py:406 indexes with the boolean mask; the equivalent index list avoids a host sync per epoch
     loss = st.loss_fcn(logits[st.train_idx], st.labels[st.train_idx])
     st.optimizer.zero_grad(set_to_none=True)
@@ -376,6 +380,25 @@ def train_epoch(st: TrainState, epoch: int, selected: Optional[list] = None) -> 
     ctx.reducer.synchronize()
     st.optimizer.step()
     st.last_logits = logits
+    return loss.detach()
+
+
+def probe_loss(st: TrainState, epoch: int = 0, selected: Optional[list] = None) -> torch.Tensor:
+    """The training-mode forward of ``epoch`` with every dropout switched off: no backward, no update, the epoch
+    counter restored.  A loss that the CPU oracle (``OracleRank.epoch(forward_only=True)``) and any other arrangement
+    of the same ranks (threads of one process / one process per GPU) must reproduce whatever the dropout rate of the
+    run is -- bench.py prints it as ``parity_probe``."""
+    drops = [(m, m.p) for m in st.model.modules() if isinstance(m, torch.nn.Dropout)]
+    for m, _ in drops:
+        m.p = 0.0
+    try:
+        with torch.no_grad():
+            logits = _forward_logits(st, epoch, selected)
+            loss = st.loss_fcn(logits[st.train_idx], st.labels[st.train_idx])
+    finally:
+        for m, p_ in drops:
+            m.p = p_
+        st.epoch_dev.sub_(1)
     return loss.detach()
 
 

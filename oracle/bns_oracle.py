@@ -500,8 +500,11 @@ class OracleRank:
 
     # ---- train.py:385-425 ---------------------------------------------------------------------
     def epoch(self, selected: Optional[list] = None, rng: Optional[np.random.RandomState] = None,
-              step: bool = True, trace: bool = False, relu_masks: Optional[Dict[int, torch.Tensor]] = None) -> float:
+              step: bool = True, trace: bool = False, relu_masks: Optional[Dict[int, torch.Tensor]] = None,
+              forward_only: bool = False) -> float:
         """One training epoch; returns the local (sum-reduced) loss.  ``selected`` injects the sampled sets.
+        ``forward_only``: the training-mode forward with every dropout switched off, no backward, no update (bench.py's
+        ``parity_probe``: a loss both sides can compute at the initial weights whatever the dropout rate is).
 
         ``relu_masks`` ({norm index i: bool [n_in, F]}): the active set another implementation of the SAME forward took
         at the ReLU after norm i.  Gradient parity is only defined on a common active set: where a pre-activation sits
@@ -522,18 +525,19 @@ class OracleRank:
         g = self.construct_graph(one_hops)
         self.graph = g
         self.net.train()
-        if self.model_name == "gcn":
-            parts = [self.out_norm[:self.n_in]] + [self.out_norm[self.pos[i][one_hops[i]]]
-                                                   for i in range(self.size) if i != self.rank]   # train.py:245-253
-            logits = self.net(g, self.feat, self.in_norm, torch.cat(parts))
-        elif self.model_name == "gat":
-            res = [self.feat[0:self.n_in]]                                                   # construct_feat, train.py:284-297
-            for i in range(self.size):
-                if i != self.rank and one_hops[i].shape[0] > 0:
-                    res.append(self.feat[self.pos[i][one_hops[i]]])
-            logits = self.net(g, torch.cat(res))
-        else:
-            logits = self.net(g, self.feat, self.in_norm)
+        if forward_only:
+            drops = [(m, m.p) for m in self.net.modules() if isinstance(m, nn.Dropout)]
+            for m, _ in drops:
+                m.p = 0.0
+            try:
+                with torch.no_grad():
+                    logits = self._forward_logits(g, one_hops)
+            finally:
+                for m, p_ in drops:
+                    m.p = p_
+            mask = self.inp.train_mask
+            return float(self.loss_fn(logits[mask], self.inp.label[mask]).item())
+        logits = self._forward_logits(g, one_hops)
         mask = self.inp.train_mask
         loss = self.loss_fn(logits[mask], self.inp.label[mask])
         self.opt.zero_grad(set_to_none=True)
@@ -549,6 +553,21 @@ class OracleRank:
         if trace:
             self.trace["logits"] = logits.detach().clone()
         return float(loss.item())
+
+    def _forward_logits(self, g, one_hops):
+        if self.model_name == "gcn":
+            parts = [self.out_norm[:self.n_in]] + [self.out_norm[self.pos[i][one_hops[i]]]
+                                                   for i in range(self.size) if i != self.rank]   # train.py:245-253
+            logits = self.net(g, self.feat, self.in_norm, torch.cat(parts))
+        elif self.model_name == "gat":
+            res = [self.feat[0:self.n_in]]                                                   # construct_feat, train.py:284-297
+            for i in range(self.size):
+                if i != self.rank and one_hops[i].shape[0] > 0:
+                    res.append(self.feat[self.pos[i][one_hops[i]]])
+            logits = self.net(g, torch.cat(res))
+        else:
+            logits = self.net(g, self.feat, self.in_norm)
+        return logits
 
 
 class _Exchange(torch.autograd.Function):

@@ -81,6 +81,64 @@ def test_spmm_plain(built, F):
     assert empty.any() and torch.all(y[empty] == 0)
 
 
+@pytest.mark.parametrize("F", [256, 604, 128, 44])
+@pytest.mark.parametrize("slab", [0, 256, 128, 64, 32])
+def test_spmm_every_slab_variant(built, F, slab):
+    """Every column-slab instantiation of spmm_kernel against oracle/spmm_ref.c -- including the ones the default
+    heuristic only picks on graphs too large for a unit test: <4,32,1> with n_tiles > 1 (F = 256 as two 128-float slabs,
+    the instantiation behind the headline bench number), <4,16,1> and <4,8,1> multi-tile (sub-warp row groups), with the
+    GUARD path where the slab does not divide F (604, 44).  Rows longer than one chunk exercise the partial sums."""
+    from bns_gcn_b200 import ops
+    dev = torch.device("cuda:0")
+    indptr, idx = _rand_csr(900, 1100, 14, seed=F + slab, heavy=3)
+    x = torch.randn(1100, F, generator=torch.Generator().manual_seed(F + slab + 1))
+    g = ops.DeviceGraph.from_csr(indptr.to(dev), idx.int().to(dev), 1100)
+    assert g.n_split_rows >= 3
+    y = ops.spmm(g, x.to(dev), slab=slab).cpu()
+    ref = _ref_spmm(indptr, idx, x)
+    assert _relerr(y, ref) < RTOL
+    # full-warp slabs (256 / 128) keep the per-row summation order of the unblocked kernel: bit-identical; sub-warp
+    # row groups (64 / 32) sum the entries of a chunk in a different order: equal to rounding
+    y_full = ops.spmm(g, x.to(dev), slab=256).cpu()
+    if slab in (128, 256):
+        assert torch.equal(y, y_full)
+    else:
+        assert _relerr(y, y_full) < 1e-6
+
+
+@pytest.mark.parametrize("slab", [256, 128, 64])
+@pytest.mark.parametrize("F", [256, 604, 128])
+def test_spmm_slab_variants_with_maps_scales_accumulate(built, F, slab):
+    """The per-epoch forms (slot-mapped halo columns + col/row scales + accumulate; row-mapped backward) under a forced
+    slab: the MAP / CSCALE instantiations of the blocked kernels."""
+    from bns_gcn_b200 import ops
+    dev = torch.device("cuda:0")
+    gen = torch.Generator().manual_seed(31 + F + slab)
+    n_rows, n_direct, n_halo, n_slab = 500, 500, 420, 150
+    indptr, idx = _rand_csr(n_rows, n_direct + n_halo, 18, seed=F + slab, heavy=2)
+    slot = torch.full((n_halo,), -1, dtype=torch.int32)
+    chosen = torch.randperm(n_halo, generator=gen)[:n_slab]
+    slot[chosen] = torch.randperm(n_slab, generator=gen).int()
+    x = torch.randn(n_direct + n_slab, F, generator=gen)
+    cs = torch.rand(n_direct + n_halo, generator=gen) + 0.5
+    rs = torch.rand(n_rows, generator=gen) + 0.5
+    col_map = torch.where(slot >= 0, slot + n_direct, slot)
+    g = ops.DeviceGraph.from_csr(indptr.to(dev), idx.int().to(dev), n_direct + n_halo)
+    y0 = torch.randn(n_rows, F, generator=gen)
+    y = y0.clone().to(dev)
+    ops.spmm(g, x.to(dev), y, row_scale=rs.to(dev), col_scale=cs.to(dev), col_map=col_map.to(dev),
+             n_direct=n_direct, accumulate=True, slab=slab)
+    ref = _ref_spmm(indptr, idx, x, row_scale=rs, col_scale=cs, col_map=col_map, n_direct=n_direct) + y0
+    assert _relerr(y.cpu(), ref) < RTOL
+    ind2, idx2 = _rand_csr(n_halo, n_rows, 20, seed=F + slab + 100, heavy=1, empty_frac=0.0)
+    dy = torch.randn(n_rows, F, generator=gen)
+    g2 = ops.DeviceGraph.from_csr(ind2.to(dev), idx2.int().to(dev), n_rows)
+    out = torch.full((n_slab, F), 7.0, device=dev)
+    ops.spmm(g2, dy.to(dev), out, row_map=slot.to(dev), row_scale=cs[n_direct:].to(dev), slab=slab)
+    ref2 = _ref_spmm(ind2, idx2, dy, row_scale=cs[n_direct:], row_map=slot, n_out=n_slab)
+    assert _relerr(out.cpu(), ref2) < RTOL
+
+
 def test_spmm_roundtrip_csr_and_transpose(built):
     from bns_gcn_b200 import ops
     dev = torch.device("cuda:0")

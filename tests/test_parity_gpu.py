@@ -113,9 +113,6 @@ def test_cuda_path_reproduces_reference_golden(built, name):
             assert _relerr(o["grads"][k], gg) < TOL, (r, nm)
 
 
-@pytest.mark.xfail(strict=False, reason="kink-aware retry: harness logic is CPU-tested with a stub product "
-                                       "(tests/test_oracle_cpu.py); its CUDA-side mask capture was written after the "
-                                       "round's GPU budget ended and has not run on hardware yet")
 def test_training_parity_through_a_relu_kink(built):
     """The graph_seed=0 twin of the test above: epoch 2 has one LayerNorm output at -2.8e-6 on rank 0 and the CUDA
     forward takes the other side of the ReLU kink.  run_parity_case must notice the mismatch, re-run both sides on the
@@ -263,10 +260,6 @@ def test_gat_training_parity(built, kw):
     _run(shape=shape, model="gat", n_epochs=2, multilabel=(shape == "tiny-ml"), **kw)
 
 
-@pytest.mark.xfail(strict=False, reason="written after the round's GPU budget ended: the host pieces (checkpoint names / "
-                                       "keys, accuracy, result lines) are CPU-tested in tests/test_store_eval_cpu.py and "
-                                       "the full-graph forward by test_eval_branch_full_graph; this end-to-end wiring "
-                                       "has not run on hardware yet -- drop the marker once it has")
 def test_run_with_eval_writes_checkpoints_and_results(built, tmp_path, monkeypatch):
     """train.run with --eval (train.py:427-456): every log_every epochs rank 0 saves a checkpoint, evaluates on the full
     graph with the same kernels and appends the result line; at the end the best model is saved and tested."""
