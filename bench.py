@@ -179,10 +179,7 @@ def run_ours(a):
     # tests/ pins to the oracle, bench shape included (tests/test_bench_shape_gpu.py).
     probe = None
     if not a.no_probe:
-        lp = train.probe_loss(st, 0).double().reshape(1)
-        if world > 1:
-            dist.all_reduce(lp)
-        probe = {"loss_epoch0_dropout_off": float(lp.item())}
+        probe = {"loss_epoch0_dropout_off": float(train.probe_loss(st, 0).item())}     # summed over ranks inside
     epoch = 0
     for _ in range(W):                                   # untimed warm-up
         train.train_epoch(st, epoch)
@@ -462,9 +459,9 @@ def inprocess_probe_loss(shape: str, world: int, dev) -> float:
                                          "n_train": p.meta["n_train"], "dataset": shape})
         with contextlib.redirect_stdout(sys.stderr):
             st = train.setup(p.graph, p.node_dict, p.gpb, args, dev)
-        return float(train.probe_loss(st, 0).double().item())
+        return float(train.probe_loss(st, 0).item())          # already the sum over the ranks
 
-    return float(sum(run_threads(world, fn, device=str(dev))))
+    return float(run_threads(world, fn, device=str(dev))[0])
 
 
 # =====================================================================================================

@@ -8,13 +8,32 @@ from __future__ import annotations
 
 import ctypes
 import os
-from ctypes import POINTER, c_char_p, c_float, c_int, c_int32, c_int64, c_size_t, c_uint64, c_void_p
+from ctypes import POINTER, Structure, c_char_p, c_float, c_int, c_int32, c_int64, c_size_t, c_uint64, c_void_p
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "csrc", "libbnsgcn.so")
 
-ABI_VERSION = 1
+ABI_VERSION = 2
 P2P_HANDLE_BYTES = 64
+
+MAX_PEERS = 16      # BNS_MAX_PEERS
+
+
+class EpochMaps(Structure):          # bns_epoch_maps
+    _fields_ = [("n_seg", c_int32), ("sel_begin", c_int64 * (MAX_PEERS + 1)), ("hop_begin", c_int64 * (MAX_PEERS + 1)),
+                ("pos", c_void_p * MAX_PEERS), ("inv", c_void_p * MAX_PEERS), ("selected_cat", c_void_p),
+                ("one_hops_cat", c_void_p), ("slot", c_void_p), ("n_in", c_int64)]
+
+
+class PutAll(Structure):             # bns_put_all
+    _fields_ = [("n_seg", c_int32), ("row_begin", c_int64 * (MAX_PEERS + 1)), ("peer", c_int32 * MAX_PEERS),
+                ("remote_off", c_uint64 * MAX_PEERS), ("src_begin", c_int64 * MAX_PEERS), ("div", c_float * MAX_PEERS)]
+
+
+class DeriveEntry(Structure):        # bns_derive_entry
+    _fields_ = [("op", c_int32), ("rows", c_int32), ("cols", c_int32), ("ld_a", c_int32), ("ld_dst", c_int32),
+                ("pad_", c_int32), ("a", c_void_p), ("b", c_void_p), ("dst", c_void_p)]
+
 
 # name -> (restype, argtypes); must list every function of include/bnsgcn.h (tests check this)
 SIGNATURES = {
@@ -49,10 +68,10 @@ SIGNATURES = {
                                             c_int64, c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),
     "bns_split_tf32_f32": (c_int, [c_void_p, c_int64, c_void_p, c_void_p, c_void_p]),
     "bns_split_bf16x3_f32": (c_int, [c_void_p, c_int64, c_void_p, c_void_p, c_void_p, c_void_p]),
-    "bns_dense_tn_3xtf32": (c_int, [c_void_p, c_int64, c_void_p, c_int64, c_void_p, c_void_p, c_int64, c_void_p, c_int64,
-                                    c_int64, c_int64, c_int64, c_void_p]),
+    "bns_dense_tn_3xtf32": (c_int, [c_void_p, c_int64, c_void_p, c_int64, c_void_p, c_void_p, c_int64, c_void_p, c_void_p,
+                                    c_int64, c_int64, c_int64, c_int64, c_void_p]),
     "bns_colsum_workspace_bytes": (c_size_t, [c_int64]),
-    "bns_colsum_f32": (c_int, [c_void_p, c_int64, c_int64, c_int64, c_void_p, c_void_p, c_size_t, c_void_p]),
+    "bns_colsum_f32": (c_int, [c_void_p, c_int64, c_int64, c_int64, c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),
     "bns_dense_nt_workspace_bytes": (c_size_t, [c_int64, c_int64, c_int64]),
     "bns_dense_nt_3xtf32": (c_int, [c_void_p, c_int64, c_void_p, c_int64, c_void_p, c_int64, c_int64, c_int64, c_int64,
                                     c_void_p, c_size_t, c_void_p]),
@@ -67,6 +86,28 @@ SIGNATURES = {
     "bns_p2p_put_rows_f32": (c_int, [c_void_p, c_int32, c_size_t, c_int64, c_void_p, c_int64, c_int64, c_void_p,
                                      c_int64, c_float, c_int32, c_uint64, c_void_p, c_void_p]),
     "bns_p2p_wait_flag": (c_int, [c_void_p, c_int32, c_uint64, c_void_p, c_void_p]),
+    # ---- ABI 2 ----
+    "bns_epoch_maps_update": (c_int, [POINTER(EpochMaps), c_void_p, c_size_t, c_void_p]),
+    "bns_graph_compact_cols": (c_int, [c_void_p, c_void_p, c_int64, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
+    "bns_spmm_compact_f32": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int64, c_void_p, c_int64,
+                                     c_void_p, c_int64, c_int32, c_int, c_void_p, c_size_t, c_void_p]),
+    "bns_p2p_put_all_f32": (c_int, [c_void_p, POINTER(PutAll), c_int64, c_void_p, c_int64, c_int64, c_void_p, c_int32,
+                                    c_int32, c_uint64, c_void_p, c_void_p]),
+    "bns_p2p_put_ids_i64": (c_int, [c_void_p, c_int32, POINTER(c_int64), POINTER(c_int32), POINTER(c_uint64), c_void_p,
+                                    c_int32, c_int32, c_uint64, c_void_p, c_void_p]),
+    "bns_p2p_wait_all": (c_int, [c_void_p, c_int32, POINTER(c_int32), c_uint64, c_void_p, c_void_p]),
+    "bns_scatter_rows_all_f32": (c_int, [c_void_p, c_int64, c_int64, c_int64, c_int32, POINTER(c_void_p), POINTER(c_void_p),
+                                         c_int64, POINTER(c_float), c_void_p]),
+    "bns_xent_workspace_bytes": (c_size_t, []),
+    "bns_xent_f32": (c_int, [c_void_p, c_int64, c_int64, c_int32, c_void_p, c_void_p, c_int64, c_void_p, c_float, c_void_p,
+                             c_void_p, c_int64, c_int32, c_void_p, c_size_t, c_void_p]),
+    "bns_derive_entry_bytes": (c_size_t, []),
+    "bns_adam_step_f32": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_float, c_float, c_float, c_float,
+                                  c_float, c_void_p, c_void_p]),
+    "bns_derive_refresh": (c_int, [c_void_p, c_int32, c_void_p, c_void_p]),
+    "bns_dropout_f32": (c_int, [c_void_p, c_int64, c_int64, c_int64, c_float, c_uint64, c_uint64, c_void_p, c_void_p,
+                                c_int64, c_void_p]),
+    "bns_scale_rows_f32": (c_int, [c_void_p, c_int64, c_int64, c_int64, c_void_p, c_void_p, c_int64, c_void_p]),
 }
 
 

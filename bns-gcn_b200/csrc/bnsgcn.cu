@@ -387,6 +387,7 @@ struct SpmmArgs {
     const int32_t *chunk_row;
     const int64_t *chunk_start;
     const int32_t *chunk_part;
+    const int32_t *chunk_cnt;      // compact mode (bns_graph_compact_cols): live entries of each chunk, NULL otherwise
     const int32_t *split_row;
     const int32_t *split_part;
     int64_t n_chunks, n_split;
@@ -491,8 +492,16 @@ __global__ void __launch_bounds__(kThreads) spmm_kernel(SpmmArgs a) {
             if (orow < 0) continue;
         }
         const int64_t s = a.chunk_start[c];
-        int64_t e = a.indptr[row + 1];
-        if (e > s + a.chunk_nnz) e = s + a.chunk_nnz;
+        int64_t e;
+        if (a.chunk_cnt) {         // per-epoch compacted indices: the chunk's live entries sit at the start of its range
+            const int32_t cnt = a.chunk_cnt[c];
+            // nothing sampled in this chunk: adding zero to Y would only cost a read-modify-write of the row
+            if (cnt == 0 && a.accumulate && a.chunk_part[c] < 0) continue;
+            e = s + cnt;
+        } else {
+            e = a.indptr[row + 1];
+            if (e > s + a.chunk_nnz) e = s + a.chunk_nnz;
+        }
         Vec<W> acc[NV];
 #pragma unroll
         for (int t = 0; t < NV; ++t) acc[t].zero();
@@ -716,6 +725,26 @@ int pick_slab(int64_t F, int64_t x_rows, int32_t forced) {
     return fmax;
 }
 
+int spmm_dispatch(const SpmmArgs &a, int64_t x_rows, int32_t slab_hint, cudaStream_t st) {
+    const int64_t F = a.F;
+    const bool vec = (F % 4 == 0) && (a.ldx % 4 == 0) && (a.ldy % 4 == 0) &&
+                     ((reinterpret_cast<uintptr_t>(a.X) | reinterpret_cast<uintptr_t>(a.Y)) % 16 == 0);
+    if (vec) {
+        int slab = pick_slab(F, x_rows, slab_hint);
+        while (slab > 32 && slab / 2 >= F) slab >>= 1;       // never wider than needed (F = 64 -> 64-wide groups)
+        switch (slab) {
+            case 256: dispatch_flags<4, 32, 2>(a, st); break;
+            case 128: dispatch_flags<4, 32, 1>(a, st); break;
+            case 64:  dispatch_flags<4, 16, 1>(a, st); break;
+            default:  dispatch_flags<4, 8, 1>(a, st); break;
+        }
+    } else {
+        dispatch_flags<1, 32, 8>(a, st);
+    }
+    BNS_CUDA(cudaGetLastError());
+    return BNS_OK;
+}
+
 }  // namespace
 
 extern "C" size_t bns_spmm_workspace_bytes(const bns_graph_t *g, int64_t F) {
@@ -741,7 +770,7 @@ extern "C" int bns_spmm_sum_f32(const bns_graph_t *g, const float *X, int64_t ld
     if (x_rows <= 0) x_rows = g->n_cols;
     SpmmArgs a;
     a.indptr = g->indptr; a.indices = g->indices;
-    a.chunk_row = g->chunk_row; a.chunk_start = g->chunk_start; a.chunk_part = g->chunk_part;
+    a.chunk_row = g->chunk_row; a.chunk_start = g->chunk_start; a.chunk_part = g->chunk_part; a.chunk_cnt = nullptr;
     a.split_row = g->split_row; a.split_part = g->split_part;
     a.n_chunks = g->n_chunks; a.n_split = g->n_split; a.chunk_nnz = g->chunk_nnz;
     a.X = X; a.ldx = ldx; a.Y = Y; a.ldy = ldy; a.F = (int32_t)F;
@@ -749,23 +778,35 @@ extern "C" int bns_spmm_sum_f32(const bns_graph_t *g, const float *X, int64_t ld
     a.n_direct = (int32_t)n_direct; a.accumulate = accumulate ? 1 : 0;
     a.ws = reinterpret_cast<float *>(ws); a.ldws = ws_ld(F);
     a.n_tiles = 1;
-    cudaStream_t st = as_stream(stream);
-    const bool vec = (F % 4 == 0) && (ldx % 4 == 0) && (ldy % 4 == 0) &&
-                     ((reinterpret_cast<uintptr_t>(X) | reinterpret_cast<uintptr_t>(Y)) % 16 == 0);
-    if (vec) {
-        int slab = pick_slab(F, x_rows, slab_hint);
-        while (slab > 32 && slab / 2 >= F) slab >>= 1;       // never wider than needed (F = 64 -> 64-wide groups)
-        switch (slab) {
-            case 256: dispatch_flags<4, 32, 2>(a, st); break;
-            case 128: dispatch_flags<4, 32, 1>(a, st); break;
-            case 64:  dispatch_flags<4, 16, 1>(a, st); break;
-            default:  dispatch_flags<4, 8, 1>(a, st); break;
-        }
-    } else {
-        dispatch_flags<1, 32, 8>(a, st);
-    }
-    BNS_CUDA(cudaGetLastError());
-    return BNS_OK;
+    return spmm_dispatch(a, x_rows, slab_hint, as_stream(stream));
+}
+
+// The same kernel over the per-epoch compacted indices of bns_graph_compact_cols: `cidx` already holds rows of X, the
+// chunk's live entries come first in its range, `chunk_cnt` says how many; `cw` = per-entry weights gathered at
+// compaction time (GCN's 1/sqrt(out_deg) of the halo sources) or NULL.  Work is proportional to the SAMPLE, not to the
+// halo (the col_map kernel walks every halo edge to use ~10 % of them).
+extern "C" int bns_spmm_compact_f32(const bns_graph_t *g, const int32_t *cidx, const float *cw, const int32_t *chunk_cnt,
+                                    const float *X, int64_t ldx, int64_t F, float *Y, int64_t ldy, const float *row_scale,
+                                    int64_t x_rows, int32_t slab_hint, int accumulate, void *ws, size_t ws_bytes, void *stream) {
+    BNS_REQUIRE(g && cidx && chunk_cnt, "bns_spmm_compact_f32: NULL argument");
+    BNS_REQUIRE(F > 0 && F < (1 << 24), "bns_spmm_compact_f32: bad feature width %lld", (long long)F);
+    if (g->n_rows == 0) return BNS_OK;
+    BNS_REQUIRE(Y && (X || g->nnz == 0), "bns_spmm_compact_f32: NULL matrix");
+    BNS_REQUIRE(ldx >= F && ldy >= F, "bns_spmm_compact_f32: leading dimension smaller than F");
+    const size_t need = bns_spmm_workspace_bytes(g, F);
+    if (need > 0 && (ws == nullptr || ws_bytes < need))
+        return fail(BNS_E_WORKSPACE, "bns_spmm_compact_f32: workspace %zu bytes < %zu needed", ws_bytes, need);
+    SpmmArgs a;
+    a.indptr = g->indptr; a.indices = cidx;
+    a.chunk_row = g->chunk_row; a.chunk_start = g->chunk_start; a.chunk_part = g->chunk_part; a.chunk_cnt = chunk_cnt;
+    a.split_row = g->split_row; a.split_part = g->split_part;
+    a.n_chunks = g->n_chunks; a.n_split = g->n_split; a.chunk_nnz = g->chunk_nnz;
+    a.X = X; a.ldx = ldx; a.Y = Y; a.ldy = ldy; a.F = (int32_t)F;
+    a.row_scale = row_scale; a.col_scale = nullptr; a.edge_weight = cw; a.row_map = nullptr; a.col_map = nullptr;
+    a.n_direct = (int32_t)g->n_cols; a.accumulate = accumulate ? 1 : 0;
+    a.ws = reinterpret_cast<float *>(ws); a.ldws = ws_ld(F);
+    a.n_tiles = 1;
+    return spmm_dispatch(a, x_rows > 0 ? x_rows : g->n_cols, slab_hint, as_stream(stream));
 }
 
 // =================================================================================================
@@ -1333,7 +1374,8 @@ __global__ void __launch_bounds__(kThreads) colsum_partial_kernel(const float *_
     }
 }
 
-__global__ void colsum_final_kernel(const float4 *__restrict__ partial, int n_part, int CV, float4 *__restrict__ out) {
+__global__ void colsum_final_kernel(const float4 *__restrict__ partial, int n_part, int CV, float4 *__restrict__ out,
+                                    float4 *__restrict__ out2) {
     const int c = blockIdx.x * blockDim.x + threadIdx.x;
     if (c >= CV) return;
     float4 acc = partial[c];
@@ -1342,6 +1384,7 @@ __global__ void colsum_final_kernel(const float4 *__restrict__ partial, int n_pa
         acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
     }
     out[c] = acc;
+    if (out2) out2[c] = acc;
 }
 
 inline int colsum_blocks() { return sm_count() * 4; }
@@ -1352,9 +1395,10 @@ extern "C" size_t bns_colsum_workspace_bytes(int64_t cols) {
     return cols > 0 ? (size_t)colsum_blocks() * (size_t)((cols + 3) / 4) * sizeof(float4) : 0;
 }
 
-extern "C" int bns_colsum_f32(const float *X, int64_t ld, int64_t rows, int64_t cols, float *out, void *ws, size_t ws_bytes,
-                              void *stream) {
+extern "C" int bns_colsum_f32(const float *X, int64_t ld, int64_t rows, int64_t cols, float *out, float *out2, void *ws,
+                              size_t ws_bytes, void *stream) {
     BNS_REQUIRE(X && out, "bns_colsum_f32: NULL argument");
+    BNS_REQUIRE(!out2 || (reinterpret_cast<uintptr_t>(out2) & 15u) == 0, "bns_colsum_f32: out2 must be 16-byte aligned");
     BNS_REQUIRE(rows > 0 && cols > 0 && cols % 4 == 0 && cols <= kColsumMaxCols, "bns_colsum_f32: need 0 < cols <= 1024, cols %% 4 == 0");
     BNS_REQUIRE(ld >= cols && ld % 4 == 0 && (reinterpret_cast<uintptr_t>(X) & 15u) == 0 && (reinterpret_cast<uintptr_t>(out) & 15u) == 0,
                 "bns_colsum_f32: 16-byte aligned rows required");
@@ -1367,7 +1411,7 @@ extern "C" int bns_colsum_f32(const float *X, int64_t ld, int64_t rows, int64_t 
     cudaStream_t st = as_stream(stream);
     colsum_partial_kernel<<<blocks, kThreads, 0, st>>>(X, ld, rows, CV, reinterpret_cast<float4 *>(ws));
     colsum_final_kernel<<<(CV + 127) / 128, 128, 0, st>>>(reinterpret_cast<const float4 *>(ws), blocks, CV,
-                                                          reinterpret_cast<float4 *>(out));
+                                                          reinterpret_cast<float4 *>(out), reinterpret_cast<float4 *>(out2));
     g_launches += 2;
     BNS_CUDA(cudaGetLastError());
     return BNS_OK;
@@ -1577,6 +1621,8 @@ __global__ void p2p_wait_kernel(const unsigned long long *flag, unsigned long lo
 
 }  // namespace
 
+namespace { void preload_exchange_kernels(); }      // fused.cuh
+
 extern "C" int bns_p2p_create(bns_p2p_t **out, int32_t rank, int32_t world, size_t slab_bytes, int32_t n_flags) {
     BNS_REQUIRE(out, "bns_p2p_create: out is NULL");
     BNS_REQUIRE(world >= 1 && rank >= 0 && rank < world, "bns_p2p_create: bad rank/world");
@@ -1589,8 +1635,9 @@ extern "C" int bns_p2p_create(bns_p2p_t **out, int32_t rank, int32_t world, size
     p->peer_flags = new unsigned long long *[world]();
     p->peer_slab_bytes = new size_t[world]();
     p->imported = new bool[world]();
-    // flags block: n_flags u64 + one u32 ticket per peer (for the put kernel), zero-initialised
-    const size_t flag_bytes = align256((size_t)n_flags * 8) + align256((size_t)world * 4);
+    // flags block: n_flags u64 + u32 completion tickets (one per peer for bns_p2p_put_rows_f32, 16 more for the
+    // all-peer puts), zero-initialised
+    const size_t flag_bytes = align256((size_t)n_flags * 8) + align256((size_t)(world + 16) * 4);
     if (cudaMalloc(&p->slab, p->slab_bytes) != cudaSuccess || cudaMalloc(&p->flags, flag_bytes) != cudaSuccess) {
         int rc = fail(BNS_E_CUDA, "bns_p2p_create: cudaMalloc failed: %s", cudaGetErrorString(cudaGetLastError()));
         bns_p2p_destroy(p);
@@ -1612,6 +1659,7 @@ extern "C" int bns_p2p_create(bns_p2p_t **out, int32_t rank, int32_t world, size
     cudaFuncGetAttributes(&fa, rows_kernel<false, true>);
     cudaFuncGetAttributes(&fa, rows_kernel<true, false>);
     cudaFuncGetAttributes(&fa, rows_kernel<false, false>);
+    preload_exchange_kernels();
     *out = p;
     return BNS_OK;
 }
@@ -1719,6 +1767,11 @@ extern "C" int bns_p2p_wait_flag(bns_p2p_t *p, int32_t flag_index, uint64_t flag
     BNS_CUDA(cudaGetLastError());
     return BNS_OK;
 }
+
+// =================================================================================================
+// the tail of the epoch: loss, Adam, consolidated exchange, per-epoch maps, halo compaction
+// =================================================================================================
+#include "fused.cuh"
 
 // =================================================================================================
 // K8: dense layers on tcgen05 (3xTF32 with the operand split fused into the pipeline)

@@ -150,7 +150,8 @@ template <bool kMN, bool kTrunc>
 __global__ void __launch_bounds__(kThreadsTc, 1)
 gemm3x_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
               float *__restrict__ C, int64_t ldc, int64_t split_stride, const float *__restrict__ bias,
-              const float *__restrict__ addend, int64_t ldadd, int M, int N, int num_kb, int tiles_n, int tiles, int splits) {
+              const float *__restrict__ addend, int64_t ldadd, const float *__restrict__ row_scale, int M, int N, int num_kb,
+              int tiles_n, int tiles, int splits) {
     extern __shared__ uint8_t smem_raw[];
     const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
@@ -304,6 +305,7 @@ gemm3x_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__
             const int row = m_t * BM + (int)(32 * q + lane);
             float *Cout = C + (int64_t)split_ * split_stride + (int64_t)row * ldc;
             const float *Add = addend ? addend + (int64_t)row * ldadd : nullptr;
+            const float rsc = (row_scale && row < M) ? __ldg(row_scale + row) : 1.f;
             const uint32_t tbase = tmem_base + ((32u * q) << 16) + buf * (uint32_t)(kAcc * BN);
 #pragma unroll 1
             for (int c = 0; c < BN / 32; ++c) {
@@ -331,11 +333,12 @@ gemm3x_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__
                                 const float4 aa = *reinterpret_cast<const float4 *>(Add + col);
                                 o.x += aa.x; o.y += aa.y; o.z += aa.z; o.w += aa.w;
                             }
+                            if (row_scale) { o.x *= rsc; o.y *= rsc; o.z *= rsc; o.w *= rsc; }
                             *reinterpret_cast<float4 *>(Cout + col) = o;
                         } else {
                             for (int e = 0; e < 4; ++e)
                                 if (col + e < N)
-                                    Cout[col + e] = __uint_as_float(v[4 * j + e]) + (bias ? bias[col + e] : 0.f) + (Add ? Add[col + e] : 0.f);
+                                    Cout[col + e] = (__uint_as_float(v[4 * j + e]) + (bias ? bias[col + e] : 0.f) + (Add ? Add[col + e] : 0.f)) * rsc;
                         }
                     }
                 }
@@ -429,8 +432,8 @@ int configure() {
 
 // C[M, N] = A[M, K] * B[N, K]^T (+ bias[N]) (+ addend[M, N])
 extern "C" int bns_dense_tn_3xtf32(const float *A, int64_t lda, const float *B, int64_t ldb, const float *bias,
-                                   const float *addend, int64_t ldadd, float *C, int64_t ldc, int64_t M, int64_t N, int64_t K,
-                                   void *stream) {
+                                   const float *addend, int64_t ldadd, const float *row_scale, float *C, int64_t ldc, int64_t M,
+                                   int64_t N, int64_t K, void *stream) {
     BNS_REQUIRE(A && B && C, "bns_dense_tn_3xtf32: NULL argument");
     BNS_REQUIRE(M > 0 && N > 0 && K > 0 && M < (1ll << 31) && N < (1ll << 31) && K < (1ll << 31), "bns_dense_tn_3xtf32: bad shape");
     BNS_REQUIRE(lda >= K && ldb >= K && ldc >= N, "bns_dense_tn_3xtf32: leading dimension smaller than the row");
@@ -453,10 +456,10 @@ extern "C" int bns_dense_tn_3xtf32(const float *A, int64_t lda, const float *B, 
     dim3 grid((unsigned)(tiles < sm_count() ? tiles : sm_count()), 1, 1);
     if (tr)
         tc::gemm3x_kernel<false, true><<<grid, tc::kThreadsTc, tc::SMEM_BYTES, as_stream(stream)>>>(ma, mb, C, ldc, 0, bias, addend, ldadd,
-                                                                                                   (int)M, (int)N, num_kb, tiles_n, tiles, 1);
+                                                                                                   row_scale, (int)M, (int)N, num_kb, tiles_n, tiles, 1);
     else
         tc::gemm3x_kernel<false, false><<<grid, tc::kThreadsTc, tc::SMEM_BYTES, as_stream(stream)>>>(ma, mb, C, ldc, 0, bias, addend, ldadd,
-                                                                                                    (int)M, (int)N, num_kb, tiles_n, tiles, 1);
+                                                                                                    row_scale, (int)M, (int)N, num_kb, tiles_n, tiles, 1);
     ++g_launches;
     BNS_CUDA(cudaGetLastError());
     return BNS_OK;
@@ -524,11 +527,11 @@ extern "C" int bns_dense_nt_3xtf32(const float *A, int64_t lda, const float *B, 
     float *w = splits == 1 ? C : static_cast<float *>(ws);
     const int64_t ldw = splits == 1 ? ldc : N2, slice = splits == 1 ? 0 : N1 * N2;
     if (tr)
-        tc::gemm3x_kernel<true, true><<<grid, tc::kThreadsTc, tc::SMEM_BYTES, st>>>(ma, mb, w, ldw, slice, nullptr, nullptr, 0, (int)N1,
-                                                                                    (int)N2, num_kb, tiles_n, tiles, splits);
+        tc::gemm3x_kernel<true, true><<<grid, tc::kThreadsTc, tc::SMEM_BYTES, st>>>(ma, mb, w, ldw, slice, nullptr, nullptr, 0, nullptr,
+                                                                                    (int)N1, (int)N2, num_kb, tiles_n, tiles, splits);
     else
-        tc::gemm3x_kernel<true, false><<<grid, tc::kThreadsTc, tc::SMEM_BYTES, st>>>(ma, mb, w, ldw, slice, nullptr, nullptr, 0, (int)N1,
-                                                                                     (int)N2, num_kb, tiles_n, tiles, splits);
+        tc::gemm3x_kernel<true, false><<<grid, tc::kThreadsTc, tc::SMEM_BYTES, st>>>(ma, mb, w, ldw, slice, nullptr, nullptr, 0, nullptr,
+                                                                                     (int)N1, (int)N2, num_kb, tiles_n, tiles, splits);
     if (splits == 1) {
         ++g_launches;
     } else {

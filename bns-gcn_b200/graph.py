@@ -27,6 +27,17 @@ class PartitionGraph:
         self.slot = torch.full((max(n_halo, 1),), -1, dtype=torch.int32, device=device)
         self.n_u = n_in
         self._recip: Dict[int, torch.Tensor] = {}
+        # per-epoch compaction of a_out to the sampled halo columns (ops.CompactedCols), refreshed by construct_graph
+        self.compact: Optional[ops.CompactedCols] = None
+        self.halo_col_scale: Optional[torch.Tensor] = None      # GCN: 1/sqrt(out_deg) of the halo nodes (static)
+
+    def refresh_compaction(self) -> None:
+        """Call after every change of ``slot`` (train.construct_graph does)."""
+        if self.a_out is None or self.a_out.nnz == 0:
+            return
+        if self.compact is None:
+            self.compact = ops.CompactedCols(self.a_out, with_weights=self.halo_col_scale is not None)
+        self.compact.refresh(self.slot, 0, self.halo_col_scale)
 
     def num_nodes(self, ntype: str = '_V') -> int:
         return self.n_in if ntype == '_V' else self.n_u
@@ -61,6 +72,16 @@ class FullGraphHandle:
         return self._out
 
 
+def halo_aggregate(g: PartitionGraph, x_halo: torch.Tensor, y: torch.Tensor, rs, cs_halo) -> None:
+    """``y += rs * A_out[:, sampled] (cs_halo * x_halo)``.  With the epoch's compaction (the default) the kernel walks
+    the sampled entries only; without it (a graph whose slot map was set by hand) every halo entry is looked up."""
+    c = g.compact
+    if c is not None and (c.cw is not None) == (cs_halo is not None):
+        ops.spmm_compact(c, x_halo, y, row_scale=rs, accumulate=True)
+    else:
+        ops.spmm(g.a_out, x_halo, y, row_scale=rs, col_scale=cs_halo, col_map=g.slot, n_direct=0, accumulate=True)
+
+
 class PartitionAggregate(torch.autograd.Function):
     """K1 + K2 (+ K1b in backward) on a ``PartitionGraph``:
 
@@ -82,8 +103,7 @@ class PartitionAggregate(torch.autograd.Function):
         if ready is not None:
             torch.cuda.current_stream(h_u.device).wait_event(ready)
         if g.a_out is not None and ctx.n_u > g.n_in:
-            ops.spmm(g.a_out, h_u[g.n_in:], y, row_scale=rs, col_scale=cs_halo, col_map=g.slot, n_direct=0,
-                     accumulate=True)
+            halo_aggregate(g, h_u[g.n_in:], y, rs, cs_halo)
         return y
 
     @staticmethod

@@ -24,7 +24,7 @@ from typing import List, Optional
 import torch
 
 from .. import ops
-from .._lib import P2P_HANDLE_BYTES, check, lib
+from .._lib import MAX_PEERS, P2P_HANDLE_BYTES, EpochMaps, PutAll, check, lib
 from . import context as ctx
 from .timer.timer import comm_timer
 
@@ -53,9 +53,11 @@ class Buffer(object):
         self._send_buf, self._b_recv = None, None
         self._p2p = None
         self._seq = {}
-        # CUDA-graph mode (train.GraphedEpoch): no timing events, sequence numbers come from a device counter
+        # CUDA-graph mode (train.GraphedEpoch): no timing events; flag sequence numbers = seq_base + *seq_dev
         self.graph_mode = False
         self.seq_dev = None
+        self.seq_base = 0
+        self._maps = None
 
     # helper/feature_buffer.py:23-33
     def __init_pl_pr(self):
@@ -118,10 +120,20 @@ class Buffer(object):
         n_comm_layers = max(self._n_layers - 1, 1)
         fwd_rows, bwd_rows = self._n_u, max(self._send_total, 1)
         row_bytes = width * 4
+        if self._size - 1 > MAX_PEERS:
+            raise RuntimeError(f"p2p transport: at most {MAX_PEERS + 1} partitions (BNS_MAX_PEERS)")
         self._fwd_off = [l * (fwd_rows + bwd_rows) * row_bytes for l in range(n_comm_layers)]
         self._bwd_off = [o + fwd_rows * row_bytes for o in self._fwd_off]
-        slab_bytes = n_comm_layers * (fwd_rows + bwd_rows) * row_bytes
-        n_flags = n_comm_layers * 2 * self._size
+        # after the feature regions: the received id lists of the epoch (data_transfer NODE), int64 [sum of recv sizes]
+        self._ids_off = (n_comm_layers * (fwd_rows + bwd_rows) * row_bytes + 255) // 256 * 256
+        self._hop_begin, tot = [], 0
+        for j in range(self._size):
+            self._hop_begin.append(tot)
+            tot += 0 if j == self._rank else self._recv_shape[j]
+        self._recv_total = tot
+        slab_bytes = self._ids_off + max(tot, 1) * 8
+        self._n_comm_layers = n_comm_layers
+        n_flags = (n_comm_layers * 2 + 1) * self._size          # (layer, direction, source) + (ids, source)
         h = ctypes.c_void_p()
         with torch.cuda.device(self._device):
             check(lib.bns_p2p_create(ctypes.byref(h), self._rank, self._size, slab_bytes, n_flags), "bns_p2p_create")
@@ -131,7 +143,7 @@ class Buffer(object):
         self._slab_ptr = slab.value
         # publish: where peers must write inside MY slab (row offsets of their segment) + how to map my memory
         my = {"fwd_off": self._fwd_off, "bwd_off": self._bwd_off, "pl": self._pl, "send_begin": self._send_begin,
-              "slab_bytes": nbytes.value}
+              "ids_off": self._ids_off, "hop_begin": self._hop_begin, "slab_bytes": nbytes.value}
         if c.kind == "thread":
             my["ptrs"] = (slab.value, flags.value)
         else:
@@ -151,6 +163,89 @@ class Buffer(object):
                 with torch.cuda.device(self._device):
                     check(lib.bns_p2p_import(h, j, table[j]["handle"], table[j]["slab_bytes"]), "bns_p2p_import")
         c.barrier()
+        self._peers = [j for j in range(self._size) if j != self._rank]               # ascending: segment order
+        self._ring_out = [(self._rank + i) % self._size for i in range(1, self._size)]
+        self._ring_in = [(self._rank - i + self._size) % self._size for i in range(1, self._size)]
+
+    # ---- per-epoch ids and maps (p2p transport) ------------------------------------------------------
+    def set_maps(self, maps: torch.Tensor, n_halo: int, pos):
+        """``maps``: ONE int32 allocation ``[n_halo + (P-1) * n_in]`` = the slot map of the partition graph followed by
+        the inverse map of every peer (ascending); ``pos``: train.get_pos()."""
+        self._maps, self._n_halo, self._pos = maps, n_halo, pos
+        self._inv = {}
+        for s_, j in enumerate(self._peers):
+            b = n_halo + s_ * self._num_in
+            self._inv[j] = maps[b:b + self._num_in]
+
+    def uses_p2p_ids(self) -> bool:
+        return self._p2p is not None and self._maps is not None
+
+    def exchange_ids(self, sel_cat: torch.Tensor):
+        """data_transfer(selected, ..., tag=NODE) (helper/utils.py:187-213, train.py:389) over peer memory: one kernel
+        stores every peer's sampled id list into that peer's slab and raises its flag, one kernel waits for the lists of
+        all peers.  Returns ``(one_hops_cat, [per-peer views])`` -- views of this rank's slab."""
+        cs = self._comm_stream
+        main = torch.cuda.current_stream(self._device)
+        n = len(self._peers)
+        begin = (ctypes.c_int64 * (n + 1))()
+        peers = (ctypes.c_int32 * max(n, 1))()
+        roff = (ctypes.c_uint64 * max(n, 1))()
+        tot = 0
+        for s_, j in enumerate(self._peers):
+            begin[s_] = tot
+            tot += self._send_shape[j]
+            peers[s_] = j
+            lay = self._peer_layout[j]
+            roff[s_] = lay["ids_off"] + lay["hop_begin"][self._rank] * 8
+        begin[n] = tot
+        flag_base = self._n_comm_layers * 2 * self._size
+        seq, seq_dev = self._seq_args("ids", False)
+        start = torch.cuda.Event()
+        start.record(main)
+        cs.wait_event(start)
+        with torch.cuda.stream(cs):
+            check(lib.bns_p2p_put_ids_i64(self._p2p, n, begin, peers, roff, sel_cat.data_ptr() if tot else None,
+                                          flag_base + self._rank, self._size + 15, seq, seq_dev, cs.cuda_stream),
+                  "bns_p2p_put_ids_i64")
+            for j in self._peers:
+                self._post_put_event(j, 1999, cs)
+            for j in self._peers:
+                self._await_put_event(j, 1999, cs)
+            idx = (ctypes.c_int32 * max(n, 1))(*[flag_base + j for j in self._peers])
+            check(lib.bns_p2p_wait_all(self._p2p, n, idx, seq, seq_dev, cs.cuda_stream), "bns_p2p_wait_all")
+            done = torch.cuda.Event()
+            done.record(cs)
+        if not self.graph_mode:
+            sel_cat.record_stream(cs)
+        main.wait_event(done)
+        cat = torch.as_tensor(_DevArray(self._slab_ptr + self._ids_off, (max(self._recv_total, 1),), "<i8"),
+                              device=self._device)[:self._recv_total]
+        views = [None] * self._size
+        for j in self._peers:
+            views[j] = cat[self._hop_begin[j]:self._hop_begin[j] + self._recv_shape[j]]
+        return cat, views
+
+    def update_maps(self, sel_cat: torch.Tensor, hops_cat: torch.Tensor, slot: torch.Tensor):
+        """construct_graph (train.py:256-281) for all peers + the inverse maps of the gradient scatter: one memset, one
+        kernel (``bns_epoch_maps_update``)."""
+        m = EpochMaps()
+        n = len(self._peers)
+        m.n_seg = n
+        a = b = 0
+        for s_, j in enumerate(self._peers):
+            m.sel_begin[s_], m.hop_begin[s_] = a, b
+            a += self._send_shape[j]
+            b += self._recv_shape[j]
+            m.pos[s_] = self._pos[j].data_ptr()
+            m.inv[s_] = self._inv[j].data_ptr()
+        m.sel_begin[n], m.hop_begin[n] = a, b
+        m.selected_cat = sel_cat.data_ptr() if a else None
+        m.one_hops_cat = hops_cat.data_ptr() if b else None
+        m.slot = slot.data_ptr()
+        m.n_in = self._num_in
+        with torch.cuda.device(self._device):
+            check(lib.bns_epoch_maps_update(ctypes.byref(m), self._maps.data_ptr(), self._maps.numel() * 4,
+                                            torch.cuda.current_stream(self._device).cuda_stream), "bns_epoch_maps_update")
 
     # Ranks that are THREADS of one process share a CUDA context, where a kernel spinning on a flag can block the
     # very launch that would set it (lazy module loading and stream->hardware-queue aliasing both synchronise the
@@ -174,7 +269,7 @@ class Buffer(object):
     def _seq_args(self, layer, backward):
         """(immediate, device pointer) of this exchange's flag value."""
         if self.graph_mode:
-            return 0, self.seq_dev.data_ptr()
+            return self.seq_base, self.seq_dev.data_ptr()
         key = (layer, 1 if backward else 0)
         self._seq[key] = self._seq.get(key, 0) + 1
         return self._seq[key], None
@@ -185,8 +280,14 @@ class Buffer(object):
     def _slab_view(self, byte_off, rows):
         return torch.as_tensor(_DevArray(self._slab_ptr + byte_off, (rows, self._width)), device=self._device)
 
-    def set_selected(self, selected):
+    def set_selected(self, selected, selected_cat=None):
+        """``selected_cat``: the same lists concatenated in ascending peer order (what the sampler produced); built here
+        when the caller injects per-peer lists."""
         self._selected = selected
+        if selected_cat is None and self._p2p is not None:
+            parts = [selected[j] for j in self._peers if selected[j] is not None and selected[j].numel()]
+            selected_cat = torch.cat(parts) if parts else torch.empty(0, dtype=torch.int64, device=self._device)
+        self._selected_cat = selected_cat
 
     # ---- forward ---------------------------------------------------------------------------------
     def update(self, layer, feat, overlap=False):
@@ -230,20 +331,29 @@ class Buffer(object):
                     self._comm.alltoall(send, recv, tag=16 + layer)                               # C1/C2
                 else:
                     seq, seq_dev = self._seq_args(layer, False)
-                    for i in range(1, self._size):
-                        j = (self._rank + i) % self._size
+                    segs = PutAll()
+                    segs.n_seg = len(self._peers)
+                    tot = 0
+                    for s_, j in enumerate(self._peers):
                         lay = self._peer_layout[j]
-                        off = lay["fwd_off"][layer - 1] + lay["pl"][self._rank] * self._width * 4
-                        check(lib.bns_p2p_put_rows_f32(self._p2p, j, off, self._width, feat.data_ptr(), feat.stride(0),
-                                                       F, ops._ptr(self._selected[j]), self._send_shape[j],
-                                                       float(self._ratio[j]), self._flag(layer, False, self._rank), seq,
-                                                       seq_dev, cs.cuda_stream), "bns_p2p_put_rows_f32")
+                        segs.row_begin[s_] = tot
+                        tot += self._send_shape[j]
+                        segs.peer[s_] = j
+                        segs.remote_off[s_] = lay["fwd_off"][layer - 1] + lay["pl"][self._rank] * self._width * 4
+                        segs.div[s_] = float(self._ratio[j]) if self._send_shape[j] else 1.0
+                    segs.row_begin[segs.n_seg] = tot
+                    sel_cat = self._selected_cat
+                    check(lib.bns_p2p_put_all_f32(self._p2p, ctypes.byref(segs), self._width, feat.data_ptr(), feat.stride(0),
+                                                  F, sel_cat.data_ptr() if tot else None,
+                                                  self._flag(layer, False, self._rank), self._size + (layer - 1) * 2, seq,
+                                                  seq_dev, cs.cuda_stream), "bns_p2p_put_all_f32")
+                    for j in self._peers:
                         self._post_put_event(j, 2000 + 2 * layer, cs)
-                    for i in range(1, self._size):
-                        j = (self._rank - i + self._size) % self._size
+                    for j in self._peers:
                         self._await_put_event(j, 2000 + 2 * layer, cs)
-                        check(lib.bns_p2p_wait_flag(self._p2p, self._flag(layer, False, j), seq, seq_dev, cs.cuda_stream),
-                              "bns_p2p_wait_flag")
+                    idx = (ctypes.c_int32 * len(self._peers))(*[self._flag(layer, False, j) for j in self._peers])
+                    check(lib.bns_p2p_wait_all(self._p2p, len(self._peers), idx, seq, seq_dev, cs.cuda_stream),
+                          "bns_p2p_wait_all")
             ready.record(cs)
         if not self.graph_mode:
             feat.record_stream(cs)
@@ -275,32 +385,54 @@ class Buffer(object):
                     self._comm.alltoall(send, recv, tag=64 + layer)
                 else:
                     seq, seq_dev = self._seq_args(layer, True)
-                    for i in range(1, self._size):
-                        j = (self._rank + i) % self._size
+                    segs = PutAll()
+                    segs.n_seg = len(self._peers)
+                    tot = 0
+                    for s_, j in enumerate(self._peers):
                         lay = self._peer_layout[j]
-                        off = lay["bwd_off"][layer - 1] + lay["send_begin"][self._rank] * self._width * 4
-                        src = grad[self._pl[j]:self._pr[j]]
-                        check(lib.bns_p2p_put_rows_f32(self._p2p, j, off, self._width, src.data_ptr(), grad.stride(0), F,
-                                                       None, self._recv_shape[j], 1.0,
-                                                       self._flag(layer, True, self._rank), seq, seq_dev, cs.cuda_stream),
-                              "bns_p2p_put_rows_f32")
+                        segs.row_begin[s_] = tot
+                        tot += self._recv_shape[j]
+                        segs.peer[s_] = j
+                        segs.remote_off[s_] = lay["bwd_off"][layer - 1] + lay["send_begin"][self._rank] * self._width * 4
+                        segs.src_begin[s_] = self._pl[j]
+                        segs.div[s_] = 1.0
+                    segs.row_begin[segs.n_seg] = tot
+                    check(lib.bns_p2p_put_all_f32(self._p2p, ctypes.byref(segs), self._width, grad.data_ptr(), grad.stride(0),
+                                                  F, None, self._flag(layer, True, self._rank),
+                                                  self._size + (layer - 1) * 2 + 1, seq, seq_dev, cs.cuda_stream),
+                          "bns_p2p_put_all_f32")
+                    for j in self._peers:
                         self._post_put_event(j, 2001 + 2 * layer, cs)
+                    for j in self._peers:
+                        self._await_put_event(j, 2001 + 2 * layer, cs)
+                    idx = (ctypes.c_int32 * len(self._peers))(*[self._flag(layer, True, j) for j in self._peers])
+                    check(lib.bns_p2p_wait_all(self._p2p, len(self._peers), idx, seq, seq_dev, cs.cuda_stream),
+                          "bns_p2p_wait_all")
                     recv = [None] * self._size
                     bwd = self._slab_view(self._bwd_off[layer - 1], max(self._send_total, 1))
-                    for i in range(1, self._size):
-                        j = (self._rank - i + self._size) % self._size
-                        self._await_put_event(j, 2001 + 2 * layer, cs)
-                        check(lib.bns_p2p_wait_flag(self._p2p, self._flag(layer, True, j), seq, seq_dev, cs.cuda_stream),
-                              "bns_p2p_wait_flag")
+                    for j in self._peers:
                         recv[j] = bwd[self._send_begin[j]:self._send_begin[j] + self._send_shape[j], :F]
             done.record(cs)
         if not self.graph_mode:
             grad.record_stream(cs)
         main.wait_event(done)
         inner = grad[:self._num_in]
-        for i in range(1, self._size):               # the reference's order: idx = left, i = 1 .. P-1 (:111-129)
-            left = (self._rank - i + self._size) % self._size
-            ops.scatter_add_div(inner, self._selected[left], recv[left], self._ratio[left])      # K5
+        if self._backend == 'nccl' or self._maps is None:
+            for i in range(1, self._size):           # the reference's order: idx = left, i = 1 .. P-1 (:111-129)
+                left = (self._rank - i + self._size) % self._size
+                ops.scatter_add_div(inner, self._selected[left], recv[left], self._ratio[left])      # K5
+        else:
+            # the same P-1 scatter-adds, in the same order, as ONE race-free launch over the inverse maps
+            order = [j for j in self._ring_in if self._send_shape[j] > 0]
+            if order:
+                n = len(order)
+                inv = (ctypes.c_void_p * n)(*[self._inv[j].data_ptr() for j in order])
+                base = self._slab_ptr + self._bwd_off[layer - 1]
+                rcv = (ctypes.c_void_p * n)(*[base + self._send_begin[j] * self._width * 4 for j in order])
+                div = (ctypes.c_float * n)(*[float(self._ratio[j]) for j in order])
+                with torch.cuda.device(self._device):
+                    check(lib.bns_scatter_rows_all_f32(inner.data_ptr(), inner.stride(0), self._num_in, F, n, inv, rcv,
+                                                       self._width, div, main.cuda_stream), "bns_scatter_rows_all_f32")
         if trace is not None:
             trace[f"grad_h{layer}"] = inner.detach().clone()
         return inner

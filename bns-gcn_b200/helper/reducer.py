@@ -37,13 +37,23 @@ class Reducer(object):
             self._stream = torch.cuda.Stream(device=dev)
         self._comm = ctx.comm()
 
+    def init_arena(self, arena):
+        """Fused training step (fused.ParamArena): the arena's gradient buffer IS the all-reduce bucket; the layer
+        functions fill it (already divided by n_train: the factor rides on d(logits)), no per-parameter hook runs."""
+        self._arena = arena
+        self._flat = arena.flat_g
+        dev = self._flat.device
+        if dev.type == 'cuda':
+            self._stream = torch.cuda.Stream(device=dev)
+        self._comm = ctx.comm()
+
     def reduce(self, param, name, data, n_train):
         off, n = self._slices[name]
         torch.div(data, n_train, out=self._flat[off:off + n].view_as(data))      # reducer.py:34 (grad /= n_train)
         self._pending.append((param, name))
 
     def synchronize(self):
-        if not self._pending:
+        if not self._pending and getattr(self, "_arena", None) is None:
             return
         c = self._comm
         if c.size > 1:

@@ -171,12 +171,14 @@ def tc_eligible(x: torch.Tensor, weight: torch.Tensor, bias=None) -> bool:
                                   and bias.data_ptr() % 16 == 0)))
 
 
-def tc_mm_tn(a: torch.Tensor, b: torch.Tensor, bias=None, addend=None) -> torch.Tensor:
-    """``a @ b.T (+ bias) (+ addend)``: a [M, K], b [N, K], addend [M, >= N] (``bns_dense_tn_3xtf32``)."""
+def tc_mm_tn(a: torch.Tensor, b: torch.Tensor, bias=None, addend=None, row_scale=None, out=None) -> torch.Tensor:
+    """``(a @ b.T (+ bias) (+ addend)) (* row_scale[:, None])``: a [M, K], b [N, K], addend [M, >= N]
+    (``bns_dense_tn_3xtf32``).  ``out`` may alias ``addend`` (in-place accumulation into a gradient buffer)."""
     from .._lib import check, lib
     M, K = a.shape
     N = b.shape[0]
-    out = torch.empty((M, N), dtype=torch.float32, device=a.device)
+    if out is None:
+        out = torch.empty((M, N), dtype=torch.float32, device=a.device)
     prof = PROFILE
     if prof is not None:
         ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -185,7 +187,8 @@ def tc_mm_tn(a: torch.Tensor, b: torch.Tensor, bias=None, addend=None) -> torch.
         check(lib.bns_dense_tn_3xtf32(a.data_ptr(), a.stride(0), b.data_ptr(), b.stride(0),
                                       None if bias is None else bias.data_ptr(),
                                       None if addend is None else addend.data_ptr(),
-                                      0 if addend is None else addend.stride(0), out.data_ptr(), out.stride(0), M, N, K,
+                                      0 if addend is None else addend.stride(0),
+                                      None if row_scale is None else row_scale.data_ptr(), out.data_ptr(), out.stride(0), M, N, K,
                                       torch.cuda.current_stream().cuda_stream), "bns_dense_tn_3xtf32")
     if prof is not None:
         ev1.record(torch.cuda.current_stream(a.device))
@@ -193,30 +196,51 @@ def tc_mm_tn(a: torch.Tensor, b: torch.Tensor, bias=None, addend=None) -> torch.
     return out
 
 
-def colsum(x: torch.Tensor) -> torch.Tensor:
+_WS = {}
+
+
+def _workspace(kind: str, nbytes: int, device) -> torch.Tensor:
+    """Scratch reused across calls, one per (kind, device, stream): ranks that are threads of one process run on their
+    own streams and must not share it; consecutive calls on one stream are ordered."""
+    key = (kind, device, torch.cuda.current_stream(device).cuda_stream)
+    ws = _WS.get(key)
+    if ws is None or ws.numel() < nbytes:
+        ws = _WS[key] = torch.empty(max(nbytes, 16), dtype=torch.uint8, device=device)
+    return ws
+
+
+def colsum(x: torch.Tensor, out=None, out2=None) -> torch.Tensor:
     """``x.sum(0)`` of a 2-D f32 CUDA matrix (bias gradients): ``bns_colsum_f32`` where the rows are 16-byte
-    multiples, torch otherwise."""
+    multiples, torch otherwise.  ``out`` / ``out2``: destinations (e.g. gradient slots of the parameter arena)."""
     if not (_tc_operand(x) and x.shape[1] % 4 == 0 and x.shape[1] <= 1024):
-        return x.sum(0)
+        r = x.sum(0)
+        if out is not None:
+            out.copy_(r)
+        if out2 is not None:
+            out2.copy_(r)
+        return r if out is None else out
     from .._lib import check, lib
     rows, cols = x.shape
-    out = torch.empty(cols, dtype=torch.float32, device=x.device)
+    if out is None:
+        out = torch.empty(cols, dtype=torch.float32, device=x.device)
     nbytes = lib.bns_colsum_workspace_bytes(cols)
-    ws = torch.empty(nbytes, dtype=torch.uint8, device=x.device)
+    ws = _workspace("colsum", nbytes, x.device)
     with torch.cuda.device(x.device):
-        check(lib.bns_colsum_f32(x.data_ptr(), x.stride(0), rows, cols, out.data_ptr(), ws.data_ptr(), nbytes,
+        check(lib.bns_colsum_f32(x.data_ptr(), x.stride(0), rows, cols, out.data_ptr(),
+                                 None if out2 is None else out2.data_ptr(), ws.data_ptr(), nbytes,
                                  torch.cuda.current_stream().cuda_stream), "bns_colsum_f32")
     return out
 
 
-def tc_mm_nt(a: torch.Tensor, b: torch.Tensor) -> torch.Tensor:
+def tc_mm_nt(a: torch.Tensor, b: torch.Tensor, out=None) -> torch.Tensor:
     """``a.T @ b``: a [R, N1], b [R, N2] -> [N1, N2], contraction over the rows (``bns_dense_nt_3xtf32``)."""
     from .._lib import check, lib
     R, N1 = a.shape
     N2 = b.shape[1]
-    out = torch.empty((N1, N2), dtype=torch.float32, device=a.device)
+    if out is None:
+        out = torch.empty((N1, N2), dtype=torch.float32, device=a.device)
     nbytes = lib.bns_dense_nt_workspace_bytes(R, N1, N2)
-    ws = torch.empty(max(nbytes, 16), dtype=torch.uint8, device=a.device)
+    ws = _workspace("mm_nt", nbytes, a.device)
     prof = PROFILE
     if prof is not None:
         ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)

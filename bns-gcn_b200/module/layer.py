@@ -107,7 +107,21 @@ class GraphSAGELayer(nn.Module):
 
     _lin = staticmethod(_apply)
 
-    def forward(self, graph, feat, in_norm):
+    def forward(self, graph, feat, in_norm, fused=None):
+        """``fused = (arena, dropout p of the input, Philox seed)``: the fused training step (fused.py) -- one
+        autograd node for the whole layer, parameter gradients written into the arena."""
+        if self.training and fused is not None:
+            from .. import fused as _f
+            arena, p, seed = fused
+            if self.use_pp:
+                return _f.PPLinearFn.apply(feat, self.linear.weight, self.linear.bias, arena, p, seed)
+            out_f, in_f = self.linear2.out_features, self.linear2.in_features
+            narrow = AGGREGATE_AFTER_TRANSFORM and out_f < in_f
+            out = _f.SageConvFn.apply(feat, self.linear1.weight, self.linear1.bias, self.linear2.weight,
+                                      self.linear2.bias, graph, graph.recip(in_norm), getattr(feat, '_bns_ready', None),
+                                      arena, narrow)
+            self._padded_out = out              # [n_in, ceil4(out_features)]: the loss kernel reads / writes this layout
+            return out if out.shape[1] == out_f else out[:, :out_f]
         if self.training:
             if self.use_pp:
                 return self._lin(self.linear, feat)                                 # layer.py:82-83

@@ -34,6 +34,10 @@ class GNNBase(nn.Module):
         if self.use_norm:
             self.norm = nn.ModuleList()
         self.dropout = nn.Dropout(p=dropout)
+        # fused.ParamArena, set by train.setup when the whole model can take the fused training step (fused.py);
+        # None = the op-by-op autograd path
+        self._arena = None
+        self._padded_logits = None
 
     @property
     def n_conv(self) -> int:
@@ -56,7 +60,10 @@ class GNNBase(nn.Module):
         if (may_fuse and FUSE_NORM_ACT_DROPOUT and isinstance(nm, nn.LayerNorm) and self.activation is F.relu
                 and nm.elementwise_affine and ops.ln_relu_dropout_supported(h, h.shape[1])):
             p = self.dropout.p if self.training else 0.0
-            return ops.LnReluDropout.apply(h, nm.weight, nm.bias, nm.eps, p, ops.RNG["seed"] + 7919 * (i + 1)), True
+            slots = None
+            if self._arena is not None and self.training:
+                slots = (self._arena.grad_padded(nm.weight), self._arena.grad_padded(nm.bias))
+            return ops.LnReluDropout.apply(h, nm.weight, nm.bias, nm.eps, p, ops.RNG["seed"] + 7919 * (i + 1), slots), True
         if nm is not None:
             h = nm(h)
         return self.activation(h), False
@@ -64,15 +71,30 @@ class GNNBase(nn.Module):
     def _forward(self, g, feat, *norms):
         """GCN / GraphSAGE (module/model.py:42-58, 77-93): dropout -> [exchange] -> layer -> norm -> activation."""
         h, dropped = feat, False               # dropped: this layer's input dropout was applied by the fused step
+        arena = self._arena if self.training else None
+        self._padded_logits = None
         for i, layer in enumerate(self.layers):
-            if not dropped:
+            kw = {}
+            if arena is not None and i < self.n_conv:
+                # fused training step (fused.py): the layer writes its parameter gradients straight into the arena; the
+                # precomputed layer 0 also applies its own input dropout (Philox, replay-safe)
+                p = 0.0
+                if not dropped:
+                    if i == 0 and self.use_pp:
+                        p = self.dropout.p
+                    else:
+                        h = self.dropout(h)
+                kw = {"fused": (arena, p, ops.RNG["seed"] + 104729 * (i + 1))}
+            elif not dropped:
                 h = self.dropout(h)
             if i >= self.n_conv:
                 h = layer(h)
             else:
                 if self.training and (i > 0 or not self.use_pp):
                     h = ctx.buffer.update(i, h, overlap=True)          # model.py:47-48, 82-83
-                h = layer(g, h, *norms)
+                h = layer(g, h, *norms, **kw)
+                if arena is not None and i == self.n_layers - 1:
+                    self._padded_logits = getattr(layer, "_padded_out", None)
             dropped = False
             if i < self.n_layers - 1:
                 h, dropped = self._between(i, h, True)

@@ -166,6 +166,55 @@ def spmm(g: DeviceGraph, x: torch.Tensor, out: Optional[torch.Tensor] = None, *,
     return out
 
 
+class CompactedCols:
+    """Per-epoch compaction of a column-mapped matrix (``bns_graph_compact_cols``): the sampled entries of every
+    chunk, already mapped to rows of X, moved to the front of the chunk's own index range."""
+
+    def __init__(self, g: DeviceGraph, with_weights: bool = False):
+        self.g = g
+        dev = g.device
+        self.cidx = torch.empty(max(g.nnz, 1), dtype=torch.int32, device=dev)
+        self.cw = torch.empty(max(g.nnz, 1), dtype=torch.float32, device=dev) if with_weights else None
+        self.chunk_cnt = torch.zeros(max(g.n_chunks, 1), dtype=torch.int32, device=dev)
+
+    def refresh(self, col_map: torch.Tensor, n_direct: int = 0, col_scale: Optional[torch.Tensor] = None) -> None:
+        _req(col_map, torch.int32, "col_map")
+        if (col_scale is None) != (self.cw is None):
+            raise _lib.BnsError("CompactedCols: col_scale must be given exactly when it was built with_weights")
+        with torch.cuda.device(self.g.device):
+            check(lib.bns_graph_compact_cols(self.g._h, col_map.data_ptr(), n_direct, _ptr(col_scale), self.cidx.data_ptr(),
+                                             _ptr(self.cw), self.chunk_cnt.data_ptr(), _stream_ptr()),
+                  "bns_graph_compact_cols")
+
+
+def spmm_compact(c: CompactedCols, x: torch.Tensor, out: torch.Tensor, *, row_scale: Optional[torch.Tensor] = None,
+                 accumulate: bool = False, slab: int = 0, live_nnz: Optional[int] = None) -> torch.Tensor:
+    """``bns_spmm_compact_f32``: the SpMM over the compacted (sampled) entries only."""
+    g = c.g
+    _req(x, torch.float32, "x")
+    _req(out, torch.float32, "out")
+    if x.dim() != 2 or x.stride(1) != 1 or out.stride(1) != 1 or out.shape[1] != x.shape[1]:
+        raise _lib.BnsError("x / out must be row-major [*, F]")
+    F = x.shape[1]
+    ws = g.workspace(F)
+    prof = PROFILE
+    if prof is not None:
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        ev0.record(torch.cuda.current_stream(x.device))
+    with torch.cuda.device(x.device):
+        check(lib.bns_spmm_compact_f32(g._h, c.cidx.data_ptr(), _ptr(c.cw), c.chunk_cnt.data_ptr(), x.data_ptr(), x.stride(0),
+                                       F, out.data_ptr(), out.stride(0), _ptr(row_scale), x.shape[0], slab,
+                                       1 if accumulate else 0, _ptr(ws), 0 if ws is None else ws.numel(), _stream_ptr()),
+              "bns_spmm_compact_f32")
+    if prof is not None:
+        ev1.record(torch.cuda.current_stream(x.device))
+        live = int(g.nnz * min(1.0, x.shape[0] / max(g.n_cols, 1))) if live_nnz is None else live_nnz
+        # algorithmic bytes of the SAMPLED product: its live entries, the rows of X it can reference, the output rows
+        alg = 8 * (g.n_rows + 1) + 4 * live + 4 * F * x.shape[0] + 4 * F * out.shape[0]
+        prof.append((ev0, ev1, alg, live, F, live))
+    return out
+
+
 def sddmm_dot(g: DeviceGraph, a: torch.Tensor, b: torch.Tensor, *, row_map=None, col_map=None, n_direct: int = 0,
               out: Optional[torch.Tensor] = None) -> torch.Tensor:
     """``out[k] = <a[arow(r)], b[xrow(c_k)]>`` for every entry ``k`` (``bns_sddmm_dot_f32``)."""
@@ -324,7 +373,10 @@ class LnReluDropout(torch.autograd.Function):
     """``dropout_p(relu(layer_norm(x)))`` in one pass each way (``bns_ln_relu_dropout_{fwd,bwd}_f32``)."""
 
     @staticmethod
-    def forward(ctx, x, gamma, beta, eps: float, p: float, seed: int):
+    def forward(ctx, x, gamma, beta, eps: float, p: float, seed: int, grad_slots=None):
+        """``grad_slots = (dgamma, dbeta)``: destinations of the parameter gradients (slots of fused.ParamArena); the
+        backward then writes them there and returns None for gamma / beta."""
+        ctx.grad_slots = grad_slots
         x = x.contiguous()
         n, F = x.shape
         y = torch.empty_like(x)
@@ -347,7 +399,10 @@ class LnReluDropout(torch.autograd.Function):
         dy = dy.contiguous()
         n, F = x.shape
         dx = torch.empty_like(x)
-        dgamma, dbeta = torch.empty_like(gamma), torch.empty_like(beta)
+        if ctx.grad_slots is not None:
+            dgamma, dbeta = ctx.grad_slots
+        else:
+            dgamma, dbeta = torch.empty_like(gamma), torch.empty_like(beta)
         # per (device, width, stream): ranks that live as threads of one process (tests, smoke) run their backward
         # passes concurrently on their own streams and must not share the partial-sum scratch
         key = (x.device, F, torch.cuda.current_stream(x.device).cuda_stream)
@@ -360,7 +415,9 @@ class LnReluDropout(torch.autograd.Function):
                                                   eps, p, seed & (2**64 - 1), off & (2**64 - 1), _ptr(off_dev),
                                                   dx.data_ptr(), dx.stride(0), dgamma.data_ptr(), dbeta.data_ptr(),
                                                   ws.data_ptr(), ws.numel(), _stream_ptr()), "bns_ln_relu_dropout_bwd_f32")
-        return dx, dgamma, dbeta, None, None, None
+        if ctx.grad_slots is not None:
+            return dx, None, None, None, None, None, None
+        return dx, dgamma, dbeta, None, None, None, None
 
 
 def ln_relu_dropout_supported(x: torch.Tensor, F: int) -> bool:

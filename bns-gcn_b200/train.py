@@ -143,22 +143,32 @@ def select_node(boundary, send_size, sampler: Optional[ops.BoundarySampler] = No
     return sampler.sample(seed, epoch)[1]
 
 
-def construct_graph(part: PartitionGraph, graph, pos, one_hops):
+def construct_graph(part: PartitionGraph, graph, pos, one_hops, hops_cat=None):
     """train.py:256-281 (K7).  Instead of a new heterograph: refresh the slot map of the static graph.
-    U-numbering = ``[inner | sampled halo of peer 0 | peer 1 ...]`` in the order of the received ``one_hops``."""
+    U-numbering = ``[inner | sampled halo of peer 0 | peer 1 ...]`` in the order of the received ``one_hops``.
+    ``hops_cat`` (the received lists as ONE tensor, from ``Buffer.exchange_ids``): all peers in one launch, together
+    with the inverse maps of the gradient scatter (``Buffer.update_maps``); otherwise one small launch per peer.
+    Either way the halo matrix is then compacted to this epoch's sampled columns."""
     rank, size = _rank_size()
     tot = part.n_in
-    if part.n_halo:
-        ops.fill_i32(part.slot, -1)
-    for i in range(size):
-        if i == rank:
-            continue
-        u = one_hops[i]
-        if u is None or u.shape[0] == 0:
-            continue
-        ops.halo_slot_update(pos[i], u, part.n_in, tot - part.n_in, part.slot)
-        tot += u.shape[0]
+    if hops_cat is not None:
+        buf = ctx.buffer._get()
+        buf.update_maps(buf._selected_cat, hops_cat, part.slot)
+        tot += int(hops_cat.shape[0])
+    else:
+        if part.n_halo:
+            ops.fill_i32(part.slot, -1)
+        for i in range(size):
+            if i == rank:
+                continue
+            u = one_hops[i]
+            if u is None or u.shape[0] == 0:
+                continue
+            ops.halo_slot_update(pos[i], u, part.n_in, tot - part.n_in, part.slot)
+            tot += u.shape[0]
     part.n_u = tot
+    if size > 1:
+        part.refresh_compaction()
     return part
 
 
@@ -275,6 +285,21 @@ class TrainState:
     epoch_dev: Optional[torch.Tensor] = None     # int64 [1] on the device: epochs started so far
     graph_mode: bool = False
     train_idx: Optional[torch.Tensor] = None     # nonzero(train_mask), computed once (mask indexing would sync)
+    arena: Optional[object] = None               # fused.ParamArena when the fused training step is on
+
+
+def _fused_eligible(args, layer_size, dev) -> bool:
+    """The fused training step (fused.py) covers the BASELINE configuration family: GraphSAGE, --use-pp, LayerNorm +
+    ReLU between the layers, no trailing linear layers, widths the 16-byte vector / TMA paths take.  BNS_FUSED=0 turns
+    it off (the op-by-op autograd path, kept for every other configuration, then runs here too)."""
+    import os
+    from .module import dense
+    if os.environ.get("BNS_FUSED", "1") == "0" or dense.MODE != "tc" or dev.type != "cuda":
+        return False
+    if args.model != 'graphsage' or not args.use_pp or args.n_linear != 0 or args.norm != 'layer':
+        return False
+    widths_ok = (2 * layer_size[0]) % 4 == 0 and all(w % 4 == 0 and w <= 1024 for w in layer_size[1:-1])
+    return widths_ok and len(layer_size) >= 3
 
 
 def setup(graph: LocalGraph, node_dict, gpb, args, device=None) -> TrainState:
@@ -300,9 +325,16 @@ def setup(graph: LocalGraph, node_dict, gpb, args, device=None) -> TrainState:
         if lock is not None:
             lock.release()
     model.to(dev)
-    ctx.reducer.init(model)
-    for name, param in model.named_parameters():
-        param.register_hook(reduce_hook(param, name, args.n_train))         # train.py:337-338
+    arena = None
+    if _fused_eligible(args, layer_size, dev):
+        from . import fused
+        arena = fused.ParamArena(model)
+        model._arena = arena
+        ctx.reducer.init_arena(arena)
+    else:
+        ctx.reducer.init(model)
+        for name, param in model.named_parameters():
+            param.register_hook(reduce_hook(param, name, args.n_train))     # train.py:337-338
     labels = node_dict['label']
     part_train = int(node_dict['train_mask'].int().sum().item())
     pos = get_pos(node_dict, gpb)
@@ -311,6 +343,12 @@ def setup(graph: LocalGraph, node_dict, gpb, args, device=None) -> TrainState:
     ctx.buffer.init_buffer(in_graph.n_rows, ratio, send_size, recv_size,
                            layer_size[:args.n_layers - args.n_linear], use_pp=args.use_pp, backend=args.backend,
                            device=dev)
+    if size > 1 and ctx.buffer._get()._p2p is not None:
+        # slot map + the inverse maps of the gradient scatter in ONE allocation (one memset + one kernel per epoch)
+        n_slot = max(graph.n_halo, 1)
+        maps = torch.full((n_slot + (size - 1) * graph.n_in,), -1, dtype=torch.int32, device=dev)
+        part.slot = maps[:n_slot]
+        ctx.buffer._get().set_maps(maps, n_slot, pos)
     out_deg_all = collect_out_degree(node_dict, boundary)                   # train.py:350
     if args.use_pp:
         node_dict['feat'] = precompute(part, graph, node_dict, boundary, args.model, gpb, pos, out_deg_all)
@@ -318,19 +356,26 @@ def setup(graph: LocalGraph, node_dict, gpb, args, device=None) -> TrainState:
         loss_fcn = torch.nn.BCEWithLogitsLoss(reduction='sum')              # train.py:358-361
     else:
         loss_fcn = torch.nn.CrossEntropyLoss(reduction='sum')
-    # capturable: the step counter lives on the device, so the optimizer step can sit inside a CUDA graph
-    optimizer = torch.optim.Adam(model.parameters(), lr=args.lr, weight_decay=args.weight_decay, capturable=True)
+    if arena is not None:
+        from . import fused
+        optimizer = fused.FusedAdam(arena, lr=args.lr, weight_decay=args.weight_decay)
+    else:
+        # capturable: the step counter lives on the device, so the optimizer step can sit inside a CUDA graph
+        optimizer = torch.optim.Adam(model.parameters(), lr=args.lr, weight_decay=args.weight_decay, capturable=True)
     out_norm = None
     if args.model == 'gcn':
         in_norm = torch.sqrt(node_dict['in_deg'].float())                   # train.py:377-378
         out_norm = torch.sqrt(out_deg_all.float())
+        if graph.n_halo:
+            part.halo_col_scale = part.recip(out_norm)[graph.n_in:].contiguous()
+            part.compact = None
     else:
         in_norm = node_dict['in_deg']                                       # train.py:380 (unused by GAT)
     sampler = ops.BoundarySampler(boundary, send_size, dev) if size > 1 else None
     return TrainState(args, part, model, optimizer, loss_fcn, node_dict['feat'], labels, node_dict['train_mask'],
                       in_norm, out_norm, boundary, pos, send_size, recv_size, ratio, sampler, part_train,
                       epoch_dev=torch.zeros(1, dtype=torch.int64, device=dev),
-                      train_idx=torch.nonzero(node_dict['train_mask'], as_tuple=True)[0])
+                      train_idx=torch.nonzero(node_dict['train_mask'], as_tuple=True)[0], arena=arena)
 
 
 def _forward_logits(st: TrainState, epoch: int, selected: Optional[list] = None) -> torch.Tensor:
@@ -345,20 +390,26 @@ def _forward_logits(st: TrainState, epoch: int, selected: Optional[list] = None)
     else:
         ops.RNG["offset"], ops.RNG["offset_dev"] = int(epoch), None
         comm_timer.clear()                  # train.py:425 (interval names are per epoch)
+    hops_cat = None
     if size > 1:
+        sel_cat = None
         if selected is None and st.graph_mode:
             # replayed from a CUDA graph: the Philox offset is (device epoch counter - 1), i.e. the same epoch
             # index an eager run passes as an immediate
-            selected = st.sampler.sample(getattr(args, 'sampler_seed', 0), 2 ** 64 - 1, st.epoch_dev)[1]
+            sel_cat, selected = st.sampler.sample(getattr(args, 'sampler_seed', 0), 2 ** 64 - 1, st.epoch_dev)
         elif selected is None:
-            selected = st.sampler.sample(getattr(args, 'sampler_seed', 0), epoch)[1]            # K6
-        recv_shape = [torch.Size([s]) for s in st.recv_size]
-        one_hops = data_transfer(selected, recv_shape, tag=TransferTag.NODE, dtype=torch.long)  # C3
-        ctx.buffer.set_selected(selected)
+            sel_cat, selected = st.sampler.sample(getattr(args, 'sampler_seed', 0), epoch)      # K6
+        buf = ctx.buffer._get()
+        buf.set_selected(selected, sel_cat)
+        if buf.uses_p2p_ids():
+            hops_cat, one_hops = buf.exchange_ids(buf._selected_cat)                            # C3 over peer memory
+        else:
+            recv_shape = [torch.Size([s]) for s in st.recv_size]
+            one_hops = data_transfer(selected, recv_shape, tag=TransferTag.NODE, dtype=torch.long)  # C3
     else:
         selected, one_hops = [None], [None]
     st.selected, st.one_hops = selected, one_hops
-    g = construct_graph(st.part, None, st.pos, one_hops)                                        # K7
+    g = construct_graph(st.part, None, st.pos, one_hops, hops_cat)                              # K7
     st.model.train()
     if args.model == 'gcn':
         return st.model(g, st.feat, st.in_norm, st.out_norm)
@@ -373,6 +424,17 @@ def train_epoch(st: TrainState, epoch: int, selected: Optional[list] = None) -> 
     """One pass of the epoch body (train.py:388-413).  Returns the local sum-reduced loss (device scalar).
     ``selected`` injects the sampled sets (parity runs); by default they come from the Philox sampler."""
     logits = _forward_logits(st, epoch, selected)
+    if st.arena is not None:
+        # fused step: loss + d(logits) in one kernel (the 1/n_train of helper/reducer.py:34 rides on d(logits)), backward
+        # through the layer functions (gradients land in the arena = the all-reduce bucket), one all-reduce, one Adam
+        from . import fused
+        pad = st.model._padded_logits
+        loss, dl = fused.softmax_xent(pad.detach(), st.args.n_class, st.labels, st.train_mask, 1.0 / st.args.n_train)
+        pad.backward(dl)
+        ctx.reducer.synchronize()
+        st.optimizer.step()
+        st.last_logits = logits
+        return loss
     # train.py:406 indexes with the boolean mask; the equivalent index list avoids a host sync per epoch
     loss = st.loss_fcn(logits[st.train_idx], st.labels[st.train_idx])
     st.optimizer.zero_grad(set_to_none=True)
@@ -394,11 +456,14 @@ def probe_loss(st: TrainState, epoch: int = 0, selected: Optional[list] = None) 
     try:
         with torch.no_grad():
             logits = _forward_logits(st, epoch, selected)
-            loss = st.loss_fcn(logits[st.train_idx], st.labels[st.train_idx])
+            loss = st.loss_fcn(logits[st.train_idx], st.labels[st.train_idx]).double().reshape(1)
     finally:
         for m, p_ in drops:
             m.p = p_
         st.epoch_dev.sub_(1)
+    # the sum over ranks -- and the rendezvous that keeps a fast rank's NEXT exchange out of the slabs a slow rank is
+    # still reading (a training epoch ends with the gradient all-reduce; a forward-only pass must bring its own)
+    ctx.comm().all_reduce_sum(loss)
     return loss.detach()
 
 
@@ -430,6 +495,11 @@ class GraphedEpoch:
         buf, red = ctx.buffer._get(), ctx.reducer._get()
         st.graph_mode = buf.graph_mode = red.graph_mode = True
         buf.seq_dev = st.epoch_dev
+        # flag values of the replays: seq_base + epoch counter, strictly above every value the eager epochs (and any
+        # forward-only probe) have already published
+        buf.seq_base = max(buf._seq.values(), default=0) - int(st.epoch_dev.item())
+        assert buf.seq_base >= 0 or _rank_size()[1] == 1, buf.seq_base
+        buf.seq_base = max(buf.seq_base, 0)
         self.graph = torch.cuda.CUDAGraph()
         try:
             # thread_local: other threads of the process (NCCL watchdog, copy threads) may keep calling CUDA meanwhile

@@ -36,7 +36,7 @@ extern "C" {
 #define BNS_E_WORKSPACE  (-3)   /* workspace too small */
 #define BNS_E_UNSUPPORTED (-4)
 
-#define BNS_ABI_VERSION 1
+#define BNS_ABI_VERSION 2
 
 typedef struct bns_graph bns_graph_t;   /* opaque: a static CSR matrix resident in HBM */
 typedef struct bns_p2p   bns_p2p_t;     /* opaque: peer-mapped exchange slabs of one rank */
@@ -136,7 +136,9 @@ int bns_split_tf32_f32(const float *x, int64_t n, float *hi, float *lo, void *st
  * BNS_E_INVALID and the caller uses the library GEMM.
  * ----------------------------------------------------------------------------------------------*/
 int    bns_dense_tn_3xtf32(const float *A, int64_t lda, const float *B, int64_t ldb, const float *bias /*device [N] or NULL*/,
-                           const float *addend /*device [M, N] with leading dimension ldadd, or NULL*/, int64_t ldadd,
+                           const float *addend /*device [M, N] with leading dimension ldadd, or NULL; may alias C*/, int64_t ldadd,
+                           const float *row_scale /*device [M] or NULL: C[r, :] = (A B^T + bias + addend)[r, :] * row_scale[r]
+                                                    (the 1/deg pre-scale of the aggregation's backward, module/layer.py:91)*/,
                            float *C, int64_t ldc, int64_t M, int64_t N, int64_t K, void *stream);
 size_t bns_dense_nt_workspace_bytes(int64_t R, int64_t N1, int64_t N2);
 int    bns_dense_nt_3xtf32(const float *A, int64_t lda, const float *B, int64_t ldb, float *C, int64_t ldc,
@@ -144,8 +146,9 @@ int    bns_dense_nt_3xtf32(const float *A, int64_t lda, const float *B, int64_t 
 /* Bias gradient of the same layers (autograd's dY.sum(0)): out[c] = sum_r X[r, c], two deterministic passes.
  * cols % 4 == 0, cols <= 1024, ld % 4 == 0, 16-byte aligned; ws >= bns_colsum_workspace_bytes(cols). */
 size_t bns_colsum_workspace_bytes(int64_t cols);
-int    bns_colsum_f32(const float *X, int64_t ld, int64_t rows, int64_t cols, float *out, void *ws, size_t ws_bytes,
-                      void *stream);
+int    bns_colsum_f32(const float *X, int64_t ld, int64_t rows, int64_t cols, float *out,
+                      float *out2 /*optional second destination (linear1.bias and linear2.bias share dY.sum(0))*/, void *ws,
+                      size_t ws_bytes, void *stream);
 
 /* ------------------------------------------------------------------------------------------------
  * K10 (GAT, module/model.py:96-132 via dgl.nn.GATConv): the attention gradient.  For every entry k of row r:
@@ -258,6 +261,124 @@ int bns_p2p_put_rows_f32(bns_p2p_t *p, int32_t peer, size_t remote_off, int64_t 
  * (20 s): a peer that never signals traps the kernel (a loud CUDA error) instead of hanging the device. */
 int bns_p2p_wait_flag(bns_p2p_t *p, int32_t flag_index, uint64_t flag_value, const uint64_t *flag_value_dev,
                       void *stream);
+
+
+/* ================================================================================================
+ * ABI 2: the rest of the epoch (train.py:385-425) as ONE launch per step instead of one per peer / per parameter /
+ * per ATen op.  At 8 partitions the round-1 epoch spent ~59 % of its time in such launches.
+ * ================================================================================================*/
+#define BNS_MAX_PEERS 16
+
+/* ------------------------------------------------------------------------------------------------
+ * K7': slot map of ALL peers + the inverse maps the gradient scatter walks, one memset + one kernel.  Replaces the
+ * per-peer loop of train.py:256-281 (construct_graph) done by bns_fill_i32 + bns_halo_slot_update x (P-1):
+ *     slot[pos_s[one_hops_cat[k]] - n_in] = k                         k over the concatenated received id lists
+ *     inv_s[selected_cat[i]] = i - sel_begin[s]                       i over the concatenated sampled id lists
+ * Segments = the peers in ascending order, self skipped.  [fill_base, +fill_bytes) -- the allocation that holds `slot`
+ * and every inv_s -- is set to -1 first.
+ * ----------------------------------------------------------------------------------------------*/
+typedef struct bns_epoch_maps {
+    int32_t n_seg;
+    int64_t sel_begin[BNS_MAX_PEERS + 1];
+    int64_t hop_begin[BNS_MAX_PEERS + 1];
+    const int64_t *pos[BNS_MAX_PEERS];      /* device: get_pos() of train.py:90-104 */
+    int32_t *inv[BNS_MAX_PEERS];            /* device [n_in] each, may be NULL */
+    const int64_t *selected_cat, *one_hops_cat;
+    int32_t *slot;                          /* device [n_halo] */
+    int64_t n_in;
+} bns_epoch_maps;
+int bns_epoch_maps_update(const bns_epoch_maps *maps /*host*/, void *fill_base, size_t fill_bytes, void *stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * K1 on the SAMPLED halo only.  bns_graph_compact_cols rewrites, once per epoch, the column ids of a column-mapped
+ * matrix (A_out with col_map = slot): chunk by chunk, the entries whose column is sampled are moved -- already mapped to
+ * rows of X, CSR order kept -- to the front of the chunk's own index range in `cidx`, their number goes to
+ * `chunk_cnt`; bns_spmm_compact_f32 then runs the plain kernel over exactly those entries.  Same numbers added in the
+ * same order as bns_spmm_sum_f32(col_map): bit-identical results, work proportional to the sample
+ * (train.py:256-281 builds the sampled graph per epoch for the same reason).
+ * ----------------------------------------------------------------------------------------------*/
+int bns_graph_compact_cols(const bns_graph_t *g, const int32_t *col_map, int64_t n_direct,
+                           const float *col_scale /*device [n_cols] or NULL: gathered per live entry into cw*/,
+                           int32_t *cidx /*device [nnz]*/, float *cw /*device [nnz] or NULL*/,
+                           int32_t *chunk_cnt /*device [n_chunks]*/, void *stream);
+int bns_spmm_compact_f32(const bns_graph_t *g, const int32_t *cidx, const float *cw, const int32_t *chunk_cnt,
+                         const float *X, int64_t ldx, int64_t F, float *Y, int64_t ldy, const float *row_scale,
+                         int64_t x_rows, int32_t slab_hint, int accumulate, void *ws, size_t ws_bytes, void *stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * C1/C2 + K3/K5 for ALL peers at once (helper/feature_buffer.py:101-129).
+ * bns_p2p_put_all_f32: segment s sends rows [row_begin[s], row_begin[s+1]) of the concatenated send list to peer[s]:
+ *     remote_s[i, :F] = H[idx_cat[row_begin[s] + i], :F] / div[s]      (idx_cat == NULL: H[src_begin[s] + i, :F])
+ * into the peer's slab at byte offset remote_off[s]; after the last row of the LAUNCH every peer's flags[flag_index]
+ * is set to flag_value (+ *flag_value_dev) with a system-scope release.  ticket_index < world + 16 picks the completion
+ * counter; launches that share one must be stream-ordered.
+ * bns_p2p_put_ids_i64: the same for the sampled id lists (data_transfer(..., tag=NODE), helper/utils.py:187-213).
+ * bns_p2p_wait_all: one kernel that waits for n flags of this rank (bounded spin, 20 s -> trap).
+ * bns_scatter_rows_all_f32: G[r, :] += recv_s[inv_s[r], :] / div[s] for every segment s IN ORDER and every row r with
+ *     inv_s[r] >= 0 -- the P-1 scatter-adds of :129 in the reference's peer order, race-free in one launch.
+ * ----------------------------------------------------------------------------------------------*/
+typedef struct bns_put_all {
+    int32_t n_seg;
+    int64_t row_begin[BNS_MAX_PEERS + 1];
+    int32_t peer[BNS_MAX_PEERS];
+    uint64_t remote_off[BNS_MAX_PEERS];
+    int64_t src_begin[BNS_MAX_PEERS];
+    float div[BNS_MAX_PEERS];
+} bns_put_all;
+int bns_p2p_put_all_f32(bns_p2p_t *p, const bns_put_all *segs /*host*/, int64_t ld_remote, const float *H, int64_t ldh,
+                        int64_t F, const int64_t *idx_cat, int32_t flag_index, int32_t ticket_index, uint64_t flag_value,
+                        const uint64_t *flag_value_dev, void *stream);
+int bns_p2p_put_ids_i64(bns_p2p_t *p, int32_t n_seg, const int64_t *begin /*host [n_seg+1]*/, const int32_t *peers /*host*/,
+                        const uint64_t *remote_off /*host*/, const int64_t *ids_cat /*device*/, int32_t flag_index,
+                        int32_t ticket_index, uint64_t flag_value, const uint64_t *flag_value_dev, void *stream);
+int bns_p2p_wait_all(bns_p2p_t *p, int32_t n, const int32_t *flag_indices /*host*/, uint64_t flag_value,
+                     const uint64_t *flag_value_dev, void *stream);
+int bns_scatter_rows_all_f32(float *G, int64_t ldg, int64_t n_rows, int64_t F, int32_t n_seg,
+                             const int32_t *const *inv /*host array of device pointers*/,
+                             const float *const *recv /*host array of device pointers*/, int64_t ld_recv,
+                             const float *div /*host*/, void *stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Loss and its gradient in one launch.  Replaces train.py:406-408 for the two losses of train.py:358-361:
+ *     loss = CrossEntropyLoss(reduction='sum')(logits[train_mask], labels[train_mask])          (labels != NULL)
+ *     loss = BCEWithLogitsLoss(reduction='sum')(logits[train_mask], labels[train_mask])        (labels_f != NULL)
+ * dlogits[r, :n_class] = d loss / d logits[r, :] * grad_scale for train rows, 0 for the others and for the pad columns
+ * [n_class, n_cols_out).  grad_scale = 1 / n_train folds helper/reducer.py:34 (grad /= n_train) into the source of
+ * every gradient.  The loss is summed block by block in a fixed order (deterministic).  ws: bns_xent_workspace_bytes()
+ * bytes, zeroed ONCE by the caller.
+ * ----------------------------------------------------------------------------------------------*/
+size_t bns_xent_workspace_bytes(void);
+int bns_xent_f32(const float *logits, int64_t ld, int64_t n_rows, int32_t n_class, const int64_t *labels,
+                 const float *labels_f, int64_t ldl, const uint8_t *mask /*device bool [n_rows] or NULL*/, float grad_scale,
+                 float *loss_out /*device [1]*/, float *dlogits, int64_t ldd, int32_t n_cols_out, void *ws, size_t ws_bytes,
+                 void *stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * torch.optim.Adam (train.py:362, :413) over ONE flat parameter arena: every parameter, its gradient and both moments
+ * live at the same offsets of four flat buffers, so the step is one launch (torch: ~15 multi-tensor launches).
+ *     g += weight_decay * p;  m += (1 - b1) (g - m);  v = b2 v + (1 - b2) g^2;
+ *     p -= lr / (1 - b1^t) * m / (sqrt(v) / sqrt(1 - b2^t) + eps),        t = *step_dev + 1
+ * bns_derive_refresh (enqueue right after): refreshes the table of derived parameters -- cached W^T for the input
+ * gradients, bias sums -- and advances *step_dev.  Entry layout: bns_derive_entry, table in device memory.
+ * ----------------------------------------------------------------------------------------------*/
+typedef struct bns_derive_entry {
+    int32_t op;        /* 0: dst[c * ld_dst + r] = a[r * ld_a + c], r < rows, c < cols;  1: dst[i] = a[i] + b[i], i < rows */
+    int32_t rows, cols, ld_a, ld_dst, pad_;
+    const float *a, *b;
+    float *dst;
+} bns_derive_entry;
+size_t bns_derive_entry_bytes(void);
+int bns_adam_step_f32(float *param, const float *grad, float *exp_avg, float *exp_avg_sq, int64_t n, float lr, float beta1,
+                      float beta2, float eps, float weight_decay, const int64_t *step_dev, void *stream);
+int bns_derive_refresh(const void *table_dev, int32_t n_entries, int64_t *step_dev, void *stream);
+
+/* y = dropout_p(x) with the Philox mask of bns_ln_relu_dropout_fwd_f32 (counter = (row, vector, offset), key = seed):
+ * module/model.py:80 for the layer-0 input; nothing but y is stored. */
+int bns_dropout_f32(const float *x, int64_t ldx, int64_t n, int64_t F, float p, uint64_t seed, uint64_t offset,
+                    const uint64_t *offset_dev, float *y, int64_t ldy, void *stream);
+/* y[r, :] = x[r, :] * row_scale[r] */
+int bns_scale_rows_f32(const float *x, int64_t ldx, int64_t n, int64_t F, const float *row_scale, float *y, int64_t ldy,
+                       void *stream);
 
 #ifdef __cplusplus
 }

@@ -441,3 +441,219 @@ def test_dense_bf16x3_is_fp32_accurate(built):
     assert _relerr(y.detach().double().cpu(), (xd @ wd.t() + bd).cpu()) < 2e-6
     assert _relerr(x.grad.double().cpu(), (dy.double() @ wd).cpu()) < 2e-6
     assert _relerr(w.grad.double().cpu(), (dy.double().t() @ xd).cpu()) < 2e-6
+
+
+# =====================================================================================================================
+# ABI 2: the one-launch-per-step kernels of csrc/fused.cuh
+# =====================================================================================================================
+@pytest.mark.parametrize("n,C,Cp", [(3000, 41, 44), (500, 5, 8), (1000, 100, 100)])
+def test_fused_cross_entropy_loss_and_gradient(built, n, C, Cp):
+    """bns_xent_f32 == CrossEntropyLoss(reduction='sum') over the masked rows, forward and d(logits) (train.py:358-361,
+    406-408); pad columns and unmasked rows get exact zeros; the loss is bit-reproducible."""
+    from bns_gcn_b200 import fused
+    dev = torch.device("cuda:0")
+    g = torch.Generator().manual_seed(n + C)
+    logits = (torch.randn(n, Cp, generator=g) * 3).to(dev)
+    labels = torch.randint(0, C, (n,), generator=g).to(dev)
+    mask = (torch.rand(n, generator=g) < 0.6).to(dev)
+    scale = 1.0 / 777.0
+    loss, dl = fused.softmax_xent(logits, C, labels, mask, scale)
+    x = logits[:, :C].detach().clone().requires_grad_(True)
+    ref = torch.nn.functional.cross_entropy(x[mask], labels[mask], reduction="sum")
+    ref.backward()
+    assert abs(loss.item() - ref.item()) <= 2e-6 * abs(ref.item())
+    assert _relerr(dl[:, :C].cpu(), (x.grad * scale).cpu()) < 2e-6
+    assert torch.all(dl[:, C:] == 0) and torch.all(dl[~mask] == 0)
+    loss2, dl2 = fused.softmax_xent(logits, C, labels, mask, scale)
+    assert loss2.item() == loss.item() and torch.equal(dl, dl2)
+
+
+def test_fused_bce_with_logits_loss_and_gradient(built):
+    from bns_gcn_b200 import fused
+    dev = torch.device("cuda:0")
+    g = torch.Generator().manual_seed(5)
+    n, C, Cp = 2000, 6, 8
+    logits = (torch.randn(n, Cp, generator=g) * 4).to(dev)
+    y = (torch.rand(n, C, generator=g) < 0.2).float().to(dev)
+    mask = (torch.rand(n, generator=g) < 0.7).to(dev)
+    loss, dl = fused.softmax_xent(logits, C, y, mask, 0.5)
+    x = logits[:, :C].detach().clone().requires_grad_(True)
+    ref = torch.nn.functional.binary_cross_entropy_with_logits(x[mask], y[mask], reduction="sum")
+    ref.backward()
+    assert abs(loss.item() - ref.item()) <= 2e-6 * abs(ref.item())
+    assert _relerr(dl[:, :C].cpu(), (x.grad * 0.5).cpu()) < 2e-6
+    assert torch.all(dl[:, C:] == 0) and torch.all(dl[~mask] == 0)
+
+
+@pytest.mark.parametrize("wd", [0.0, 5e-4])
+def test_fused_adam_matches_torch_adam(built, wd):
+    """bns_adam_step_f32 over the flat arena + bns_derive_refresh == torch.optim.Adam on the same parameters, several
+    steps; padded slots stay zero; cached transposes and bias sums follow the parameters."""
+    from bns_gcn_b200 import fused
+    dev = torch.device("cuda:0")
+    torch.manual_seed(0)
+    net = torch.nn.Sequential(torch.nn.Linear(30, 41), torch.nn.LayerNorm(41), torch.nn.Linear(41, 7)).to(dev)
+    ref = [p.detach().clone().requires_grad_(True) for p in net.parameters()]
+    arena = fused.ParamArena(net)
+    opt = fused.FusedAdam(arena, lr=1e-2, weight_decay=wd)
+    ropt = torch.optim.Adam(ref, lr=1e-2, weight_decay=wd)
+    w0 = net[0].weight
+    wt = arena.transposed(w0)                   # [30, 44] cache of the padded weight
+    bsum = arena.bias_sum(net[0].bias, net[1].bias)
+    assert arena.padded(w0).shape == (44, 30) and torch.all(arena.padded(w0)[41:] == 0)
+    g = torch.Generator().manual_seed(1)
+    for step in range(5):
+        for p, r in zip(net.parameters(), ref):
+            gr = torch.randn(p.shape, generator=g).to(dev)
+            p.grad.copy_(gr)                    # the arena's gradient views
+            r.grad = gr.clone()
+        opt.step()
+        ropt.step()
+        for p, r in zip(net.parameters(), ref):
+            assert _relerr(p.detach().cpu(), r.detach().cpu()) < 2e-6, step
+        assert torch.all(arena.padded(w0)[41:] == 0)
+        assert torch.equal(wt[:, :41], w0.detach().t()) and torch.all(wt[:, 41:] == 0)
+        assert torch.equal(bsum[:41], net[0].bias.detach() + net[1].bias.detach())
+    assert int(opt.step_dev.item()) == 5
+
+
+def test_scatter_rows_all_equals_successive_scatter_adds(built):
+    """bns_scatter_rows_all_f32 over the inverse maps of bns_epoch_maps_update == the P-1 successive
+    bns_scatter_add_div_f32 calls of the reference's order (helper/feature_buffer.py:111-129), bit for bit; the slot
+    map part of the same kernel == fill + per-peer bns_halo_slot_update."""
+    import ctypes
+    from bns_gcn_b200 import ops
+    from bns_gcn_b200._lib import EpochMaps, check, lib
+    dev = torch.device("cuda:0")
+    gen = torch.Generator().manual_seed(3)
+    n_in, n_halo, F, peers = 700, 500, 256, 3
+    sel = [torch.randperm(n_in, generator=gen)[:k] for k in (150, 0, 260)]
+    ratios = [0.3, 0.0, 0.26]
+    part_sizes = [400, 300, 500]
+    pos, hops, halo_next = [], [], n_in
+    for s_, ps in enumerate(part_sizes):
+        p_ = torch.full((ps,), -1, dtype=torch.int64)
+        cnt = [120, 200, 180][s_]
+        owned = torch.randperm(ps, generator=gen)[:cnt]
+        p_[owned] = halo_next + torch.arange(cnt)
+        halo_next += cnt
+        pos.append(p_)
+        hops.append(owned[torch.randperm(cnt, generator=gen)[:[40, 0, 77][s_]]])
+    sel_cat, hops_cat = torch.cat(sel).to(dev), torch.cat(hops).to(dev)
+    maps = torch.full((n_halo + peers * n_in,), 5, dtype=torch.int32, device=dev)
+    pos_d = [p_.to(dev) for p_ in pos]
+    m = EpochMaps()
+    m.n_seg = peers
+    a = b = 0
+    for s_ in range(peers):
+        m.sel_begin[s_], m.hop_begin[s_] = a, b
+        a += sel[s_].numel()
+        b += hops[s_].numel()
+        m.pos[s_] = pos_d[s_].data_ptr()
+        m.inv[s_] = maps[n_halo + s_ * n_in:].data_ptr()
+    m.sel_begin[peers], m.hop_begin[peers] = a, b
+    m.selected_cat, m.one_hops_cat, m.slot, m.n_in = sel_cat.data_ptr(), hops_cat.data_ptr(), maps.data_ptr(), n_in
+    check(lib.bns_epoch_maps_update(ctypes.byref(m), maps.data_ptr(), maps.numel() * 4,
+                                    torch.cuda.current_stream().cuda_stream))
+    slot_ref = torch.empty(n_halo, dtype=torch.int32, device=dev)
+    ops.fill_i32(slot_ref, -1)
+    off = 0
+    for s_ in range(peers):
+        if hops[s_].numel():
+            ops.halo_slot_update(pos_d[s_], hops[s_].to(dev), n_in, off, slot_ref)
+        off += hops[s_].numel()
+    assert torch.equal(maps[:n_halo], slot_ref)
+    for s_ in range(peers):
+        inv = maps[n_halo + s_ * n_in:n_halo + (s_ + 1) * n_in].cpu()
+        want = torch.full((n_in,), -1, dtype=torch.int32)
+        want[sel[s_]] = torch.arange(sel[s_].numel(), dtype=torch.int32)
+        assert torch.equal(inv, want)
+    G0 = torch.randn(n_in, F, generator=gen).to(dev)
+    recv = [torch.randn(max(sel[s_].numel(), 1), F, generator=gen).to(dev) for s_ in range(peers)]
+    order = [2, 0]                                   # the reference's ring order, peers with an empty sample skipped
+    ref = G0.clone()
+    for s_ in order:
+        ops.scatter_add_div(ref, sel[s_].to(dev), recv[s_][:sel[s_].numel()], ratios[s_])
+    got = G0.clone()
+    inv_p = (ctypes.c_void_p * 2)(*[maps[n_halo + s_ * n_in:].data_ptr() for s_ in order])
+    rcv_p = (ctypes.c_void_p * 2)(*[recv[s_].data_ptr() for s_ in order])
+    div = (ctypes.c_float * 2)(*[ratios[s_] for s_ in order])
+    check(lib.bns_scatter_rows_all_f32(got.data_ptr(), got.stride(0), n_in, F, 2, inv_p, rcv_p, F, div,
+                                       torch.cuda.current_stream().cuda_stream))
+    assert torch.equal(got, ref)
+
+
+@pytest.mark.parametrize("F", [256, 44, 604])
+def test_compacted_halo_spmm_is_bit_identical_to_the_column_mapped_one(built, F):
+    """bns_graph_compact_cols + bns_spmm_compact_f32 == bns_spmm_sum_f32(col_map): same entries, same order."""
+    from bns_gcn_b200 import ops
+    dev = torch.device("cuda:0")
+    gen = torch.Generator().manual_seed(17 + F)
+    n_rows, n_halo, n_slab = 600, 900, 90                        # ~10 % of the halo columns sampled
+    indptr, idx = _rand_csr(n_rows, n_halo, 40, seed=F, heavy=2)
+    slot = torch.full((n_halo,), -1, dtype=torch.int32)
+    chosen = torch.randperm(n_halo, generator=gen)[:n_slab]
+    slot[chosen] = torch.randperm(n_slab, generator=gen).int()
+    x = torch.randn(n_slab, F, generator=gen).to(dev)
+    rs = (torch.rand(n_rows, generator=gen) + 0.5).to(dev)
+    cs = (torch.rand(n_halo, generator=gen) + 0.5).to(dev)
+    g = ops.DeviceGraph.from_csr(indptr.to(dev), idx.int().to(dev), n_halo, 64)
+    y0 = torch.randn(n_rows, F, generator=gen).to(dev)
+    for weights in (False, True):
+        ref = y0.clone()
+        ops.spmm(g, x, ref, row_scale=rs, col_scale=cs if weights else None, col_map=slot.to(dev), n_direct=0,
+                 accumulate=True)
+        c = ops.CompactedCols(g, with_weights=weights)
+        c.refresh(slot.to(dev), 0, cs if weights else None)
+        got = y0.clone()
+        ops.spmm_compact(c, x, got, row_scale=rs, accumulate=True)
+        assert torch.equal(got, ref), weights
+        live = int((slot[idx] >= 0).sum())
+        assert int(c.chunk_cnt.sum()) == live
+    # a second epoch with another sample reuses the buffers
+    slot2 = torch.full((n_halo,), -1, dtype=torch.int32)
+    slot2[torch.randperm(n_halo, generator=gen)[:n_slab]] = torch.randperm(n_slab, generator=gen).int()
+    c.refresh(slot2.to(dev), 0, cs)
+    ref = torch.zeros(n_rows, F, device=dev)
+    ops.spmm(g, x, ref, col_scale=cs, col_map=slot2.to(dev), n_direct=0)
+    got = torch.zeros(n_rows, F, device=dev)
+    ops.spmm_compact(c, x, got)
+    assert torch.equal(got, ref)
+
+
+def test_dropout_and_scale_rows_kernels(built):
+    from bns_gcn_b200 import fused, ops
+    dev = torch.device("cuda:0")
+    x = torch.randn(4000, 1204, generator=torch.Generator().manual_seed(0)).to(dev)
+    ops.RNG.update(seed=9, offset=3, offset_dev=None)
+    y = fused.dropout(x, 0.5, 1234)
+    keep = (y != 0)
+    assert abs(keep.float().mean().item() - 0.5) < 0.005
+    assert torch.equal(y[keep], (x * 2.0)[keep])
+    assert torch.equal(y, fused.dropout(x, 0.5, 1234))
+    ops.RNG.update(offset=4)
+    assert not torch.equal(y, fused.dropout(x, 0.5, 1234))
+    ops.RNG.update(seed=0, offset=0, offset_dev=None)
+    assert fused.dropout(x, 0.0, 1) is x
+    rs = torch.rand(4000, device=dev)
+    assert torch.equal(fused.scale_rows(x, rs), x * rs.unsqueeze(1))
+
+
+def test_dense_epilogue_row_scale_and_in_place_addend(built):
+    from bns_gcn_b200.module import dense
+    dev = torch.device("cuda:0")
+    g = torch.Generator().manual_seed(2)
+    a = torch.randn(5000, 256, generator=g).to(dev)
+    w = (torch.rand(256, 256, generator=g) - 0.5).to(dev)
+    rs = (torch.rand(5000, generator=g) + 0.5).to(dev)
+    ref = (a.double() @ w.double().t()) * rs.double().unsqueeze(1)
+    got = dense.tc_mm_tn(a, w, row_scale=rs)
+    assert _relerr(got.double().cpu(), ref.cpu()) < 1e-5
+    acc = torch.randn(6000, 256, generator=g).to(dev)
+    want = acc.clone()
+    want[:5000] += (a.double() @ w.double().t()).float()
+    dense.tc_mm_tn(a, w, addend=acc[:5000], out=acc[:5000])          # C aliases the addend: accumulate in place
+    assert _relerr(acc.cpu(), want.cpu()) < 1e-5
+    o1, o2 = torch.empty(256, device=dev), torch.empty(256, device=dev)
+    dense.colsum(a, out=o1, out2=o2)
+    assert torch.equal(o1, o2) and _relerr(o1.cpu(), a.double().sum(0).float().cpu()) < 1e-5
