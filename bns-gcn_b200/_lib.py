@@ -105,6 +105,13 @@ SIGNATURES = {
     "bns_adam_step_f32": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_float, c_float, c_float, c_float,
                                   c_float, c_void_p, c_void_p]),
     "bns_derive_refresh": (c_int, [c_void_p, c_int32, c_void_p, c_void_p]),
+    "bns_bn_workspace_bytes": (c_size_t, [c_int64]),
+    "bns_bn_colsums_f32": (c_int, [c_int, c_void_p, c_int64, c_void_p, c_int64, c_int64, c_int64, c_void_p, c_void_p, c_void_p,
+                                   c_void_p, c_size_t, c_void_p]),
+    "bns_bn_apply_f32": (c_int, [c_void_p, c_int64, c_int64, c_int64, c_void_p, c_float, c_float, c_void_p, c_void_p, c_float,
+                                 c_void_p, c_void_p, c_void_p, c_int64, c_void_p, c_void_p, c_void_p]),
+    "bns_bn_bwd_f32": (c_int, [c_void_p, c_int64, c_void_p, c_int64, c_int64, c_int64, c_void_p, c_void_p, c_void_p, c_void_p,
+                               c_float, c_void_p, c_int64, c_void_p]),
     "bns_dropout_f32": (c_int, [c_void_p, c_int64, c_int64, c_int64, c_float, c_uint64, c_uint64, c_void_p, c_void_p,
                                 c_int64, c_void_p]),
     "bns_scale_rows_f32": (c_int, [c_void_p, c_int64, c_int64, c_int64, c_void_p, c_void_p, c_int64, c_void_p]),

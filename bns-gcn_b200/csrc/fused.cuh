@@ -698,3 +698,194 @@ extern "C" int bns_graph_compact_cols(const bns_graph_t *g, const int32_t *col_m
     BNS_CUDA(cudaGetLastError());
     return BNS_OK;
 }
+
+// =====================================================================================================================
+// SyncBatchNorm (--norm batch, module/sync_bn.py:7-56 of the reference): batch statistics over ALL partitions.
+// Per step and layer: ONE pass producing both moments (sum x, sum x^2) per column, one packed [2F] all-reduce (done by
+// the caller), ONE normalise+affine pass; mirrored in backward (sum dy, sum dy*x_hat -> packed all-reduce -> dx).  The
+// reference issues four [F] all-reduces and ~12 element-wise ATen launches for the same.
+// =====================================================================================================================
+namespace {
+
+// MODE 0: (x, x^2)      MODE 1: (dy, dy * x_hat) with x_hat = (x - mean) * rstd
+// block b sums a contiguous row range; thread (rg, c) owns float4 column c of every RG-th row of it; fixed order.
+template <int MODE>
+__global__ void __launch_bounds__(kThreads) colsum2_partial_kernel(const float *__restrict__ A, int64_t lda,
+                                                                  const float *__restrict__ X, int64_t ldx, int64_t rows, int CV,
+                                                                  const float4 *__restrict__ mean, const float4 *__restrict__ rstd,
+                                                                  float4 *__restrict__ partial) {
+    __shared__ float4 s0[kThreads], s1[kThreads];
+    const int RG = kThreads / CV;
+    const int rg = threadIdx.x / CV, c = threadIdx.x % CV;
+    float4 a0 = make_float4(0.f, 0.f, 0.f, 0.f), a1 = a0;
+    if (rg < RG) {
+        float4 mu = a0, rs = a0;
+        if (MODE == 1) { mu = mean[c]; rs = rstd[c]; }
+        const int64_t per = (rows + gridDim.x - 1) / gridDim.x;
+        const int64_t r0 = (int64_t)blockIdx.x * per, r1 = r0 + per < rows ? r0 + per : rows;
+        for (int64_t r = r0 + rg; r < r1; r += RG) {
+            const float4 v = __ldg(reinterpret_cast<const float4 *>(A + r * lda) + c);
+            a0.x += v.x; a0.y += v.y; a0.z += v.z; a0.w += v.w;
+            if (MODE == 0) {
+                a1.x = fmaf(v.x, v.x, a1.x); a1.y = fmaf(v.y, v.y, a1.y); a1.z = fmaf(v.z, v.z, a1.z); a1.w = fmaf(v.w, v.w, a1.w);
+            } else {
+                const float4 x = __ldg(reinterpret_cast<const float4 *>(X + r * ldx) + c);
+                a1.x = fmaf(v.x, (x.x - mu.x) * rs.x, a1.x); a1.y = fmaf(v.y, (x.y - mu.y) * rs.y, a1.y);
+                a1.z = fmaf(v.z, (x.z - mu.z) * rs.z, a1.z); a1.w = fmaf(v.w, (x.w - mu.w) * rs.w, a1.w);
+            }
+        }
+    }
+    s0[threadIdx.x] = a0; s1[threadIdx.x] = a1;
+    __syncthreads();
+    if (rg == 0) {
+        for (int g = 1; g < RG; ++g) {
+            const float4 u = s0[g * CV + c], w = s1[g * CV + c];
+            a0.x += u.x; a0.y += u.y; a0.z += u.z; a0.w += u.w;
+            a1.x += w.x; a1.y += w.y; a1.z += w.z; a1.w += w.w;
+        }
+        partial[(int64_t)blockIdx.x * 2 * CV + c] = a0;
+        partial[(int64_t)blockIdx.x * 2 * CV + CV + c] = a1;
+    }
+}
+
+// y = (x - mean) * rstd * w + b with mean = S1 / n, var = (S2 - mean * S1) / n (the reference's one-pass variance,
+// sync_bn.py:19-20); block 0 also stores mean / rstd for the backward and moves the running statistics
+__global__ void __launch_bounds__(kThreads) bn_apply_kernel(const float *__restrict__ x, int64_t ldx, int64_t rows, int32_t F,
+                                                           const float *__restrict__ sums, float n, float eps,
+                                                           const float *__restrict__ w, const float *__restrict__ b,
+                                                           float momentum, float *running_mean, float *running_var,
+                                                           float *__restrict__ y, int64_t ldy, float *mean_out, float *rstd_out) {
+    const int lane = threadIdx.x & 31;
+    const int64_t warps_total = (int64_t)gridDim.x * kWarps;
+    if (blockIdx.x == 0) {
+        for (int f = threadIdx.x; f < F; f += kThreads) {
+            const float mu = sums[f] / n, var = (sums[F + f] - mu * sums[f]) / n;
+            mean_out[f] = mu;
+            rstd_out[f] = 1.f / sqrtf(var + eps);
+            if (running_mean) {
+                running_mean[f] = running_mean[f] * (1.f - momentum) + mu * momentum;
+                running_var[f] = running_var[f] * (1.f - momentum) + var * momentum;
+            }
+        }
+    }
+    for (int f0 = lane * 4; f0 < F; f0 += 128) {
+        float mu[4], rs[4], ww[4], bb[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const int f = f0 + i;
+            mu[i] = sums[f] / n;
+            const float var = (sums[F + f] - mu[i] * sums[f]) / n;
+            rs[i] = 1.f / sqrtf(var + eps);
+            ww[i] = w[f]; bb[i] = b[f];
+        }
+        for (int64_t row = (int64_t)blockIdx.x * kWarps + (threadIdx.x >> 5); row < rows; row += warps_total) {
+            const float4 v = *reinterpret_cast<const float4 *>(x + row * ldx + f0);
+            float4 o;
+            o.x = fmaf((v.x - mu[0]) * rs[0], ww[0], bb[0]); o.y = fmaf((v.y - mu[1]) * rs[1], ww[1], bb[1]);
+            o.z = fmaf((v.z - mu[2]) * rs[2], ww[2], bb[2]); o.w = fmaf((v.w - mu[3]) * rs[3], ww[3], bb[3]);
+            *reinterpret_cast<float4 *>(y + row * ldy + f0) = o;
+        }
+    }
+}
+
+// dx = (w / n) * rstd * (n * dy - dbias - x_hat * dweight)      (sync_bn.py:51-54)
+__global__ void __launch_bounds__(kThreads) bn_bwd_kernel(const float *__restrict__ dy, int64_t lddy, const float *__restrict__ x,
+                                                         int64_t ldx, int64_t rows, int32_t F, const float *__restrict__ mean,
+                                                         const float *__restrict__ rstd, const float *__restrict__ w,
+                                                         const float *__restrict__ sums, float n, float *__restrict__ dx,
+                                                         int64_t lddx) {
+    const int lane = threadIdx.x & 31;
+    const int64_t warps_total = (int64_t)gridDim.x * kWarps;
+    for (int f0 = lane * 4; f0 < F; f0 += 128) {
+        float mu[4], rs[4], k[4], db[4], dw[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const int f = f0 + i;
+            mu[i] = mean[f]; rs[i] = rstd[f]; k[i] = (w[f] / n) * rs[i]; db[i] = sums[f]; dw[i] = sums[F + f];
+        }
+        for (int64_t row = (int64_t)blockIdx.x * kWarps + (threadIdx.x >> 5); row < rows; row += warps_total) {
+            const float4 g = *reinterpret_cast<const float4 *>(dy + row * lddy + f0);
+            const float4 v = *reinterpret_cast<const float4 *>(x + row * ldx + f0);
+            float4 o;
+            o.x = k[0] * (n * g.x - db[0] - (v.x - mu[0]) * rs[0] * dw[0]);
+            o.y = k[1] * (n * g.y - db[1] - (v.y - mu[1]) * rs[1] * dw[1]);
+            o.z = k[2] * (n * g.z - db[2] - (v.z - mu[2]) * rs[2] * dw[2]);
+            o.w = k[3] * (n * g.w - db[3] - (v.w - mu[3]) * rs[3] * dw[3]);
+            *reinterpret_cast<float4 *>(dx + row * lddx + f0) = o;
+        }
+    }
+}
+
+inline bool bn_shape_ok(const void *a, int64_t ld, int64_t F) {
+    return F > 0 && F % 4 == 0 && F <= kColsumMaxCols && ld % 4 == 0 && ld >= F && (reinterpret_cast<uintptr_t>(a) & 15u) == 0;
+}
+
+}  // namespace
+
+extern "C" size_t bns_bn_workspace_bytes(int64_t F) { return 2 * bns_colsum_workspace_bytes(F); }
+
+// mode 0: out[0:F] = column sums of A, out[F:2F] = column sums of A^2            (forward moments; X, mean, rstd unused)
+// mode 1: out[0:F] = column sums of A (= dy), out[F:2F] = column sums of A * x_hat, x_hat = (X - mean) * rstd
+// rows == 0 writes zeros.  Deterministic (fixed two-pass order).  ws: bns_bn_workspace_bytes(F).
+extern "C" int bns_bn_colsums_f32(int mode, const float *A, int64_t lda, const float *X, int64_t ldx, int64_t rows, int64_t F,
+                                  const float *mean, const float *rstd, float *out /*[2F]*/, void *ws, size_t ws_bytes,
+                                  void *stream) {
+    BNS_REQUIRE(mode == 0 || mode == 1, "bns_bn_colsums_f32: mode must be 0 or 1");
+    BNS_REQUIRE(out && (reinterpret_cast<uintptr_t>(out) & 15u) == 0, "bns_bn_colsums_f32: bad output");
+    BNS_REQUIRE(rows >= 0 && F > 0 && F % 4 == 0 && F <= kColsumMaxCols, "bns_bn_colsums_f32: need F %% 4 == 0, F <= 1024");
+    cudaStream_t st = as_stream(stream);
+    if (rows == 0) {
+        BNS_CUDA(cudaMemsetAsync(out, 0, 2 * F * sizeof(float), st));
+        return BNS_OK;
+    }
+    BNS_REQUIRE(A && bn_shape_ok(A, lda, F), "bns_bn_colsums_f32: A must have 16-byte aligned rows");
+    if (mode == 1)
+        BNS_REQUIRE(X && mean && rstd && bn_shape_ok(X, ldx, F) && ((reinterpret_cast<uintptr_t>(mean) | reinterpret_cast<uintptr_t>(rstd)) & 15u) == 0,
+                    "bns_bn_colsums_f32: mode 1 needs X, mean, rstd (16-byte aligned)");
+    if (!ws || ws_bytes < bns_bn_workspace_bytes(F) || (reinterpret_cast<uintptr_t>(ws) & 15u))
+        return fail(BNS_E_WORKSPACE, "bns_bn_colsums_f32: workspace %zu bytes < %zu needed", ws_bytes, bns_bn_workspace_bytes(F));
+    const int CV = (int)(F / 4);
+    int blocks = colsum_blocks();
+    if ((int64_t)blocks > rows) blocks = (int)rows;
+    if (mode == 0)
+        colsum2_partial_kernel<0><<<blocks, kThreads, 0, st>>>(A, lda, nullptr, 0, rows, CV, nullptr, nullptr, reinterpret_cast<float4 *>(ws));
+    else
+        colsum2_partial_kernel<1><<<blocks, kThreads, 0, st>>>(A, lda, X, ldx, rows, CV, reinterpret_cast<const float4 *>(mean),
+                                                              reinterpret_cast<const float4 *>(rstd), reinterpret_cast<float4 *>(ws));
+    colsum_final_kernel<<<(2 * CV + 127) / 128, 128, 0, st>>>(reinterpret_cast<const float4 *>(ws), blocks, 2 * CV,
+                                                              reinterpret_cast<float4 *>(out), nullptr);
+    g_launches += 2;
+    BNS_CUDA(cudaGetLastError());
+    return BNS_OK;
+}
+
+extern "C" int bns_bn_apply_f32(const float *x, int64_t ldx, int64_t rows, int64_t F, const float *sums /*[2F], all ranks*/,
+                                float whole_size, float eps, const float *weight, const float *bias, float momentum,
+                                float *running_mean, float *running_var, float *y, int64_t ldy, float *mean_out, float *rstd_out,
+                                void *stream) {
+    BNS_REQUIRE(rows >= 0 && F > 0 && F % 4 == 0 && F <= kColsumMaxCols, "bns_bn_apply_f32: need F %% 4 == 0, F <= 1024");
+    BNS_REQUIRE(sums && weight && bias && mean_out && rstd_out && whole_size > 0.f, "bns_bn_apply_f32: NULL argument");
+    BNS_REQUIRE((running_mean == nullptr) == (running_var == nullptr), "bns_bn_apply_f32: running stats go together");
+    BNS_REQUIRE(rows == 0 || (x && y && bn_shape_ok(x, ldx, F) && bn_shape_ok(y, ldy, F)), "bns_bn_apply_f32: bad matrix");
+    bn_apply_kernel<<<ln_grid(rows > 0 ? rows : 1), kThreads, 0, as_stream(stream)>>>(x, ldx, rows, (int32_t)F, sums, whole_size, eps,
+                                                                                    weight, bias, momentum, running_mean,
+                                                                                    running_var, y, ldy, mean_out, rstd_out);
+    ++g_launches;
+    BNS_CUDA(cudaGetLastError());
+    return BNS_OK;
+}
+
+extern "C" int bns_bn_bwd_f32(const float *dy, int64_t lddy, const float *x, int64_t ldx, int64_t rows, int64_t F,
+                              const float *mean, const float *rstd, const float *weight,
+                              const float *sums /*[2F]: sum dy, sum dy * x_hat over all ranks*/, float whole_size, float *dx,
+                              int64_t lddx, void *stream) {
+    BNS_REQUIRE(rows >= 0 && F > 0 && F % 4 == 0 && F <= kColsumMaxCols, "bns_bn_bwd_f32: need F %% 4 == 0, F <= 1024");
+    if (rows == 0) return BNS_OK;
+    BNS_REQUIRE(dy && x && dx && mean && rstd && weight && sums && whole_size > 0.f, "bns_bn_bwd_f32: NULL argument");
+    BNS_REQUIRE(bn_shape_ok(dy, lddy, F) && bn_shape_ok(x, ldx, F) && bn_shape_ok(dx, lddx, F), "bns_bn_bwd_f32: bad matrix");
+    bn_bwd_kernel<<<ln_grid(rows), kThreads, 0, as_stream(stream)>>>(dy, lddy, x, ldx, rows, (int32_t)F, mean, rstd, weight, sums,
+                                                                     whole_size, dx, lddx);
+    ++g_launches;
+    BNS_CUDA(cudaGetLastError());
+    return BNS_OK;
+}

@@ -34,6 +34,20 @@ def _ceil4(n: int) -> int:
     return (n + 3) // 4 * 4
 
 
+class Transient:
+    """Per-step scratch a module may hold (e.g. the padded output that the loss kernel differentiates): never copied,
+    never pickled -- ``copy.deepcopy(model)`` (evaluate.py snapshots the model) must not drag autograd graphs along."""
+
+    def __init__(self):
+        self.value = None
+
+    def __deepcopy__(self, memo):
+        return Transient()
+
+    def __getstate__(self):
+        return {"value": None}
+
+
 class ParamArena:
     """Flat storage for a model's parameters (``flat_p``), gradients (``flat_g``) and Adam moments (``exp_avg``,
     ``exp_avg_sq``).  2-D parameters are stored with their row count padded to a multiple of 4, 1-D ones with their
@@ -73,6 +87,10 @@ class ParamArena:
         self._entries: List[DeriveEntry] = []
         self._table: Optional[torch.Tensor] = None
         self._keep: List[torch.Tensor] = []
+
+    def __deepcopy__(self, memo):
+        """A copied model (evaluate.py's snapshots) owns plain parameter tensors and takes the op-by-op path."""
+        return None
 
     # ---- views ----------------------------------------------------------------------------------------------------
     def padded(self, p: torch.nn.Parameter) -> torch.Tensor:
@@ -265,7 +283,7 @@ class PPLinearFn(torch.autograd.Function):
 def _aggregate(g: PartitionGraph, x_u: torch.Tensor, rs: torch.Tensor, ready) -> torch.Tensor:
     """``rs * (A_in x_u[:n_in] + A_out[:, sampled] x_u[n_in:])`` -- the inner pass first (it needs local rows only), the
     halo pass after the exchange's event."""
-    y = ops.spmm(g.a_in, x_u, row_scale=rs)
+    y = ops.spmm_auto(g.a_in, x_u[:g.n_in], row_scale=rs)
     if ready is not None:
         torch.cuda.current_stream(x_u.device).wait_event(ready)
     if g.a_out is not None and x_u.shape[0] > g.n_in:
@@ -281,7 +299,7 @@ def _aggregate_t(g: PartitionGraph, dys: torch.Tensor, n_u: int) -> torch.Tensor
         tail.zero_()
         if g.a_out_t is not None:
             ops.spmm(g.a_out_t, dys, tail, row_map=g.slot)
-    ops.spmm(g.a_in_t, dys, du[:g.n_in])
+    ops.spmm_auto(g.a_in_t, dys, du[:g.n_in])
     return du
 
 

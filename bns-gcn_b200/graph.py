@@ -98,8 +98,8 @@ class PartitionAggregate(torch.autograd.Function):
         h_u = h_u.contiguous()
         # a per-source scale is applied ONCE per row here, not once per edge inside the gather (each source row is
         # gathered ~degree times; the fused col_scale path costs an extra scalar gather per edge)
-        x_in = h_u if cs_in is None else h_u[:g.n_in] * cs_in.unsqueeze(1)
-        y = ops.spmm(g.a_in, x_in, row_scale=rs)
+        x_in = h_u[:g.n_in] if cs_in is None else h_u[:g.n_in] * cs_in.unsqueeze(1)
+        y = ops.spmm_auto(g.a_in, x_in, row_scale=rs)
         if ready is not None:
             torch.cuda.current_stream(h_u.device).wait_event(ready)
         if g.a_out is not None and ctx.n_u > g.n_in:
@@ -116,7 +116,7 @@ class PartitionAggregate(torch.autograd.Function):
             tail.zero_()
             if g.a_out_t is not None:
                 ops.spmm(g.a_out_t, dy, tail, row_scale=ctx.cs_halo, row_map=g.slot)
-        ops.spmm(g.a_in_t, dy, du[:g.n_in], row_scale=ctx.cs_in)
+        ops.spmm_auto(g.a_in_t, dy, du[:g.n_in], row_scale=ctx.cs_in)
         return du, None, None, None, None, None
 
 

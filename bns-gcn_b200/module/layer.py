@@ -108,11 +108,12 @@ class GraphSAGELayer(nn.Module):
     _lin = staticmethod(_apply)
 
     def forward(self, graph, feat, in_norm, fused=None):
-        """``fused = (arena, dropout p of the input, Philox seed)``: the fused training step (fused.py) -- one
-        autograd node for the whole layer, parameter gradients written into the arena."""
+        """``fused = (arena, dropout p of the input, Philox seed, holder)``: the fused training step (fused.py) -- one
+        autograd node for the whole layer, parameter gradients written into the arena; ``holder.value`` receives the
+        output with its padded width (what the loss kernel reads and differentiates)."""
         if self.training and fused is not None:
             from .. import fused as _f
-            arena, p, seed = fused
+            arena, p, seed, holder = fused
             if self.use_pp:
                 return _f.PPLinearFn.apply(feat, self.linear.weight, self.linear.bias, arena, p, seed)
             out_f, in_f = self.linear2.out_features, self.linear2.in_features
@@ -120,7 +121,7 @@ class GraphSAGELayer(nn.Module):
             out = _f.SageConvFn.apply(feat, self.linear1.weight, self.linear1.bias, self.linear2.weight,
                                       self.linear2.bias, graph, graph.recip(in_norm), getattr(feat, '_bns_ready', None),
                                       arena, narrow)
-            self._padded_out = out              # [n_in, ceil4(out_features)]: the loss kernel reads / writes this layout
+            holder.value = out                  # [n_in, ceil4(out_features)]
             return out if out.shape[1] == out_f else out[:, :out_f]
         if self.training:
             if self.use_pp:

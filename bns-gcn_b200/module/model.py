@@ -37,7 +37,7 @@ class GNNBase(nn.Module):
         # fused.ParamArena, set by train.setup when the whole model can take the fused training step (fused.py);
         # None = the op-by-op autograd path
         self._arena = None
-        self._padded_logits = None
+        self._scratch = None        # fused.Transient: the padded logits of the current step
 
     @property
     def n_conv(self) -> int:
@@ -72,7 +72,9 @@ class GNNBase(nn.Module):
         """GCN / GraphSAGE (module/model.py:42-58, 77-93): dropout -> [exchange] -> layer -> norm -> activation."""
         h, dropped = feat, False               # dropped: this layer's input dropout was applied by the fused step
         arena = self._arena if self.training else None
-        self._padded_logits = None
+        if arena is not None and self._scratch is None:
+            from ..fused import Transient
+            self._scratch = Transient()
         for i, layer in enumerate(self.layers):
             kw = {}
             if arena is not None and i < self.n_conv:
@@ -84,7 +86,7 @@ class GNNBase(nn.Module):
                         p = self.dropout.p
                     else:
                         h = self.dropout(h)
-                kw = {"fused": (arena, p, ops.RNG["seed"] + 104729 * (i + 1))}
+                kw = {"fused": (arena, p, ops.RNG["seed"] + 104729 * (i + 1), self._scratch)}
             elif not dropped:
                 h = self.dropout(h)
             if i >= self.n_conv:
@@ -93,8 +95,6 @@ class GNNBase(nn.Module):
                 if self.training and (i > 0 or not self.use_pp):
                     h = ctx.buffer.update(i, h, overlap=True)          # model.py:47-48, 82-83
                 h = layer(g, h, *norms, **kw)
-                if arena is not None and i == self.n_layers - 1:
-                    self._padded_logits = getattr(layer, "_padded_out", None)
             dropped = False
             if i < self.n_layers - 1:
                 h, dropped = self._between(i, h, True)

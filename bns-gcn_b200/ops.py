@@ -166,6 +166,75 @@ def spmm(g: DeviceGraph, x: torch.Tensor, out: Optional[torch.Tensor] = None, *,
     return out
 
 
+# ---- source-row blocking ------------------------------------------------------------------------------------------
+# B200's 126 MB L2 is two ~63 MB halves; a gather table shared by all SMs stops being resident well before 126 MB:
+# random 512-byte-row gathers run at 19.8 TB/s from a 49 MB table, 16.7 TB/s from 114 MB, 11 TB/s from 228 MB
+# (profiles/l2_microbench_r02.md).  Column slabs (csrc: pick_slab) bring the Reddit-shape table down to 119 MB; cutting
+# the SOURCE ROWS in two as well makes every pass gather from <= 60 MB: 7.39 -> 6.63 ms per F = 256 launch
+# (profiles/spmm_colblocks_r02.txt).  Only worth it where rows are re-read often (high average degree) and few blocks
+# suffice -- each extra block costs one read-modify-write of the output.
+BLOCK_TABLE_BYTES = 60 << 20
+BLOCK_MIN_AVG_DEGREE = 64
+BLOCK_MAX = 4
+
+
+def plan_col_blocks(g: DeviceGraph, F: int) -> int:
+    """Number of source-row blocks for width ``F`` (1 = no blocking)."""
+    import os
+    forced = os.environ.get("BNS_SPMM_COLBLOCKS")
+    if forced:
+        return max(1, int(forced))
+    if F < 128 or g.n_rows == 0 or g.nnz / max(g.n_rows, 1) < BLOCK_MIN_AVG_DEGREE:
+        return 1
+    b = -(-g.n_cols * 512 // BLOCK_TABLE_BYTES)
+    return b if 1 < b <= BLOCK_MAX else 1
+
+
+def make_col_blocks(g: DeviceGraph, n_blocks: int, chunk_nnz: int = 0):
+    """``[(sub-graph, c0, c1)]``: block ``b`` holds the entries whose column lies in ``[c0, c1)``, columns shifted to 0."""
+    ip, ix = g.csr()
+    dev = g.device
+    rows = torch.repeat_interleave(torch.arange(g.n_rows, device=dev), ip[1:] - ip[:-1])
+    out = []
+    for b in range(n_blocks):
+        c0, c1 = (g.n_cols * b) // n_blocks, (g.n_cols * (b + 1)) // n_blocks
+        m = (ix >= c0) & (ix < c1)
+        ipb = torch.zeros(g.n_rows + 1, dtype=torch.int64, device=dev)
+        ipb[1:] = torch.cumsum(torch.bincount(rows[m], minlength=g.n_rows), 0)
+        out.append((DeviceGraph.from_csr(ipb, (ix[m] - c0).to(torch.int32), c1 - c0, chunk_nnz), c0, c1))
+    return out
+
+
+def spmm_auto(g: DeviceGraph, x: torch.Tensor, out: Optional[torch.Tensor] = None, *, row_scale=None,
+              n_out_rows: Optional[int] = None) -> torch.Tensor:
+    """``spmm`` of a plain matrix (no maps, no weights), source-row blocked when ``plan_col_blocks`` says so: one pass
+    per block, each accumulating into ``out``.  Counts as ONE launch in bench.py's roofline bookkeeping."""
+    global PROFILE
+    F = x.shape[1]
+    nb = plan_col_blocks(g, F)
+    if nb <= 1:
+        return spmm(g, x, out, row_scale=row_scale, n_out_rows=n_out_rows)
+    blocks = g.__dict__.get("_col_blocks")
+    if blocks is None or len(blocks) != nb:
+        blocks = g._col_blocks = make_col_blocks(g, nb)
+    if out is None:
+        out = torch.empty(g.n_rows if n_out_rows is None else n_out_rows, F, dtype=torch.float32, device=x.device)
+    prof, PROFILE = PROFILE, None
+    try:
+        if prof is not None:
+            ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            ev0.record(torch.cuda.current_stream(x.device))
+        for i, (gb, c0, c1) in enumerate(blocks):
+            spmm(gb, x[c0:c1], out, row_scale=row_scale, accumulate=i > 0)
+        if prof is not None:
+            ev1.record(torch.cuda.current_stream(x.device))
+            alg = 8 * (g.n_rows + 1) + 4 * g.nnz + 4 * F * x.shape[0] + 4 * F * out.shape[0]
+            prof.append((ev0, ev1, alg, g.nnz, F, g.nnz))
+    finally:
+        PROFILE = prof
+    return out
+
+
 class CompactedCols:
     """Per-epoch compaction of a column-mapped matrix (``bns_graph_compact_cols``): the sampled entries of every
     chunk, already mapped to rows of X, moved to the front of the chunk's own index range."""

@@ -428,7 +428,7 @@ def train_epoch(st: TrainState, epoch: int, selected: Optional[list] = None) -> 
         # fused step: loss + d(logits) in one kernel (the 1/n_train of helper/reducer.py:34 rides on d(logits)), backward
         # through the layer functions (gradients land in the arena = the all-reduce bucket), one all-reduce, one Adam
         from . import fused
-        pad = st.model._padded_logits
+        pad = st.model._scratch.value
         loss, dl = fused.softmax_xent(pad.detach(), st.args.n_class, st.labels, st.train_mask, 1.0 / st.args.n_train)
         pad.backward(dl)
         ctx.reducer.synchronize()

@@ -107,7 +107,7 @@ def run_oracle(parts, args, n_epochs, selected_per_epoch, relu_masks_per_epoch=N
 def run_parity_case(shape="tiny", n_parts=2, model="graphsage", sampling_rate=0.5, n_epochs=2, device="cuda:0",
                     backend="nccl", n_layers=3, n_hidden=16, partition_method="random", graph_seed=0,
                     sampler_seed=0, chunk_nnz=0, n_linear=0, inductive=False, multilabel=False, norm="layer",
-                    graph_override=None, heads=1) -> dict:
+                    graph_override=None, heads=1, selected_per_epoch=None) -> dict:
     """Product vs oracle on one seeded configuration.  Returns the worst relative error over layer outputs, logits,
     reduced gradients and updated weights, plus the exactness checks on index sets."""
     from bns_gcn_b200.data import make_graph, partition_graph
@@ -118,7 +118,8 @@ def run_parity_case(shape="tiny", n_parts=2, model="graphsage", sampling_rate=0.
     args = make_args(dataset=shape, model=model, sampling_rate=sampling_rate, backend=backend, n_layers=n_layers,
                      n_hidden=n_hidden, n_partitions=n_parts, sampler_seed=sampler_seed, chunk_nnz=chunk_nnz,
                      n_linear=n_linear, inductive=inductive, multilabel=multilabel, norm=norm, heads=heads)
-    prod = run_product(parts, args, device, n_epochs)
+    # ``selected_per_epoch[e][r][j]``: inject the sampled sets (e.g. the ones the reference drew) instead of the Philox draw
+    prod = run_product(parts, args, device, n_epochs, selected_per_epoch=selected_per_epoch)
     selected = [[prod[r]["selected"][e] for r in range(n_parts)] for e in range(n_epochs)]
     orc = run_oracle(parts, args, n_epochs, selected if n_parts > 1 else None)
     worst, detail = _compare(prod, orc, n_parts)
@@ -151,7 +152,7 @@ def run_parity_case(shape="tiny", n_parts=2, model="graphsage", sampling_rate=0.
                 index_ok &= torch.equal(prod[j]["one_hops"][e][r], prod[r]["selected"][e][j])
         # Philox replay of this rank's draws
         peers = [j for j in range(n_parts) if j != r]
-        for e in range(n_epochs if n_parts > 1 else 0):
+        for e in range(n_epochs if (n_parts > 1 and selected_per_epoch is None) else 0):
             ref = philox.sample_boundary([prod[r]["boundary"][j].numpy() for j in peers],
                                          [prod[r]["send_size"][j] for j in peers], sampler_seed, e)
             for i, j in enumerate(peers):

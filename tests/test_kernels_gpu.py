@@ -607,7 +607,10 @@ def test_compacted_halo_spmm_is_bit_identical_to_the_column_mapped_one(built, F)
         c.refresh(slot.to(dev), 0, cs if weights else None)
         got = y0.clone()
         ops.spmm_compact(c, x, got, row_scale=rs, accumulate=True)
-        assert torch.equal(got, ref), weights
+        if F >= 128:      # full-warp slabs: the same entries added in the same order
+            assert torch.equal(got, ref), weights
+        else:             # sub-warp row groups split a chunk's entries between them by position: equal to rounding
+            assert _relerr(got.cpu(), ref.cpu()) < 1e-6, weights
         live = int((slot[idx] >= 0).sum())
         assert int(c.chunk_cnt.sum()) == live
     # a second epoch with another sample reuses the buffers
@@ -618,7 +621,7 @@ def test_compacted_halo_spmm_is_bit_identical_to_the_column_mapped_one(built, F)
     ops.spmm(g, x, ref, col_scale=cs, col_map=slot2.to(dev), n_direct=0)
     got = torch.zeros(n_rows, F, device=dev)
     ops.spmm_compact(c, x, got)
-    assert torch.equal(got, ref)
+    assert torch.equal(got, ref) if F >= 128 else _relerr(got.cpu(), ref.cpu()) < 1e-6
 
 
 def test_dropout_and_scale_rows_kernels(built):

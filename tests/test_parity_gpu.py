@@ -120,7 +120,11 @@ def test_training_parity_through_a_relu_kink(built):
     from tests.harness import run_parity_case
     res = run_parity_case(shape="small", n_parts=8, model="graphsage", sampling_rate=0.5, n_epochs=2, n_hidden=32,
                           graph_seed=0)
-    assert res["kink"] is not None and res["kink"]["flips"] >= 1 and res["kink"]["max_abs_z"] < 1e-4, res["kink"]
+    # Which side of the kink the CUDA forward lands on depends on its rounding (the op-by-op path of round 1 took the
+    # other side; the fused layer functions happen to agree with the CPU): either no retry was needed, or the retry found
+    # exactly that kind of entry.  Both ways the comparison must end inside the bar.
+    if res["kink"] is not None:
+        assert res["kink"]["flips"] >= 1 and res["kink"]["max_abs_z"] < 1e-4, res["kink"]
     assert res["max_rel_err"] < TOL, {k: v for k, v in res["detail"].items() if v >= TOL}
     assert res["index_sets_equal"]
 
@@ -145,13 +149,23 @@ def test_cuda_path_reproduces_reference_golden_eight_partitions(built):
             if b is not None:
                 assert torch.equal(o["boundary"][j], b)
     g0, o = ranks[0], out[0]
-    for i, lo in enumerate(g0["layer_out"][-1]):
-        assert _relerr(o["layers"][f"layer{i}"], lo) < TOL, i
-    assert _relerr(o["logits"], g0["logits"][-1]) < TOL
+    errs = {f"layer{i}": _relerr(o["layers"][f"layer{i}"], lo) for i, lo in enumerate(g0["layer_out"][-1])}
+    errs["logits"] = _relerr(o["logits"], g0["logits"][-1])
     for r, o in enumerate(out):
         for k, (gp, gg) in enumerate(zip(g0["params"], g0["grads"])):
-            assert _relerr(o["params"][k], gp) < TOL, (r, g0["param_names"][k])
-            assert _relerr(o["grads"][k], gg) < TOL, (r, g0["param_names"][k])
+            errs[f"r{r}/param/{g0['param_names'][k]}"] = _relerr(o["params"][k], gp)
+            errs[f"r{r}/grad/{g0['param_names'][k]}"] = _relerr(o["grads"][k], gg)
+    bad = {k: v for k, v in errs.items() if v >= TOL}
+    if bad:
+        # A ReLU kink (see test_training_parity_through_a_relu_kink): compare instead with the oracle -- which
+        # tests/test_oracle_cpu.py pins to this very golden at 1e-7 -- on the active sets the CUDA forward took; the
+        # harness accepts that only if every switched entry sat within 1e-4 of zero in the oracle's own forward.
+        from tests.harness import run_parity_case
+        res = run_parity_case(shape=cfg["shape"], n_parts=cfg["n_parts"], model=cfg["model"], sampling_rate=cfg["rate"],
+                              n_epochs=cfg["epochs"], n_layers=cfg["n_layers"], n_hidden=cfg["n_hidden"], device="cuda:0",
+                              selected_per_epoch=sel)
+        assert res["kink"] is not None and res["kink"]["flips"] >= 1 and res["kink"]["max_abs_z"] < 1e-4, (bad, res["kink"])
+        assert res["max_rel_err"] < TOL, ({k: v for k, v in res["detail"].items() if v >= TOL}, bad)
 
 
 @pytest.mark.parametrize("model", ["graphsage", "gcn"])
@@ -225,21 +239,30 @@ def test_cuda_graph_epoch_equals_eager(built, model):
 
 @pytest.mark.parametrize("kw", [
     dict(n_parts=3, sampling_rate=0.004),                 # int(p * b) == 0 for every peer: nothing is exchanged
+    dict(n_parts=3, sampling_rate=0.004, backend="p2p"),  # ... over peer memory: zero-row puts still publish their flags
     dict(n_parts=2, sampling_rate=0.5, n_linear=1),       # --n-linear: the last layer is a plain nn.Linear
     dict(n_parts=2, sampling_rate=0.5, inductive=True),   # --inductive: partition the train-node subgraph
     dict(n_parts=2, sampling_rate=0.5, shape="tiny-ml", multilabel=True),          # BCE-with-logits (yelp-style)
     dict(n_parts=2, sampling_rate=0.5, model="gcn", n_layers=4, backend="p2p"),    # deeper GCN over the p2p transport
     dict(n_parts=3, sampling_rate=0.5, norm="batch", graph_override={"train": 1.0}),   # --norm batch (SyncBatchNorm)
-], ids=["zero-sample", "n-linear", "inductive", "multilabel", "gcn4-p2p", "sync-bn"])
+], ids=["zero-sample", "zero-sample-p2p", "n-linear", "inductive", "multilabel", "gcn4-p2p", "sync-bn"])
 def test_training_parity_variants(built, kw):
     kw = dict(kw)
     kw.setdefault("shape", "tiny")
-    if kw.get("norm") == "batch":      # one epoch: afterwards the noise-driven pre-BN biases diverge (see test_oracle_cpu)
+    if kw.get("norm") == "batch":
+        # Three epochs, everything compared -- layer outputs, logits, gradients, weights -- except the gradients and
+        # values of the biases that sit directly in front of a batch norm (parameters 1, 3, 5: layers.0.linear.bias,
+        # layers.1.linear1.bias, layers.1.linear2.bias).  Their true gradient is exactly zero (the mean subtraction
+        # removes any constant shift), what is computed is rounding noise, Adam turns noise into +-lr steps, and the
+        # next normalisation removes the shift again: they differ between any two implementations and influence nothing.
         from tests.harness import run_parity_case
-        res = run_parity_case(device="cuda:0", n_epochs=1, **kw)
-        bad = {k: v for k, v in res["detail"].items() if v >= TOL and not ("grad" in k or "param" in k)}
+        res = run_parity_case(device="cuda:0", n_epochs=3, **kw)
+        skip = tuple(f"/{k}{i}" for k in ("grad", "param") for i in (1, 3, 5))
+        bad = {k: v for k, v in res["detail"].items() if v >= TOL and not k.endswith(skip)}
         assert not bad, bad
         assert res["index_sets_equal"]
+        for a, b in zip(res["loss"], res["loss_oracle"]):
+            assert abs(a - b) <= 1e-4 * abs(b)
         return
     _run(n_epochs=2, **kw)
 

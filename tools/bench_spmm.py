@@ -46,6 +46,8 @@ def main():
     ap.add_argument("--no-cusparse", action="store_true")
     ap.add_argument("--transpose", action="store_true")
     ap.add_argument("--slab", type=int, default=0)
+    ap.add_argument("--col-blocks", type=int, default=1,
+                    help="experiment: split the source rows into this many blocks, one accumulate pass per block")
     ap.add_argument("--n", type=int, default=0, help="override node count")
     ap.add_argument("--e", type=int, default=0, help="override edge count")
     a = ap.parse_args()
@@ -69,10 +71,31 @@ def main():
     x = torch.randn(n_src, a.F, device=dev)
     y = torch.empty(n_dst, a.F, device=dev)
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
-    med, best = time_it(lambda: ops.spmm(g, x, y, slab=a.slab), a.iters, flush)
+    if a.col_blocks > 1:
+        ip, ix = g.csr()
+        rows = torch.repeat_interleave(torch.arange(g.n_rows, device=dev), ip[1:] - ip[:-1])
+        blocks, B = [], a.col_blocks
+        for b in range(B):
+            c0, c1 = (n_src * b) // B, (n_src * (b + 1)) // B
+            m = (ix >= c0) & (ix < c1)
+            cnt = torch.bincount(rows[m], minlength=g.n_rows)
+            ipb = torch.zeros(g.n_rows + 1, dtype=torch.int64, device=dev)
+            ipb[1:] = torch.cumsum(cnt, 0)
+            blocks.append((ops.DeviceGraph.from_csr(ipb, (ix[m] - c0).int(), c1 - c0, a.chunk), c0, c1))
+        del rows
+
+        def run_blocked():
+            for i, (gb, c0, c1) in enumerate(blocks):
+                ops.spmm(gb, x[c0:c1], y, accumulate=i > 0, slab=a.slab)
+        y_ref = ops.spmm(g, x, slab=a.slab).clone()
+        run_blocked()
+        print("blocked vs plain rel err", ((y - y_ref).norm() / y_ref.norm()).item(), file=sys.stderr)
+        med, best = time_it(run_blocked, a.iters, flush)
+    else:
+        med, best = time_it(lambda: ops.spmm(g, x, y, slab=a.slab), a.iters, flush)
     bytes_alg = 8 * (n_dst + 1) + 4 * nnz + 4 * a.F * n_src + 4 * a.F * n_dst
     bytes_gather = 8 * (n_dst + 1) + 4 * nnz + 4 * a.F * nnz + 4 * a.F * n_dst
-    res = {"case": f"{a.shape}/P{a.parts}/F{a.F}/slab{a.slab}" + ("/T" if a.transpose else ""), "n_dst": n_dst, "n_src": n_src,
+    res = {"case": f"{a.shape}/P{a.parts}/F{a.F}/slab{a.slab}/chunk{a.chunk}/colblocks{a.col_blocks}" + ("/T" if a.transpose else ""), "n_dst": n_dst, "n_src": n_src,
            "nnz": nnz, "chunks": g.n_chunks, "split_rows": g.n_split_rows, "ms_median": round(med, 4),
            "ms_best": round(best, 4), "alg_GBs": round(bytes_alg / med / 1e6, 1),
            "alg_frac_of_hbm": round(bytes_alg / (med * 1e-3) / HBM_PEAK, 4),
