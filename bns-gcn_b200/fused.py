@@ -234,9 +234,18 @@ def dropout(x: torch.Tensor, p: float, seed: int) -> torch.Tensor:
     return y
 
 
-def scale_rows(x: torch.Tensor, rs: torch.Tensor) -> torch.Tensor:
-    x = x.contiguous()
-    y = torch.empty_like(x)
+def gather_friendly(rows: int, width: int, device) -> torch.Tensor:
+    """An uninitialised ``[rows, width]`` f32 matrix whose row stride is a multiple of 64 bytes: a narrow row that the
+    SpMM gathers (44 padded class scores = 176 bytes) then always spans the minimum number of 128-byte lines (2), where
+    a 176-byte stride makes 3 of every 8 rows straddle a third line."""
+    ld = (width + 15) // 16 * 16
+    return torch.empty(rows, ld, dtype=torch.float32, device=device)[:, :width]
+
+
+def scale_rows(x: torch.Tensor, rs: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    if x.stride(1) != 1:
+        x = x.contiguous()
+    y = torch.empty_like(x) if out is None else out
     with torch.cuda.device(x.device):
         check(lib.bns_scale_rows_f32(x.data_ptr(), x.stride(0), x.shape[0], x.shape[1], rs.data_ptr(), y.data_ptr(),
                                      y.stride(0), torch.cuda.current_stream(x.device).cuda_stream), "bns_scale_rows_f32")
@@ -322,7 +331,7 @@ class SageConvFn(torch.autograd.Function):
         if narrow_first:
             if ready is not None:               # the transform reads every row of h_u, halo rows included
                 torch.cuda.current_stream(h_u.device).wait_event(ready)
-            t = dense.tc_mm_tn(h_u, W2)                                         # [n_u, out_p]
+            t = dense.tc_mm_tn(h_u, W2, out=gather_friendly(h_u.shape[0], W2.shape[0], h_u.device))   # [n_u, out_p]
             ah = _aggregate(g, t, rs, None)                                     # [n_in, out_p]
             out = dense.tc_mm_tn(h_in, W1, arena.bias_sum(b1, b2), addend=ah)   # linear1(h) + b1 + b2 + ah
             ctx.save_for_backward(h_u)
@@ -346,7 +355,8 @@ class SageConvFn(torch.autograd.Function):
             (h_u,) = ctx.saved_tensors
             n_u = h_u.shape[0]
             dense.tc_mm_nt(dout, h_u[:n_in], out=a.grad_padded(w1))
-            dt = _aggregate_t(g, scale_rows(dout, rs), n_u)                     # [n_u, out_p]
+            dys = scale_rows(dout, rs, out=gather_friendly(n_in, dout.shape[1], dout.device))
+            dt = _aggregate_t(g, dys, n_u)                                      # [n_u, out_p]
             dense.tc_mm_nt(dt, h_u, out=a.grad_padded(w2))
             du = dense.tc_mm_tn(dt, a.transposed(w2))                           # [n_u, in]
         else:

@@ -218,8 +218,10 @@ class Buffer(object):
         if not self.graph_mode:
             sel_cat.record_stream(cs)
         main.wait_event(done)
+        # a private copy: the slab region is rewritten by the peers at the start of THEIR next epoch, and the lists stay
+        # visible to the caller (train.TrainState.one_hops) after this epoch has ended
         cat = torch.as_tensor(_DevArray(self._slab_ptr + self._ids_off, (max(self._recv_total, 1),), "<i8"),
-                              device=self._device)[:self._recv_total]
+                              device=self._device)[:self._recv_total].clone()
         views = [None] * self._size
         for j in self._peers:
             views[j] = cat[self._hop_begin[j]:self._hop_begin[j] + self._recv_shape[j]]

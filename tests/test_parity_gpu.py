@@ -252,14 +252,15 @@ def test_training_parity_variants(built, kw):
     if kw.get("norm") == "batch":
         # Three epochs, everything compared -- layer outputs, logits, gradients, weights -- except the gradients and
         # values of the biases that sit directly in front of a batch norm (parameters 1, 3, 5: layers.0.linear.bias,
-        # layers.1.linear1.bias, layers.1.linear2.bias).  Their true gradient is exactly zero (the mean subtraction
+        # layers.1.linear1.bias, layers.1.linear2.bias) -- logits, every other gradient and weight included.  Their true gradient is exactly zero (the mean subtraction
         # removes any constant shift), what is computed is rounding noise, Adam turns noise into +-lr steps, and the
         # next normalisation removes the shift again: they differ between any two implementations and influence nothing.
         from tests.harness import run_parity_case
         res = run_parity_case(device="cuda:0", n_epochs=3, **kw)
-        skip = tuple(f"/{k}{i}" for k in ("grad", "param") for i in (1, 3, 5))
+        # ... except through what is recorded BEFORE the normalisation: the raw outputs of layers 0 and 1 carry the bias.
+        skip = tuple(f"/{k}{i}" for k in ("grad", "param") for i in (1, 3, 5)) + ("/layer0", "/layer1")
         bad = {k: v for k, v in res["detail"].items() if v >= TOL and not k.endswith(skip)}
-        assert not bad, bad
+        assert not bad, sorted(bad.items())
         assert res["index_sets_equal"]
         for a, b in zip(res["loss"], res["loss_oracle"]):
             assert abs(a - b) <= 1e-4 * abs(b)
