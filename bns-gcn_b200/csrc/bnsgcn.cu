@@ -1265,14 +1265,17 @@ __global__ void __launch_bounds__(kThreads) ln_relu_dropout_kernel(LnArgs a) {
     }
 }
 
-__global__ void ln_colsum_kernel(const float *__restrict__ partial, int n_part, int F, float *__restrict__ dgamma,
-                                 float *__restrict__ dbeta) {
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+// one warp per output column (2F of them: dgamma then dbeta): lanes stride over the per-CTA partials, fixed shuffle tree
+__global__ void __launch_bounds__(kThreads) ln_colsum_kernel(const float *__restrict__ partial, int n_part, int F,
+                                                             float *__restrict__ dgamma, float *__restrict__ dbeta) {
+    const int lane = threadIdx.x & 31;
+    const int i = blockIdx.x * kWarps + (threadIdx.x >> 5);
     if (i >= 2 * F) return;
     const int which = i / F, f = i % F;
     float acc = 0.f;
-    for (int p = 0; p < n_part; ++p) acc += partial[((int64_t)p * 2 + which) * F + f];
-    (which == 0 ? dgamma : dbeta)[f] = acc;
+    for (int p = lane; p < n_part; p += 32) acc += partial[((int64_t)p * 2 + which) * F + f];
+    acc = warp_sum(acc);
+    if (lane == 0) (which == 0 ? dgamma : dbeta)[f] = acc;
 }
 
 inline unsigned ln_grid(int64_t n) {
@@ -1334,7 +1337,7 @@ extern "C" int bns_ln_relu_dropout_bwd_f32(const float *dy, int64_t lddy, const 
     a.seed = seed; a.offset = offset; a.offset_dev = offset_dev; a.partial = reinterpret_cast<float *>(ws);
     cudaStream_t st = as_stream(stream);
     launch_ln<true>(a, grid, st);
-    ln_colsum_kernel<<<(unsigned)((2 * F + 255) / 256), 256, 0, st>>>(a.partial, (int)grid, (int)F, dgamma, dbeta);
+    ln_colsum_kernel<<<(unsigned)((2 * F + kWarps - 1) / kWarps), kThreads, 0, st>>>(a.partial, (int)grid, (int)F, dgamma, dbeta);
     g_launches += 2;
     BNS_CUDA(cudaGetLastError());
     return BNS_OK;
@@ -1374,17 +1377,22 @@ __global__ void __launch_bounds__(kThreads) colsum_partial_kernel(const float *_
     }
 }
 
-__global__ void colsum_final_kernel(const float4 *__restrict__ partial, int n_part, int CV, float4 *__restrict__ out,
-                                    float4 *__restrict__ out2) {
-    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+// one warp per float4 column: lanes stride over the per-block partials, then a fixed shuffle tree (deterministic)
+__global__ void __launch_bounds__(kThreads) colsum_final_kernel(const float4 *__restrict__ partial, int n_part, int CV,
+                                                                float4 *__restrict__ out, float4 *__restrict__ out2) {
+    const int lane = threadIdx.x & 31;
+    const int c = blockIdx.x * kWarps + (threadIdx.x >> 5);
     if (c >= CV) return;
-    float4 acc = partial[c];
-    for (int p = 1; p < n_part; ++p) {
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int p = lane; p < n_part; p += 32) {
         const float4 v = partial[(int64_t)p * CV + c];
         acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
     }
-    out[c] = acc;
-    if (out2) out2[c] = acc;
+    acc.x = warp_sum(acc.x); acc.y = warp_sum(acc.y); acc.z = warp_sum(acc.z); acc.w = warp_sum(acc.w);
+    if (lane == 0) {
+        out[c] = acc;
+        if (out2) out2[c] = acc;
+    }
 }
 
 inline int colsum_blocks() { return sm_count() * 4; }
@@ -1410,8 +1418,9 @@ extern "C" int bns_colsum_f32(const float *X, int64_t ld, int64_t rows, int64_t 
     if ((int64_t)blocks > rows) blocks = (int)rows;
     cudaStream_t st = as_stream(stream);
     colsum_partial_kernel<<<blocks, kThreads, 0, st>>>(X, ld, rows, CV, reinterpret_cast<float4 *>(ws));
-    colsum_final_kernel<<<(CV + 127) / 128, 128, 0, st>>>(reinterpret_cast<const float4 *>(ws), blocks, CV,
-                                                          reinterpret_cast<float4 *>(out), reinterpret_cast<float4 *>(out2));
+    colsum_final_kernel<<<(CV + kWarps - 1) / kWarps, kThreads, 0, st>>>(reinterpret_cast<const float4 *>(ws), blocks, CV,
+                                                                         reinterpret_cast<float4 *>(out),
+                                                                         reinterpret_cast<float4 *>(out2));
     g_launches += 2;
     BNS_CUDA(cudaGetLastError());
     return BNS_OK;

@@ -662,20 +662,29 @@ __global__ void __launch_bounds__(kThreads) compact_cols_kernel(const int64_t *_
         int64_t e = indptr[row + 1];
         if (e > s + chunk_nnz) e = s + chunk_nnz;
         int32_t off = 0;
-        for (int64_t k0 = s; k0 < e; k0 += 32) {
-            const int64_t k = k0 + lane;
-            int32_t col = -1, orig = 0;
-            if (k < e) {
-                orig = ld_stream_i32(indices + k);
-                col = orig >= n_direct ? __ldg(col_map + (orig - n_direct)) : orig;
+        constexpr int U = 4;              // 4 x 32 ids and their 4 x 32 slot look-ups in flight per warp
+        for (int64_t k0 = s; k0 < e; k0 += 32 * U) {
+            int32_t orig[U], col[U];
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                const int64_t k = k0 + 32 * u + lane;
+                orig[u] = k < e ? ld_stream_i32(indices + k) : -1;
             }
-            const unsigned m = __ballot_sync(0xffffffffu, col >= 0);
-            if (col >= 0) {
-                const int pos = off + __popc(m & ((1u << lane) - 1u));
-                cidx[s + pos] = col;
-                if (cw) cw[s + pos] = __ldg(col_scale + orig);
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                col[u] = -1;
+                if (orig[u] >= 0) col[u] = orig[u] >= n_direct ? __ldg(col_map + (orig[u] - n_direct)) : orig[u];
             }
-            off += __popc(m);
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                const unsigned m = __ballot_sync(0xffffffffu, col[u] >= 0);
+                if (col[u] >= 0) {
+                    const int pos = off + __popc(m & ((1u << lane) - 1u));
+                    cidx[s + pos] = col[u];
+                    if (cw) cw[s + pos] = __ldg(col_scale + orig[u]);
+                }
+                off += __popc(m);
+            }
         }
         if (lane == 0) chunk_cnt[c] = off;
     }
@@ -852,8 +861,8 @@ extern "C" int bns_bn_colsums_f32(int mode, const float *A, int64_t lda, const f
     else
         colsum2_partial_kernel<1><<<blocks, kThreads, 0, st>>>(A, lda, X, ldx, rows, CV, reinterpret_cast<const float4 *>(mean),
                                                               reinterpret_cast<const float4 *>(rstd), reinterpret_cast<float4 *>(ws));
-    colsum_final_kernel<<<(2 * CV + 127) / 128, 128, 0, st>>>(reinterpret_cast<const float4 *>(ws), blocks, 2 * CV,
-                                                              reinterpret_cast<float4 *>(out), nullptr);
+    colsum_final_kernel<<<(2 * CV + kWarps - 1) / kWarps, kThreads, 0, st>>>(reinterpret_cast<const float4 *>(ws), blocks, 2 * CV,
+                                                                             reinterpret_cast<float4 *>(out), nullptr);
     g_launches += 2;
     BNS_CUDA(cudaGetLastError());
     return BNS_OK;

@@ -282,6 +282,16 @@ class Buffer(object):
     def _slab_view(self, byte_off, rows):
         return torch.as_tensor(_DevArray(self._slab_ptr + byte_off, (rows, self._width)), device=self._device)
 
+    def input_slot(self, layer, rows, width):
+        """The rows ``[0, n_in)`` of layer ``layer``'s concat buffer when they can be written in place (peer-mapped
+        transport, full slab width), else None.  ``update(layer, feat)`` recognises a ``feat`` that already lives there
+        and skips its copy (K4)."""
+        if self._size == 1 or self._p2p is None or rows != self._num_in or width != getattr(self, "_width", -1):
+            return None
+        if not (1 <= layer <= self._n_comm_layers):
+            return None
+        return self._slab_view(self._fwd_off[layer - 1], self._num_in)
+
     def set_selected(self, selected, selected_cat=None):
         """``selected_cat``: the same lists concatenated in ascending peer order (what the sampler produced); built here
         when the caller injects per-peer lists."""
@@ -314,7 +324,8 @@ class Buffer(object):
             h_u = self._slab_view(self._fwd_off[layer - 1], self._n_u)[:, :F] if F == self._width else None
             if h_u is None:
                 raise RuntimeError("p2p transport needs equal hidden widths")
-        ops.copy_rows(feat, h_u, self._num_in)                         # K4: the only copy of the concat
+        if feat.data_ptr() != h_u.data_ptr():                          # (written in place by the producer: input_slot)
+            ops.copy_rows(feat, h_u, self._num_in)                     # K4: the only copy of the concat
         start = torch.cuda.Event()
         start.record(main)
         cs.wait_event(start)

@@ -60,10 +60,14 @@ class GNNBase(nn.Module):
         if (may_fuse and FUSE_NORM_ACT_DROPOUT and isinstance(nm, nn.LayerNorm) and self.activation is F.relu
                 and nm.elementwise_affine and ops.ln_relu_dropout_supported(h, h.shape[1])):
             p = self.dropout.p if self.training else 0.0
-            slots = None
+            slots = out = None
             if self._arena is not None and self.training:
                 slots = (self._arena.grad_padded(nm.weight), self._arena.grad_padded(nm.bias))
-            return ops.LnReluDropout.apply(h, nm.weight, nm.bias, nm.eps, p, ops.RNG["seed"] + 7919 * (i + 1), slots), True
+            if self.training and i + 1 < self.n_conv:
+                # write straight into the head rows of the next layer's concat buffer (peer-mapped transport only)
+                out = ctx.buffer.input_slot(i + 1, h.shape[0], h.shape[1])
+            return ops.LnReluDropout.apply(h, nm.weight, nm.bias, nm.eps, p, ops.RNG["seed"] + 7919 * (i + 1), slots,
+                                           out), True
         if nm is not None:
             h = nm(h)
         return self.activation(h), False

@@ -442,13 +442,14 @@ class LnReluDropout(torch.autograd.Function):
     """``dropout_p(relu(layer_norm(x)))`` in one pass each way (``bns_ln_relu_dropout_{fwd,bwd}_f32``)."""
 
     @staticmethod
-    def forward(ctx, x, gamma, beta, eps: float, p: float, seed: int, grad_slots=None):
+    def forward(ctx, x, gamma, beta, eps: float, p: float, seed: int, grad_slots=None, out=None):
         """``grad_slots = (dgamma, dbeta)``: destinations of the parameter gradients (slots of fused.ParamArena); the
-        backward then writes them there and returns None for gamma / beta."""
+        backward then writes them there and returns None for gamma / beta.  ``out``: where to write the result (the head
+        rows of the next layer's concat buffer, ``Buffer.input_slot``: saves the copy of helper/feature_buffer.py:85-91)."""
         ctx.grad_slots = grad_slots
         x = x.contiguous()
         n, F = x.shape
-        y = torch.empty_like(x)
+        y = torch.empty_like(x) if out is None else out
         mean = torch.empty(n, dtype=torch.float32, device=x.device)
         rstd = torch.empty(n, dtype=torch.float32, device=x.device)
         off, off_dev = RNG["offset"], RNG["offset_dev"]
@@ -485,8 +486,8 @@ class LnReluDropout(torch.autograd.Function):
                                                   dx.data_ptr(), dx.stride(0), dgamma.data_ptr(), dbeta.data_ptr(),
                                                   ws.data_ptr(), ws.numel(), _stream_ptr()), "bns_ln_relu_dropout_bwd_f32")
         if ctx.grad_slots is not None:
-            return dx, None, None, None, None, None, None
-        return dx, dgamma, dbeta, None, None, None, None
+            return dx, None, None, None, None, None, None, None
+        return dx, dgamma, dbeta, None, None, None, None, None
 
 
 def ln_relu_dropout_supported(x: torch.Tensor, F: int) -> bool:

@@ -497,9 +497,8 @@ class GraphedEpoch:
         buf.seq_dev = st.epoch_dev
         # flag values of the replays: seq_base + epoch counter, strictly above every value the eager epochs (and any
         # forward-only probe) have already published
-        buf.seq_base = max(buf._seq.values(), default=0) - int(st.epoch_dev.item())
-        assert buf.seq_base >= 0 or _rank_size()[1] == 1, buf.seq_base
-        buf.seq_base = max(buf.seq_base, 0)
+        # (the staged transport publishes no flags: its dict of sequence numbers is empty)
+        buf.seq_base = max(max(buf._seq.values(), default=0) - int(st.epoch_dev.item()), 0)
         self.graph = torch.cuda.CUDAGraph()
         try:
             # thread_local: other threads of the process (NCCL watchdog, copy threads) may keep calling CUDA meanwhile

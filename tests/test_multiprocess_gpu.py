@@ -26,6 +26,10 @@ def _launch(world: int, extra, port: int, timeout: int = 600):
     env = dict(os.environ)
     env.pop("CUDA_VISIBLE_DEVICES", None)
     p = subprocess.run(cmd, cwd=ROOT, env=env, capture_output=True, text=True, timeout=timeout)
+    os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
+    tag = f"w{world}_{'graph' if '--graph' in extra else 'eager'}"
+    with open(os.path.join(ROOT, "gpurun_out", f"dist_check_{tag}.log"), "w") as f:      # kept: evidence + post-mortem
+        f.write(p.stdout[-20000:] + "\n---- stderr ----\n" + p.stderr[-20000:])
     line = None
     for ln in p.stdout.splitlines():
         if ln.startswith("{") and '"world"' in ln:
