@@ -108,7 +108,7 @@ class DeviceGraph:
             return None
         ws = self._ws.get(F)
         if ws is None or ws.numel() < need:
-            ws = torch.empty(need, dtype=torch.uint8, device=self.device)
+            ws = torch.zeros(need, dtype=torch.uint8, device=self.device)      # zeroed once: the arrival counters
             self._ws[F] = ws
         return ws
 
