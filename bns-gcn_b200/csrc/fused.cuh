@@ -270,14 +270,19 @@ __global__ void __launch_bounds__(kThreads) dropout_kernel(const float *__restri
 }
 
 __global__ void __launch_bounds__(kThreads) scale_rows_kernel(const float *__restrict__ x, int64_t ldx, int64_t n, int32_t F,
-                                                              const float *__restrict__ rs, float *__restrict__ y, int64_t ldy) {
+                                                              const float *__restrict__ rs, const float *__restrict__ bias,
+                                                              float *__restrict__ y, int64_t ldy) {
     const int lane = threadIdx.x & 31;
     const int64_t warps_total = (int64_t)gridDim.x * kWarps;
     for (int64_t row = (int64_t)blockIdx.x * kWarps + (threadIdx.x >> 5); row < n; row += warps_total) {
-        const float s = rs[row];
+        const float s = rs ? rs[row] : 1.f;
         for (int f = lane * 4; f < F; f += 128) {
             float4 v = *reinterpret_cast<const float4 *>(x + row * ldx + f);
             v.x *= s; v.y *= s; v.z *= s; v.w *= s;
+            if (bias) {
+                const float4 b = __ldg(reinterpret_cast<const float4 *>(bias + f));
+                v.x += b.x; v.y += b.y; v.z += b.z; v.w += b.w;
+            }
             *reinterpret_cast<float4 *>(y + row * ldy + f) = v;
         }
     }
@@ -299,13 +304,14 @@ extern "C" int bns_dropout_f32(const float *x, int64_t ldx, int64_t n, int64_t F
     return BNS_OK;
 }
 
-extern "C" int bns_scale_rows_f32(const float *x, int64_t ldx, int64_t n, int64_t F, const float *row_scale, float *y,
-                                  int64_t ldy, void *stream) {
+extern "C" int bns_scale_rows_f32(const float *x, int64_t ldx, int64_t n, int64_t F, const float *row_scale, const float *bias,
+                                  float *y, int64_t ldy, void *stream) {
     BNS_REQUIRE(n >= 0 && F > 0 && F % 4 == 0, "bns_scale_rows_f32: need F %% 4 == 0");
     if (n == 0) return BNS_OK;
-    BNS_REQUIRE(x && y && row_scale && ldx >= F && ldy >= F && ldx % 4 == 0 && ldy % 4 == 0, "bns_scale_rows_f32: bad argument");
-    BNS_REQUIRE(((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(y)) & 15u) == 0, "bns_scale_rows_f32: unaligned");
-    scale_rows_kernel<<<ln_grid(n), kThreads, 0, as_stream(stream)>>>(x, ldx, n, (int32_t)F, row_scale, y, ldy);
+    BNS_REQUIRE(x && y && ldx >= F && ldy >= F && ldx % 4 == 0 && ldy % 4 == 0, "bns_scale_rows_f32: bad argument");
+    BNS_REQUIRE(((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(y) | reinterpret_cast<uintptr_t>(bias)) & 15u) == 0,
+                "bns_scale_rows_f32: unaligned");
+    scale_rows_kernel<<<ln_grid(n), kThreads, 0, as_stream(stream)>>>(x, ldx, n, (int32_t)F, row_scale, bias, y, ldy);
     ++g_launches;
     BNS_CUDA(cudaGetLastError());
     return BNS_OK;

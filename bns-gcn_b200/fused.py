@@ -242,13 +242,16 @@ def gather_friendly(rows: int, width: int, device) -> torch.Tensor:
     return torch.empty(rows, ld, dtype=torch.float32, device=device)[:, :width]
 
 
-def scale_rows(x: torch.Tensor, rs: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+def scale_rows(x: torch.Tensor, rs: Optional[torch.Tensor], out: Optional[torch.Tensor] = None,
+               bias: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """``x * rs[:, None] + bias`` (``bns_scale_rows_f32``)."""
     if x.stride(1) != 1:
         x = x.contiguous()
-    y = torch.empty_like(x) if out is None else out
+    y = torch.empty(x.shape, dtype=torch.float32, device=x.device) if out is None else out
     with torch.cuda.device(x.device):
-        check(lib.bns_scale_rows_f32(x.data_ptr(), x.stride(0), x.shape[0], x.shape[1], rs.data_ptr(), y.data_ptr(),
-                                     y.stride(0), torch.cuda.current_stream(x.device).cuda_stream), "bns_scale_rows_f32")
+        check(lib.bns_scale_rows_f32(x.data_ptr(), x.stride(0), x.shape[0], x.shape[1], ops._ptr(rs), ops._ptr(bias),
+                                     y.data_ptr(), y.stride(0), torch.cuda.current_stream(x.device).cuda_stream),
+              "bns_scale_rows_f32")
     return y
 
 
@@ -300,15 +303,16 @@ def _aggregate(g: PartitionGraph, x_u: torch.Tensor, rs: torch.Tensor, ready) ->
     return y
 
 
-def _aggregate_t(g: PartitionGraph, dys: torch.Tensor, n_u: int) -> torch.Tensor:
-    """``A^T dys`` over the epoch's graph: ``[n_u, F]`` (inner rows, then the sampled halo rows)."""
+def _aggregate_t(g: PartitionGraph, dys: torch.Tensor, n_u: int, cs_in=None, cs_halo=None) -> torch.Tensor:
+    """``cs * (A^T dys)`` over the epoch's graph: ``[n_u, F]`` (inner rows, then the sampled halo rows); ``cs``: GCN's
+    per-source scale (1/sqrt(out_deg)), applied as the row scale of the transposed products."""
     du = torch.empty(n_u, dys.shape[1], dtype=torch.float32, device=dys.device)
     if n_u > g.n_in:
         tail = du[g.n_in:]
         tail.zero_()
         if g.a_out_t is not None:
-            ops.spmm(g.a_out_t, dys, tail, row_map=g.slot)
-    ops.spmm_auto(g.a_in_t, dys, du[:g.n_in])
+            ops.spmm(g.a_out_t, dys, tail, row_scale=cs_halo, row_map=g.slot)
+    ops.spmm_auto(g.a_in_t, dys, du[:g.n_in], row_scale=cs_in)
     return du
 
 
@@ -369,6 +373,65 @@ class SageConvFn(torch.autograd.Function):
         inner = du[:n_in]
         dense.tc_mm_tn(dout, a.transposed(w1), addend=inner, out=inner)         # += dout W1, in place
         return du, None, None, None, None, None, None, None, None, None
+
+
+class GcnConvFn(torch.autograd.Function):
+    """GCNLayer.forward, training branch (module/layer.py:32-38):
+
+        out = linear( (A (h_u / out_norm_u)) / in_norm )
+
+    with the same aggregate-after-transform rewrite as ``SageConvFn`` where the layer narrows.  ``rs = 1/in_norm``
+    (``[n_in]``), ``cs_u = 1/out_norm`` over the STATIC ``[inner | halo]`` numbering; the halo part rides in the epoch's
+    compaction as per-entry weights (``PartitionGraph.halo_col_scale``)."""
+
+    @staticmethod
+    def forward(ctx, h_u, w, b, g: PartitionGraph, rs, cs_u, ready, arena: ParamArena, narrow_first: bool):
+        n_in = g.n_in
+        h_u = h_u.contiguous()
+        W, bp = arena.padded(w), arena.padded(b)
+        cs_in, cs_halo = cs_u[:n_in], cs_u[n_in:]
+        has_halo = g.a_out is not None and h_u.shape[0] > n_in
+        if narrow_first:
+            if ready is not None:
+                torch.cuda.current_stream(h_u.device).wait_event(ready)
+            t = dense.tc_mm_tn(h_u, W, out=gather_friendly(h_u.shape[0], W.shape[0], h_u.device))     # [n_u, out_p]
+            ts = scale_rows(t[:n_in], cs_in, out=gather_friendly(n_in, W.shape[0], h_u.device))
+            s = ops.spmm_auto(g.a_in, ts)                                                             # raw sums
+            if has_halo:
+                halo_aggregate(g, t[n_in:], s, None, cs_halo)
+            out = scale_rows(s, rs, bias=bp)                                                          # / in_norm + b
+            ctx.save_for_backward(h_u)
+        else:
+            y = ops.spmm_auto(g.a_in, scale_rows(h_u[:n_in], cs_in), row_scale=rs)
+            if ready is not None:
+                torch.cuda.current_stream(h_u.device).wait_event(ready)
+            if has_halo:
+                halo_aggregate(g, h_u[n_in:], y, rs, cs_halo)
+            out = dense.tc_mm_tn(y, W, bp)
+            ctx.save_for_backward(y)
+        ctx.n_u = h_u.shape[0]
+        ctx.g, ctx.rs, ctx.cs, ctx.arena, ctx.narrow, ctx.params = g, rs, (cs_in, cs_halo), arena, narrow_first, (w, b)
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        g, rs, a = ctx.g, ctx.rs, ctx.arena
+        cs_in, cs_halo = ctx.cs
+        w, b = ctx.params
+        dout = dout.contiguous()
+        dense.colsum(dout, out=a.grad_padded(b))
+        if ctx.narrow:
+            (h_u,) = ctx.saved_tensors
+            dys = scale_rows(dout, rs, out=gather_friendly(g.n_in, dout.shape[1], dout.device))
+            dt = _aggregate_t(g, dys, ctx.n_u, cs_in, cs_halo)                  # [n_u, out_p]
+            dense.tc_mm_nt(dt, h_u, out=a.grad_padded(w))
+            du = dense.tc_mm_tn(dt, a.transposed(w))                            # [n_u, in]
+        else:
+            (y,) = ctx.saved_tensors
+            dense.tc_mm_nt(dout, y, out=a.grad_padded(w))
+            dys = dense.tc_mm_tn(dout, a.transposed(w), row_scale=rs)           # (dout W) / in_norm
+            du = _aggregate_t(g, dys, ctx.n_u, cs_in, cs_halo)
+        return du, None, None, None, None, None, None, None, None
 
 
 def sage_layer_eligible(layer, feat: torch.Tensor) -> bool:

@@ -71,9 +71,21 @@ class GCNLayer(nn.Module):
 
     _lin = staticmethod(_apply)
 
-    def forward(self, graph, feat, in_norm, out_norm):
+    def forward(self, graph, feat, in_norm, out_norm, fused=None):
         """``out_norm``: sqrt(out_deg) of every *local* node (inner then halo, static) -- the reference rebuilds a
-        U-ordered copy of it every epoch (train.py:245-253), which the slot map makes unnecessary."""
+        U-ordered copy of it every epoch (train.py:245-253), which the slot map makes unnecessary.
+        ``fused``: see ``GraphSAGELayer.forward``."""
+        if self.training and fused is not None:
+            from .. import fused as _f
+            arena, p, seed, holder = fused
+            if self.use_pp:
+                return _f.PPLinearFn.apply(feat, self.linear.weight, self.linear.bias, arena, p, seed)
+            out_f, in_f = self.linear.out_features, self.linear.in_features
+            narrow = AGGREGATE_AFTER_TRANSFORM and out_f < in_f
+            out = _f.GcnConvFn.apply(feat, self.linear.weight, self.linear.bias, graph, graph.recip(in_norm),
+                                     graph.recip(out_norm), getattr(feat, '_bns_ready', None), arena, narrow)
+            holder.value = out
+            return out if out.shape[1] == out_f else out[:, :out_f]
         if self.training:
             if self.use_pp:
                 return self._lin(self.linear, feat)                                 # layer.py:29-30

@@ -289,16 +289,17 @@ class TrainState:
 
 
 def _fused_eligible(args, layer_size, dev) -> bool:
-    """The fused training step (fused.py) covers the BASELINE configuration family: GraphSAGE, --use-pp, LayerNorm +
+    """The fused training step (fused.py) covers the BASELINE configuration families: GraphSAGE / GCN, --use-pp, LayerNorm +
     ReLU between the layers, no trailing linear layers, widths the 16-byte vector / TMA paths take.  BNS_FUSED=0 turns
     it off (the op-by-op autograd path, kept for every other configuration, then runs here too)."""
     import os
     from .module import dense
     if os.environ.get("BNS_FUSED", "1") == "0" or dense.MODE != "tc" or dev.type != "cuda":
         return False
-    if args.model != 'graphsage' or not args.use_pp or args.n_linear != 0 or args.norm != 'layer':
+    if args.model not in ('graphsage', 'gcn') or not args.use_pp or args.n_linear != 0 or args.norm != 'layer':
         return False
-    widths_ok = (2 * layer_size[0]) % 4 == 0 and all(w % 4 == 0 and w <= 1024 for w in layer_size[1:-1])
+    k0 = 2 * layer_size[0] if args.model == 'graphsage' else layer_size[0]       # width of the precomputed layer-0 input
+    widths_ok = k0 % 4 == 0 and all(w % 4 == 0 and w <= 1024 for w in layer_size[1:-1])
     return widths_ok and len(layer_size) >= 3
 
 

@@ -399,9 +399,9 @@ int bns_bn_bwd_f32(const float *dy, int64_t lddy, const float *x, int64_t ldx, i
  * module/model.py:80 for the layer-0 input; nothing but y is stored. */
 int bns_dropout_f32(const float *x, int64_t ldx, int64_t n, int64_t F, float p, uint64_t seed, uint64_t offset,
                     const uint64_t *offset_dev, float *y, int64_t ldy, void *stream);
-/* y[r, :] = x[r, :] * row_scale[r] */
-int bns_scale_rows_f32(const float *x, int64_t ldx, int64_t n, int64_t F, const float *row_scale, float *y, int64_t ldy,
-                       void *stream);
+/* y[r, :] = x[r, :] * row_scale[r] + bias[:]      (row_scale / bias may be NULL: 1 / 0) */
+int bns_scale_rows_f32(const float *x, int64_t ldx, int64_t n, int64_t F, const float *row_scale, const float *bias, float *y,
+                       int64_t ldy, void *stream);
 
 #ifdef __cplusplus
 }
