@@ -428,7 +428,7 @@ def run_ours(a):
             probe["ok"] = bool(probe["rel_err"] < 1e-4)
     if probe is not None:
         out["parity_probe"] = probe
-    print(json.dumps(out))
+    print(json.dumps(out), file=sys.__stdout__, flush=True)
     _leave(world)
 
 
@@ -457,11 +457,14 @@ def inprocess_probe_loss(shape: str, world: int, dev) -> float:
         p = parts[r]
         args = make_args(world, "nccl", {"n_feat": p.meta["n_feat"], "n_class": p.meta["n_class"],
                                          "n_train": p.meta["n_train"], "dataset": shape})
-        with contextlib.redirect_stdout(sys.stderr):
-            st = train.setup(p.graph, p.node_dict, p.gpb, args, dev)
+        st = train.setup(p.graph, p.node_dict, p.gpb, args, dev)
         return float(train.probe_loss(st, 0).item())          # already the sum over the ranks
 
-    return float(run_threads(world, fn, device=str(dev))[0])
+    # redirect ONCE, around the threads: contextlib.redirect_stdout swaps the process-wide sys.stdout, so entering /
+    # leaving it from several threads can leave stdout pointing at stderr for good (and the JSON line with it)
+    with contextlib.redirect_stdout(sys.stderr):
+        out = run_threads(world, fn, device=str(dev))
+    return float(out[0])
 
 
 # =====================================================================================================

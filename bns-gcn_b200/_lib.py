@@ -15,6 +15,7 @@ LIB_PATH = os.path.join(_HERE, "csrc", "libbnsgcn.so")
 
 ABI_VERSION = 2
 P2P_HANDLE_BYTES = 64
+COMM_ID_BYTES = 128
 
 MAX_PEERS = 16      # BNS_MAX_PEERS
 
@@ -112,6 +113,16 @@ SIGNATURES = {
                                  c_void_p, c_void_p, c_void_p, c_int64, c_void_p, c_void_p, c_void_p]),
     "bns_bn_bwd_f32": (c_int, [c_void_p, c_int64, c_void_p, c_int64, c_int64, c_int64, c_void_p, c_void_p, c_void_p, c_void_p,
                                c_float, c_void_p, c_int64, c_void_p]),
+    "bns_comm_unique_id": (c_int, [c_void_p]),
+    "bns_ctx_create": (c_int, [POINTER(c_void_p), c_int32, c_int32, c_void_p]),
+    "bns_ctx_destroy": (c_int, [c_void_p]),
+    "bns_allreduce_sum_f32": (c_int, [c_void_p, c_void_p, c_int64, c_void_p]),
+    "bns_alltoallv_f32": (c_int, [c_void_p, c_void_p, POINTER(c_int64), POINTER(c_int64), c_void_p, POINTER(c_int64),
+                                  POINTER(c_int64), c_int64, c_void_p]),
+    "bns_alltoallv_i64": (c_int, [c_void_p, c_void_p, POINTER(c_int64), POINTER(c_int64), c_void_p, POINTER(c_int64),
+                                  POINTER(c_int64), c_void_p]),
+    "bns_alltoallv_bytes": (c_int, [c_void_p, POINTER(c_void_p), POINTER(c_int64), POINTER(c_void_p), POINTER(c_int64),
+                                    c_void_p]),
     "bns_dropout_f32": (c_int, [c_void_p, c_int64, c_int64, c_int64, c_float, c_uint64, c_uint64, c_void_p, c_void_p,
                                 c_int64, c_void_p]),
     "bns_scale_rows_f32": (c_int, [c_void_p, c_int64, c_int64, c_int64, c_void_p, c_void_p, c_void_p, c_int64, c_void_p]),

@@ -1781,6 +1781,7 @@ extern "C" int bns_p2p_wait_flag(bns_p2p_t *p, int32_t flag_index, uint64_t flag
 // the tail of the epoch: loss, Adam, consolidated exchange, per-epoch maps, halo compaction
 // =================================================================================================
 #include "fused.cuh"
+#include "comm.cuh"
 
 // =================================================================================================
 // K8: dense layers on tcgen05 (3xTF32 with the operand split fused into the pipeline)

@@ -148,13 +148,57 @@ class DistComm:
     kind = "dist"
 
     def __init__(self):
+        import os
         import torch.distributed as dist
         self._d = dist
         self.rank, self.size = dist.get_rank(), dist.get_world_size()
         self.backend = dist.get_backend()
+        # BNS_COMM=abi: the data-path collectives go through libbnsgcn.so's own communicator (bns_ctx_create /
+        # bns_allreduce_sum_f32 / bns_alltoallv_bytes: what a non-torch host would bind);
+        # torch.distributed then only bootstraps (hands out the unique id) and serves the setup-time object exchanges
+        self._ctx = None
+        if self.backend == "nccl" and self.size > 1 and os.environ.get("BNS_COMM", "torch") == "abi":
+            self._init_abi()
+
+    def _init_abi(self):
+        import ctypes
+        from .._lib import COMM_ID_BYTES, check, lib
+        ident = ctypes.create_string_buffer(COMM_ID_BYTES)
+        if self.rank == 0:
+            check(lib.bns_comm_unique_id(ident), "bns_comm_unique_id")
+        box = [ident.raw]
+        self._d.broadcast_object_list(box, src=0)
+        ctx_ = ctypes.c_void_p()
+        check(lib.bns_ctx_create(ctypes.byref(ctx_), self.rank, self.size, box[0]), "bns_ctx_create")
+        self._ctx = ctx_
+
+    def _abi_alltoall(self, send, recv):
+        import ctypes
+        from .._lib import check, lib
+        P = self.size
+        sp, sb = (ctypes.c_void_p * P)(), (ctypes.c_int64 * P)()
+        rp, rb = (ctypes.c_void_p * P)(), (ctypes.c_int64 * P)()
+        keep = []
+        for j in range(P):
+            if j == self.rank:
+                continue
+            if send[j] is not None and send[j].numel():
+                t = send[j].contiguous()
+                keep.append(t)
+                sp[j], sb[j] = t.data_ptr(), t.numel() * t.element_size()
+            if recv[j] is not None and recv[j].numel():
+                if not recv[j].is_contiguous():
+                    raise RuntimeError("alltoall: receive buffers must be contiguous")
+                rp[j], rb[j] = recv[j].data_ptr(), recv[j].numel() * recv[j].element_size()
+        dev = next(t.device for t in list(send) + list(recv) if t is not None)
+        with torch.cuda.device(dev):
+            check(lib.bns_alltoallv_bytes(self._ctx, sp, sb, rp, rb, torch.cuda.current_stream(dev).cuda_stream),
+                  "bns_alltoallv_bytes")
 
     def alltoall(self, send, recv, tag: int = 0):
         d = self._d
+        if self._ctx is not None and any(t is not None and t.is_cuda for t in list(send) + list(recv)):
+            return self._abi_alltoall(send, recv)
         if self.backend == "nccl":
             ops = []
             for i in range(1, self.size):
@@ -178,6 +222,12 @@ class DistComm:
             r.wait()
 
     def all_reduce_sum(self, t: torch.Tensor):
+        if self._ctx is not None and t.is_cuda and t.dtype == torch.float32 and t.is_contiguous():
+            from .._lib import check, lib
+            with torch.cuda.device(t.device):
+                check(lib.bns_allreduce_sum_f32(self._ctx, t.data_ptr(), t.numel(),
+                                                torch.cuda.current_stream(t.device).cuda_stream), "bns_allreduce_sum_f32")
+            return
         self._d.all_reduce(t, op=self._d.ReduceOp.SUM)
 
     def all_gather_bytes(self, b: bytes) -> List[bytes]:

@@ -494,6 +494,12 @@ class GraphedEpoch:
             train_epoch(st, int(st.epoch_dev.item()))
         torch.cuda.synchronize(dev)
         buf, red = ctx.buffer._get(), ctx.reducer._get()
+        if _rank_size()[1] > 2 and getattr(buf, "_backend", None) == 'nccl':
+            # Measured (tools/dist_check.py --graph, 4 x B200): the staged transport replayed from a graph is correct at
+            # 2 ranks and WRONG at 4 (its NCCL send/recv batches sit on three streams of the captured graph); the
+            # peer-mapped transport -- the default, flags in peer memory -- is bit-identical to the eager run at 2/4/8.
+            raise NotImplementedError("GraphedEpoch with more than 2 partitions needs --backend p2p (the staged NCCL "
+                                      "transport is only replay-safe at 2 ranks)")
         st.graph_mode = buf.graph_mode = red.graph_mode = True
         buf.seq_dev = st.epoch_dev
         # flag values of the replays: seq_base + epoch counter, strictly above every value the eager epochs (and any

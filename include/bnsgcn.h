@@ -40,6 +40,7 @@ extern "C" {
 
 typedef struct bns_graph bns_graph_t;   /* opaque: a static CSR matrix resident in HBM */
 typedef struct bns_p2p   bns_p2p_t;     /* opaque: peer-mapped exchange slabs of one rank */
+typedef struct bns_ctx   bns_ctx_t;     /* opaque: one rank's communicator (NCCL) */
 
 int         bns_abi_version(void);
 const char *bns_last_error(void);
@@ -394,6 +395,29 @@ int bns_bn_apply_f32(const float *x, int64_t ldx, int64_t rows, int64_t F, const
 int bns_bn_bwd_f32(const float *dy, int64_t lddy, const float *x, int64_t ldx, int64_t rows, int64_t F, const float *mean,
                    const float *rstd, const float *weight, const float *sums /*device [2F]*/, float whole_size, float *dx,
                    int64_t lddx, void *stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Collectives.  One context per rank / GPU; NCCL underneath, resolved at run time (dlopen).
+ * Bootstrap: rank 0 calls bns_comm_unique_id and hands the BNS_COMM_ID_BYTES bytes to the other ranks by any
+ * out-of-band means (the reference rendezvouses over TCP, train.py:459-468); every rank then calls bns_ctx_create.
+ *   bns_allreduce_sum_f32   helper/reducer.py:28-49: the weight gradients, as ONE flat bucket, in place
+ *   bns_alltoallv_i64       helper/utils.py:187-213 data_transfer(..., tag=NODE): the sampled id lists
+ *   bns_alltoallv_f32       helper/feature_buffer.py:101-153: boundary rows, staged transport (the peer-mapped transport
+ *                           -- bns_p2p_* -- needs no collective at all)
+ * counts / offsets: host arrays [world], in rows of `width` elements; the entry of the own rank is ignored.
+ * ----------------------------------------------------------------------------------------------*/
+#define BNS_COMM_ID_BYTES 128
+int bns_comm_unique_id(void *id_out /*host, BNS_COMM_ID_BYTES*/);
+int bns_ctx_create(bns_ctx_t **out, int32_t rank, int32_t world, const void *unique_id /*host, BNS_COMM_ID_BYTES*/);
+int bns_ctx_destroy(bns_ctx_t *c);
+int bns_allreduce_sum_f32(bns_ctx_t *c, float *buf /*device*/, int64_t n, void *stream);
+int bns_alltoallv_f32(bns_ctx_t *c, const float *send, const int64_t *send_counts, const int64_t *send_offsets, float *recv,
+                      const int64_t *recv_counts, const int64_t *recv_offsets, int64_t width, void *stream);
+int bns_alltoallv_i64(bns_ctx_t *c, const int64_t *send, const int64_t *send_counts, const int64_t *send_offsets,
+                      int64_t *recv, const int64_t *recv_counts, const int64_t *recv_offsets, void *stream);
+/* the same for per-peer buffers that are separate allocations (host arrays [world] of device pointers / byte counts) */
+int bns_alltoallv_bytes(bns_ctx_t *c, const void *const *send_ptrs, const int64_t *send_bytes, void *const *recv_ptrs,
+                        const int64_t *recv_bytes, void *stream);
 
 /* y = dropout_p(x) with the Philox mask of bns_ln_relu_dropout_fwd_f32 (counter = (row, vector, offset), key = seed):
  * module/model.py:80 for the layer-0 input; nothing but y is stored. */
