@@ -358,10 +358,13 @@ def run_ours(a):
     ex_bytes = 4 * WORKLOAD["n_hidden"] * (sum(st.send_size) + sum(st.recv_size)) * n_comm_layers if world > 1 else 0
     traffic, traffic_src = None, None
     tp = os.path.join(ROOT, "profiles", "spmm_traffic.json")
-    if os.path.exists(tp) and (WORKLOAD["shape"], world) == ("reddit", 1):
+    if os.path.exists(tp) and WORKLOAD["shape"] == "reddit":
+        # not measurable inside this run (ncu replays kernels): the per-launch DRAM bytes of the F = 256 inner SpMM from
+        # the committed capture of the same kernel on the same shape (tools/ncu_spmm_traffic.sh; world 1 and 4)
         with open(tp) as f:
             tj = json.load(f)
-        traffic, traffic_src = tj.get("dram_bytes_per_launch"), tj.get("source")
+        ent = tj.get(str(world)) or (tj if world == 1 else {})
+        traffic, traffic_src = ent.get("dram_bytes_per_launch"), ent.get("source")
     ach = spmm_alg / (spmm_ms * 1e-3) / 1e9 if spmm_ms > 0 else 0.0
     out = {
         "metric": METRIC(), "value": K / (dev_ms * 1e-3),
