@@ -474,7 +474,7 @@ __device__ __forceinline__ int32_t ld_stream_i32(const int32_t *p) {
 // split into 32/G row groups of G lanes that walk different entries of the chunk concurrently (every lane
 // still issues 16-byte loads) and are summed with shuffles at the end.
 template <int W, int G, int NV, bool MAP, bool CSCALE, bool GUARD>
-__global__ void __launch_bounds__(kThreads) spmm_kernel(SpmmArgs a) {
+__global__ void __launch_bounds__(kThreads, (NV <= 1 ? 5 : 4)) spmm_kernel(SpmmArgs a) {
     constexpr int NG = 32 / G;                               // entries walked concurrently by one warp
     constexpr int UNROLL = (NV <= 2) ? 8 / NV : 2;           // independent 16-byte gathers in flight per lane
     constexpr int SLAB = G * W * NV;
