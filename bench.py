@@ -144,6 +144,8 @@ def run_ours(a):
             raise SystemExit(f"--gpus {a.gpus} needs torchrun (one rank per GPU); WORLD_SIZE is 1")
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
+    if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
+        os.environ["NCCL_DEBUG"] = "WARN"        # NCCL prints its version banner on STDOUT: keep that for the JSON line
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
     K, W = a.steps, max(a.warmup, 3)

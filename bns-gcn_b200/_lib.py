@@ -89,7 +89,18 @@ SIGNATURES = {
     "bns_p2p_wait_flag": (c_int, [c_void_p, c_int32, c_uint64, c_void_p, c_void_p]),
     # ---- ABI 2 ----
     "bns_epoch_maps_update": (c_int, [POINTER(EpochMaps), c_void_p, c_size_t, c_void_p]),
-    "bns_graph_compact_cols": (c_int, [c_void_p, c_void_p, c_int64, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
+    "bns_graph_compact_cols": (c_int, [c_void_p, c_void_p, c_int64, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
+                                       c_void_p]),
+    "bns_gat_forward_f32": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_void_p, c_int64, c_int32,
+                                    c_int32, c_void_p, c_void_p, c_float, c_float, c_uint64, c_uint64, c_void_p, c_void_p,
+                                    c_int64, c_void_p, c_void_p, c_void_p]),
+    "bns_gat_backward_f32": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_void_p, c_int64, c_int32,
+                                     c_int32, c_void_p, c_void_p, c_float, c_float, c_uint64, c_uint64, c_void_p, c_void_p,
+                                     c_int64, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
+                                     c_void_p]),
+    "bns_gat_colsum_f32": (c_int, [c_void_p, c_void_p, c_int32, c_void_p, c_int64, c_void_p, c_void_p]),
+    "bns_spmm_weighted_f32": (c_int, [c_void_p, c_void_p, c_int64, c_int64, c_void_p, c_int64, c_void_p, c_int64, c_int,
+                                      c_void_p, c_int64, c_int, c_void_p, c_size_t, c_void_p]),
     "bns_spmm_compact_f32": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int64, c_void_p, c_int64,
                                      c_void_p, c_int64, c_int32, c_int, c_void_p, c_size_t, c_void_p]),
     "bns_p2p_put_all_f32": (c_int, [c_void_p, POINTER(PutAll), c_int64, c_void_p, c_int64, c_int64, c_void_p, c_int32,

@@ -89,6 +89,7 @@ struct bns_graph {
     int32_t *chunk_row = nullptr;   // [n_chunks]
     int64_t *chunk_start = nullptr; // [n_chunks]
     int32_t *chunk_part = nullptr;  // [n_chunks]  partial-sum slot, -1 when the row is a single chunk
+    int32_t *row_chunk = nullptr;   // [n_rows+1]  first chunk of each row (row r owns chunks row_chunk[r] .. row_chunk[r+1])
     int32_t *chunk_split = nullptr; // [n_chunks]  index of the row in split_row / split_part, -1 when it is a single chunk
     int32_t *split_row = nullptr;   // [n_split]
     int32_t *split_part = nullptr;  // [n_split+1] first partial slot of each split row
@@ -225,7 +226,8 @@ int build_chunks(bns_graph *g, cudaStream_t st) {
     BNS_CUDA(cudaGetLastError());
     BNS_CUDA(cudaStreamSynchronize(st));
     cudaFree(n_chunk); cudaFree(n_part); cudaFree(is_split);
-    cudaFree(chunk_off); cudaFree(part_off); cudaFree(split_off); cudaFree(tmp);
+    g->row_chunk = chunk_off;            // kept: the row-wise walkers (gat.cuh) go from a row to its chunks
+    cudaFree(part_off); cudaFree(split_off); cudaFree(tmp);
     return BNS_OK;
 }
 
@@ -407,6 +409,8 @@ struct SpmmArgs {
     const float *row_scale;
     const float *col_scale;
     const float *edge_weight;   // per entry (CSR order) or NULL
+    const int32_t *edge_perm;   // optional: entry k's weight is edge_weight[edge_perm[k] * edge_ld] (weights kept in the
+    int64_t edge_ld;            // ORDER OF ANOTHER GRAPH, e.g. the source graph of a transpose; [nnz, heads] layouts)
     const int32_t *row_map;
     const int32_t *col_map;
     int32_t n_direct;
@@ -522,7 +526,7 @@ __global__ void __launch_bounds__(kThreads, (NV <= 1 ? 5 : 4)) spmm_kernel(SpmmA
                 col = ld_stream_i32(a.indices + k);
                 if (CSCALE) {        // per-source and / or per-entry weight (GAT attention) -> the FMA path
                     if (a.col_scale) sc = __ldg(a.col_scale + col);
-                    if (a.edge_weight) sc *= __ldg(a.edge_weight + k);
+                    if (a.edge_weight) sc *= __ldg(a.edge_weight + (a.edge_perm ? (int64_t)__ldg(a.edge_perm + k) : k) * a.edge_ld);
                 }
                 if (MAP) {
                     if (col >= a.n_direct) col = __ldg(a.col_map + (col - a.n_direct));
@@ -773,6 +777,7 @@ extern "C" int bns_spmm_sum_f32(const bns_graph_t *g, const float *X, int64_t ld
     a.n_chunks = g->n_chunks; a.n_split = g->n_split; a.chunk_nnz = g->chunk_nnz;
     a.X = X; a.ldx = ldx; a.Y = Y; a.ldy = ldy; a.F = (int32_t)F;
     a.row_scale = row_scale; a.col_scale = col_scale; a.edge_weight = edge_weight; a.row_map = row_map; a.col_map = col_map;
+    a.edge_perm = nullptr; a.edge_ld = 1;
     a.n_direct = (int32_t)n_direct; a.accumulate = accumulate ? 1 : 0;
     a.ws = reinterpret_cast<float *>(ws); a.ldws = ws_ld(F);
     a.n_tiles = 1;
@@ -803,10 +808,39 @@ extern "C" int bns_spmm_compact_f32(const bns_graph_t *g, const int32_t *cidx, c
     a.n_chunks = g->n_chunks; a.n_split = g->n_split; a.chunk_nnz = g->chunk_nnz;
     a.X = X; a.ldx = ldx; a.Y = Y; a.ldy = ldy; a.F = (int32_t)F;
     a.row_scale = row_scale; a.col_scale = nullptr; a.edge_weight = cw; a.row_map = nullptr; a.col_map = nullptr;
+    a.edge_perm = nullptr; a.edge_ld = 1;
     a.n_direct = (int32_t)g->n_cols; a.accumulate = accumulate ? 1 : 0;
     a.ws = reinterpret_cast<float *>(ws); a.ldws = ws_ld(F);
     a.n_tiles = 1;
     return spmm_dispatch(a, x_rows > 0 ? x_rows : g->n_cols, slab_hint, as_stream(stream));
+}
+
+// Y[orow(r)] (+)= sum_k w_k X[c_k] with w_k = weights[(perm ? perm[k] : k) * ldw]: the weighted aggregation of GATConv
+// (u_mul_e + sum) and -- on a transpose, with perm = its entry permutation (perm_from_transpose != 0) -- its gradient with
+// respect to the source features, the attention staying in the order of the forward graph ([nnz, heads], one head per call).
+extern "C" int bns_spmm_weighted_f32(const bns_graph_t *g, const float *X, int64_t ldx, int64_t F, float *Y, int64_t ldy,
+                                     const float *weights, int64_t ldw, int perm_from_transpose, const int32_t *row_map,
+                                     int64_t x_rows, int accumulate, void *ws, size_t ws_bytes, void *stream) {
+    BNS_REQUIRE(g && weights, "bns_spmm_weighted_f32: NULL argument");
+    BNS_REQUIRE(F > 0 && F < (1 << 24) && ldw >= 1, "bns_spmm_weighted_f32: bad width");
+    BNS_REQUIRE(!perm_from_transpose || g->perm, "bns_spmm_weighted_f32: not a graph made by bns_graph_transpose");
+    if (g->n_rows == 0) return BNS_OK;
+    BNS_REQUIRE(Y && (X || g->nnz == 0) && ldx >= F && ldy >= F, "bns_spmm_weighted_f32: bad matrix");
+    const size_t need = bns_spmm_workspace_bytes(g, F);
+    if (need > 0 && (ws == nullptr || ws_bytes < need))
+        return fail(BNS_E_WORKSPACE, "bns_spmm_weighted_f32: workspace %zu bytes < %zu needed", ws_bytes, need);
+    SpmmArgs a;
+    a.indptr = g->indptr; a.indices = g->indices;
+    a.chunk_row = g->chunk_row; a.chunk_start = g->chunk_start; a.chunk_part = g->chunk_part; a.chunk_cnt = nullptr;
+    a.split_row = g->split_row; a.split_part = g->split_part;
+    a.n_chunks = g->n_chunks; a.n_split = g->n_split; a.chunk_nnz = g->chunk_nnz;
+    a.X = X; a.ldx = ldx; a.Y = Y; a.ldy = ldy; a.F = (int32_t)F;
+    a.row_scale = nullptr; a.col_scale = nullptr; a.edge_weight = weights; a.row_map = row_map; a.col_map = nullptr;
+    a.edge_perm = perm_from_transpose ? g->perm : nullptr; a.edge_ld = ldw;
+    a.n_direct = (int32_t)g->n_cols; a.accumulate = accumulate ? 1 : 0;
+    a.ws = reinterpret_cast<float *>(ws); a.ldws = ws_ld(F);
+    a.n_tiles = 1;
+    return spmm_dispatch(a, x_rows > 0 ? x_rows : g->n_cols, 0, as_stream(stream));
 }
 
 // =================================================================================================
@@ -1781,6 +1815,7 @@ extern "C" int bns_p2p_wait_flag(bns_p2p_t *p, int32_t flag_index, uint64_t flag
 // the tail of the epoch: loss, Adam, consolidated exchange, per-epoch maps, halo compaction
 // =================================================================================================
 #include "fused.cuh"
+#include "gat.cuh"
 #include "comm.cuh"
 
 // =================================================================================================

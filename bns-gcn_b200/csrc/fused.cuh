@@ -659,7 +659,7 @@ __global__ void __launch_bounds__(kThreads) compact_cols_kernel(const int64_t *_
                                                                 int32_t chunk_nnz, const int32_t *__restrict__ col_map,
                                                                 int32_t n_direct, const float *__restrict__ col_scale,
                                                                 int32_t *__restrict__ cidx, float *__restrict__ cw,
-                                                                int32_t *__restrict__ chunk_cnt) {
+                                                                int32_t *__restrict__ cpos, int32_t *__restrict__ chunk_cnt) {
     const int lane = threadIdx.x & 31;
     const int64_t warps_total = (int64_t)gridDim.x * kWarps;
     for (int64_t c = (int64_t)blockIdx.x * kWarps + (threadIdx.x >> 5); c < n_chunks; c += warps_total) {
@@ -688,6 +688,7 @@ __global__ void __launch_bounds__(kThreads) compact_cols_kernel(const int64_t *_
                     const int pos = off + __popc(m & ((1u << lane) - 1u));
                     cidx[s + pos] = col[u];
                     if (cw) cw[s + pos] = __ldg(col_scale + orig[u]);
+                    if (cpos) cpos[s + pos] = (int32_t)(k0 + 32 * u + lane);       // where the entry sits in the CSR
                 }
                 off += __popc(m);
             }
@@ -699,8 +700,9 @@ __global__ void __launch_bounds__(kThreads) compact_cols_kernel(const int64_t *_
 }  // namespace
 
 extern "C" int bns_graph_compact_cols(const bns_graph_t *g, const int32_t *col_map, int64_t n_direct, const float *col_scale,
-                                      int32_t *cidx /*[nnz]*/, float *cw /*[nnz] or NULL*/, int32_t *chunk_cnt /*[n_chunks]*/,
-                                      void *stream) {
+                                      int32_t *cidx /*[nnz]*/, float *cw /*[nnz] or NULL*/, int32_t *cpos /*[nnz] or NULL*/,
+                                      int32_t *chunk_cnt /*[n_chunks]*/, void *stream) {
+    BNS_REQUIRE(!cpos || (g && g->nnz < INT32_MAX), "bns_graph_compact_cols: cpos needs nnz < 2^31");
     BNS_REQUIRE(g && col_map && cidx && chunk_cnt, "bns_graph_compact_cols: NULL argument");
     BNS_REQUIRE((cw == nullptr) == (col_scale == nullptr), "bns_graph_compact_cols: cw and col_scale go together");
     BNS_REQUIRE(n_direct >= 0 && n_direct <= g->n_cols, "bns_graph_compact_cols: n_direct out of range");
@@ -708,7 +710,7 @@ extern "C" int bns_graph_compact_cols(const bns_graph_t *g, const int32_t *col_m
     int64_t want = (g->n_chunks + kWarps - 1) / kWarps, cap = (int64_t)sm_count() * 8;
     compact_cols_kernel<<<(unsigned)(want < cap ? want : cap), kThreads, 0, as_stream(stream)>>>(
         g->indptr, g->indices, g->chunk_row, g->chunk_start, g->n_chunks, g->chunk_nnz, col_map, (int32_t)n_direct, col_scale,
-        cidx, cw, chunk_cnt);
+        cidx, cw, cpos, chunk_cnt);
     ++g_launches;
     BNS_CUDA(cudaGetLastError());
     return BNS_OK;

@@ -30,13 +30,15 @@ class PartitionGraph:
         # per-epoch compaction of a_out to the sampled halo columns (ops.CompactedCols), refreshed by construct_graph
         self.compact: Optional[ops.CompactedCols] = None
         self.halo_col_scale: Optional[torch.Tensor] = None      # GCN: 1/sqrt(out_deg) of the halo nodes (static)
+        self.want_positions = False                             # GAT: the compaction also records CSR positions
 
     def refresh_compaction(self) -> None:
         """Call after every change of ``slot`` (train.construct_graph does)."""
         if self.a_out is None or self.a_out.nnz == 0:
             return
         if self.compact is None:
-            self.compact = ops.CompactedCols(self.a_out, with_weights=self.halo_col_scale is not None)
+            self.compact = ops.CompactedCols(self.a_out, with_weights=self.halo_col_scale is not None,
+                                             with_positions=self.want_positions)
         self.compact.refresh(self.slot, 0, self.halo_col_scale)
 
     def num_nodes(self, ntype: str = '_V') -> int:
@@ -172,3 +174,71 @@ class WeightedAggregate(torch.autograd.Function):
                 ops.spmm(g.a_out_t, dy, tail, edge_weight=w_out[g.a_out_t.perm().long()], row_map=g.slot)
                 ops.sddmm_dot(g.a_out, dy, ft_u[n_in:], col_map=g.slot, n_direct=0, out=d_w_out)
         return d_ft, d_w_in, d_w_out, None
+
+
+class GatAttention(torch.autograd.Function):
+    """The attention of ``dgl.nn.GATConv`` for all heads (``bns_gat_forward_f32`` / ``bns_gat_backward_f32`` /
+    ``bns_gat_colsum_f32`` / ``bns_spmm_weighted_f32``):
+
+        rst_v = sum_u attn_drop(edge_softmax(leaky_relu(el_u + er_v)))_uv * ft_u
+
+    over the inner entries and this epoch's sampled halo entries (the partition graph's compaction with positions).
+    ``ft [n_u, H * Fo]``, ``el [n_u, H]``, ``er [n_in, H]`` -> ``[n_in, H * Fo]``; gradients for all three."""
+
+    @staticmethod
+    def forward(ctx, ft, el, er, g: PartitionGraph, H: int, Fo: int, slope: float, p: float, seed: int):
+        from ._lib import check, lib
+        ft, el, er = ft.contiguous(), el.contiguous(), er.contiguous()
+        n_in, dev = g.n_in, ft.device
+        c = g.compact if (g.a_out is not None and ft.shape[0] > n_in) else None
+        if c is not None and c.cpos is None:
+            raise RuntimeError("GatAttention: the partition graph was compacted without positions (want_positions)")
+        rst = torch.empty(n_in, H * Fo, dtype=torch.float32, device=dev)
+        p_in = torch.empty(max(g.a_in.nnz, 1), H, dtype=torch.float32, device=dev)
+        p_out = torch.empty(max(g.a_out.nnz, 1), H, dtype=torch.float32, device=dev) if c is not None else None
+        off, off_dev = ops.RNG["offset"], ops.RNG["offset_dev"]
+        args = (g.a_in._h, None if c is None else g.a_out._h, None if c is None else c.cidx.data_ptr(),
+                None if c is None else c.chunk_cnt.data_ptr(), None if c is None else c.cpos.data_ptr(), n_in,
+                ft.data_ptr(), ft.stride(0), H, Fo, el.data_ptr(), er.data_ptr(), float(slope), float(p),
+                seed & (2 ** 64 - 1), off & (2 ** 64 - 1), ops._ptr(off_dev))
+        with torch.cuda.device(dev):
+            check(lib.bns_gat_forward_f32(*args, rst.data_ptr(), rst.stride(0), p_in.data_ptr(), ops._ptr(p_out),
+                                          torch.cuda.current_stream(dev).cuda_stream), "bns_gat_forward_f32")
+        ctx.g, ctx.c, ctx.args, ctx.cfg = g, c, args, (H, Fo, float(p))
+        ctx.save_for_backward(ft, el, er, p_in, *(() if p_out is None else (p_out,)))
+        return rst
+
+    @staticmethod
+    def backward(ctx, d_rst):
+        from ._lib import check, lib
+        g, c = ctx.g, ctx.c
+        H, Fo, p = ctx.cfg
+        ft, el, er, p_in, *rest = ctx.saved_tensors
+        p_out = rest[0] if rest else None
+        d_rst = d_rst.contiguous()
+        dev, n_in, n_u = ft.device, g.n_in, ft.shape[0]
+        de_in = torch.empty_like(p_in)
+        de_out = torch.empty_like(p_out) if p_out is not None else None
+        a_in = torch.empty_like(p_in) if p > 0 else None
+        a_out = torch.empty_like(p_out) if (p > 0 and p_out is not None) else None
+        d_er = torch.empty(n_in, H, dtype=torch.float32, device=dev)
+        st = torch.cuda.current_stream(dev).cuda_stream
+        with torch.cuda.device(dev):
+            check(lib.bns_gat_backward_f32(*ctx.args, d_rst.data_ptr(), d_rst.stride(0), p_in.data_ptr(), ops._ptr(p_out),
+                                           de_in.data_ptr(), ops._ptr(de_out), ops._ptr(a_in), ops._ptr(a_out),
+                                           d_er.data_ptr(), st), "bns_gat_backward_f32")
+            d_el = torch.empty(n_u, H, dtype=torch.float32, device=dev)
+            check(lib.bns_gat_colsum_f32(g.a_in_t._h, de_in.data_ptr(), H, None, 0, d_el.data_ptr(), st),
+                  "bns_gat_colsum_f32")
+            if c is not None:
+                check(lib.bns_gat_colsum_f32(g.a_out_t._h, de_out.data_ptr(), H, g.slot.data_ptr(), n_in, d_el.data_ptr(),
+                                             st), "bns_gat_colsum_f32")
+        w_in, w_out = (a_in, a_out) if p > 0 else (p_in, p_out)
+        d_ft = torch.empty(n_u, H * Fo, dtype=torch.float32, device=dev)
+        for h in range(H):
+            cols = slice(h * Fo, (h + 1) * Fo)
+            ops.spmm_weighted(g.a_in_t, d_rst[:, cols], d_ft[:n_in, cols], w_in, h, through_perm=True)
+            if c is not None:
+                ops.spmm_weighted(g.a_out_t, d_rst[:, cols], d_ft[n_in:, cols], w_out, h, through_perm=True,
+                                  row_map=g.slot)
+        return d_ft, d_el, d_er, None, None, None, None, None, None

@@ -13,8 +13,14 @@ import torch
 import torch.nn.functional as F
 from torch import nn
 
-from ..graph import PartitionGraph, WeightedAggregate, gat_entries
+from .. import ops
+from ..graph import GatAttention, PartitionGraph, WeightedAggregate, gat_entries
 from . import dense
+
+
+# the attention (u_add_v, leaky_relu, edge_softmax, attn_drop, u_mul_e + sum of DGL's GATConv) as kernels
+# (graph.GatAttention); False / per-head widths that are not multiples of 4: the op-by-op torch path below
+FUSED_ATTENTION = True
 
 
 class GATConv(nn.Module):
@@ -55,6 +61,15 @@ class GATConv(nn.Module):
         ft_dst = dense.linear(h_dst, self.fc.weight).view(-1, H, Fo)
         el = (ft_src * self.attn_l).sum(dim=-1)                     # [n_U, H]
         er = (ft_dst * self.attn_r).sum(dim=-1)                     # [n_in, H]
+        if FUSED_ATTENTION and Fo % 4 == 0 and H <= 8 and H * Fo <= 1024 and \
+                (graph.a_out is None or (graph.compact is not None and graph.compact.cpos is not None)):
+            # score -> edge softmax -> dropout -> weighted aggregation (and their backward) as kernels, all heads at once
+            p = self.attn_drop.p if self.training else 0.0
+            rst = GatAttention.apply(ft_src.reshape(-1, H * Fo), el, er, graph, H, Fo, self.negative_slope, p,
+                                     ops.RNG["seed"] + 15485863 * (1 + getattr(self, "_layer_index", 0))).view(-1, H, Fo)
+            if self.bias is not None:
+                rst = rst + self.bias.view(1, H, Fo)
+            return rst
         rin, cin, rout, cout = gat_entries(graph)
         e_in = F.leaky_relu(el[cin] + er[rin], self.negative_slope)                                  # [nnz_in, H]
         n_u = ft_src.shape[0]

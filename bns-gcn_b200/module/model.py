@@ -134,6 +134,8 @@ class GAT(GNNBase):
         super().__init__(layer_size, activation, use_pp, dropout, norm, n_linear)
         from .gat import GATConv
         self._populate(layer_size, lambda i, a, b: GATConv(a, b, heads, dropout, dropout), norm, train_size)
+        for i, layer in enumerate(self.layers):
+            layer._layer_index = i              # salts the Philox stream of the layer's attention dropout
 
     def forward(self, g, feat):
         h = feat

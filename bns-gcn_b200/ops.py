@@ -239,11 +239,13 @@ class CompactedCols:
     """Per-epoch compaction of a column-mapped matrix (``bns_graph_compact_cols``): the sampled entries of every
     chunk, already mapped to rows of X, moved to the front of the chunk's own index range."""
 
-    def __init__(self, g: DeviceGraph, with_weights: bool = False):
+    def __init__(self, g: DeviceGraph, with_weights: bool = False, with_positions: bool = False):
         self.g = g
         dev = g.device
         self.cidx = torch.empty(max(g.nnz, 1), dtype=torch.int32, device=dev)
         self.cw = torch.empty(max(g.nnz, 1), dtype=torch.float32, device=dev) if with_weights else None
+        # GAT: where each live entry sits in the CSR (its attention is kept at the original positions)
+        self.cpos = torch.empty(max(g.nnz, 1), dtype=torch.int32, device=dev) if with_positions else None
         self.chunk_cnt = torch.zeros(max(g.n_chunks, 1), dtype=torch.int32, device=dev)
 
     def refresh(self, col_map: torch.Tensor, n_direct: int = 0, col_scale: Optional[torch.Tensor] = None) -> None:
@@ -252,7 +254,7 @@ class CompactedCols:
             raise _lib.BnsError("CompactedCols: col_scale must be given exactly when it was built with_weights")
         with torch.cuda.device(self.g.device):
             check(lib.bns_graph_compact_cols(self.g._h, col_map.data_ptr(), n_direct, _ptr(col_scale), self.cidx.data_ptr(),
-                                             _ptr(self.cw), self.chunk_cnt.data_ptr(), _stream_ptr()),
+                                             _ptr(self.cw), _ptr(self.cpos), self.chunk_cnt.data_ptr(), _stream_ptr()),
                   "bns_graph_compact_cols")
 
 
@@ -281,6 +283,26 @@ def spmm_compact(c: CompactedCols, x: torch.Tensor, out: torch.Tensor, *, row_sc
         # algorithmic bytes of the SAMPLED product: its live entries, the rows of X it can reference, the output rows
         alg = 8 * (g.n_rows + 1) + 4 * live + 4 * F * x.shape[0] + 4 * F * out.shape[0]
         prof.append((ev0, ev1, alg, live, F, live))
+    return out
+
+
+def spmm_weighted(g: DeviceGraph, x: torch.Tensor, out: torch.Tensor, weights: torch.Tensor, head: int = 0, *,
+                  through_perm: bool = False, row_map: Optional[torch.Tensor] = None, accumulate: bool = False) -> torch.Tensor:
+    """``bns_spmm_weighted_f32``: ``out[orow(r)] (+)= sum_k w_k x[c_k]`` with ``w_k = weights[pos(k), head]`` where
+    ``pos(k) = k``, or -- ``through_perm``, for a transpose -- the position of entry ``k`` in the graph it was made from
+    (``weights`` is ``[nnz, heads]`` in THAT graph's entry order: GAT's attention)."""
+    _req(x, torch.float32, "x")
+    _req(out, torch.float32, "out")
+    _req(weights, torch.float32, "weights")
+    if x.stride(1) != 1 or out.stride(1) != 1 or weights.dim() != 2 or weights.stride(1) != 1:
+        raise _lib.BnsError("spmm_weighted: x / out must have unit column stride, weights must be [nnz, heads]")
+    F = x.shape[1]
+    ws = g.workspace(F)
+    with torch.cuda.device(x.device):
+        check(lib.bns_spmm_weighted_f32(g._h, x.data_ptr(), x.stride(0), F, out.data_ptr(), out.stride(0),
+                                        weights.data_ptr() + 4 * head, weights.stride(0), 1 if through_perm else 0,
+                                        _ptr(row_map), x.shape[0], 1 if accumulate else 0, _ptr(ws),
+                                        0 if ws is None else ws.numel(), _stream_ptr()), "bns_spmm_weighted_f32")
     return out
 
 

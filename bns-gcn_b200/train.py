@@ -310,6 +310,7 @@ def setup(graph: LocalGraph, node_dict, gpb, args, device=None) -> TrainState:
     node_dict = dict(node_dict)
     in_graph, out_graph = get_in_out_graph(graph, node_dict, dev, getattr(args, 'chunk_nnz', 0))
     part = PartitionGraph(graph.n_in, graph.n_halo, in_graph, out_graph, dev)
+    part.want_positions = args.model == 'gat'          # the fused attention keeps per-entry values at CSR positions
     boundary = get_boundary({k: v.to(dev) for k, v in node_dict.items() if k in ('part_id', NID)}, gpb)
     layer_size = get_layer_size(args.n_feat, args.n_hidden, args.n_class, args.n_layers)
     _, _, _, node_dict, boundary = move_to_cuda(graph, in_graph, out_graph, node_dict, boundary, dev)

@@ -303,10 +303,43 @@ int bns_epoch_maps_update(const bns_epoch_maps *maps /*host*/, void *fill_base, 
 int bns_graph_compact_cols(const bns_graph_t *g, const int32_t *col_map, int64_t n_direct,
                            const float *col_scale /*device [n_cols] or NULL: gathered per live entry into cw*/,
                            int32_t *cidx /*device [nnz]*/, float *cw /*device [nnz] or NULL*/,
+                           int32_t *cpos /*device [nnz] or NULL: position of each live entry in the CSR (GAT keeps its
+                                           per-entry attention at those positions)*/,
                            int32_t *chunk_cnt /*device [n_chunks]*/, void *stream);
 int bns_spmm_compact_f32(const bns_graph_t *g, const int32_t *cidx, const float *cw, const int32_t *chunk_cnt,
                          const float *X, int64_t ldx, int64_t F, float *Y, int64_t ldy, const float *row_scale,
                          int64_t x_rows, int32_t slab_hint, int accumulate, void *ws, size_t ws_bytes, void *stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * K10 fused: the attention of dgl.nn.GATConv (module/model.py:96-132; DGL 0.9 python/dgl/nn/pytorch/conv/gatconv.py):
+ *     e_uv = leaky_relu(el_u + er_v);  p = edge_softmax(e) over each destination's in-entries;  a = attn_drop(p);
+ *     rst_v = sum_u a_uv ft_u                     for all `heads` at once, one warp per destination row.
+ * The entries of row v are those of a_in followed by the SAMPLED ones of a_out (cidx / chunk_cnt / cpos from
+ * bns_graph_compact_cols with col_map = slot, n_direct = 0; halo source k reads ft row x_halo_base + k).
+ *   ft [n_u, heads * out_feats] (head-major columns), el [n_u, heads], er [n_in, heads]; out_feats % 4 == 0,
+ *   heads <= 8, heads * out_feats <= 1024.  P_in [nnz(a_in), heads] / P_out [nnz(a_out), heads]: the probabilities,
+ *   stored at the ORIGINAL entry positions, kept for the backward.  Dropout: Philox4x32-10(counter = (entry, head),
+ *   key = seed, offset [+ *offset_dev]), regenerated in backward.
+ * bns_gat_backward_f32: d e per entry into dE_in / dE_out (same layout as P), d er [n_in, heads], and the dropped
+ *   attention a = p * mask / (1 - q) into A_in / A_out (NULL when q == 0: then a = p).
+ * bns_gat_colsum_f32 (on a_in_t, then on a_out_t with row_map = slot): d el_u = sum over column u of d e.
+ * bns_spmm_weighted_f32: d ft = A^T d rst, one head per call, the attention read through the transpose's permutation.
+ * ----------------------------------------------------------------------------------------------*/
+int bns_gat_forward_f32(const bns_graph_t *a_in, const bns_graph_t *a_out /*or NULL*/, const int32_t *cidx,
+                        const int32_t *chunk_cnt, const int32_t *cpos, int64_t x_halo_base, const float *ft, int64_t ldft,
+                        int32_t heads, int32_t out_feats, const float *el, const float *er, float negative_slope, float p_drop,
+                        uint64_t seed, uint64_t offset, const uint64_t *offset_dev, float *rst, int64_t ldr, float *P_in,
+                        float *P_out, void *stream);
+int bns_gat_backward_f32(const bns_graph_t *a_in, const bns_graph_t *a_out, const int32_t *cidx, const int32_t *chunk_cnt,
+                         const int32_t *cpos, int64_t x_halo_base, const float *ft, int64_t ldft, int32_t heads,
+                         int32_t out_feats, const float *el, const float *er, float negative_slope, float p_drop, uint64_t seed,
+                         uint64_t offset, const uint64_t *offset_dev, const float *d_rst, int64_t ldd, const float *P_in,
+                         const float *P_out, float *dE_in, float *dE_out, float *A_in, float *A_out, float *d_er, void *stream);
+int bns_gat_colsum_f32(const bns_graph_t *gT, const float *dE, int32_t heads, const int32_t *row_map, int64_t out_base,
+                       float *d_el, void *stream);
+int bns_spmm_weighted_f32(const bns_graph_t *g, const float *X, int64_t ldx, int64_t F, float *Y, int64_t ldy,
+                          const float *weights, int64_t ldw, int perm_from_transpose, const int32_t *row_map, int64_t x_rows,
+                          int accumulate, void *ws, size_t ws_bytes, void *stream);
 
 /* ------------------------------------------------------------------------------------------------
  * C1/C2 + K3/K5 for ALL peers at once (helper/feature_buffer.py:101-129).

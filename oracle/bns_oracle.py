@@ -771,7 +771,9 @@ class GATConvRef(nn.Module):
     vendored with the reference, so this restates its published layer (Velickovic et al. 2018 as implemented in
     python/dgl/nn/pytorch/conv/gatconv.py): shared ``fc`` for source and destination, ``attn_l`` / ``attn_r``,
     LeakyReLU(0.2), softmax over each destination's in-edges, dropout on features and on attention, bias, no residual
-    or activation; xavier-normal init with the ReLU gain, zero bias.  PARITY UNPINNED for this layer's internals."""
+    or activation; xavier-normal init with the ReLU gain, zero bias.  Pinned by hand-computed outputs derived from the
+    layer's published definition (tests/test_gat_pin_cpu.py: uniform attention, both LeakyReLU branches, two heads with a
+    non-trivial fc and destination scores); DGL's own kernels cannot be run here."""
 
     def __init__(self, in_feats, out_feats, num_heads, feat_drop=0.0, attn_drop=0.0, negative_slope=0.2):
         super().__init__()

@@ -660,3 +660,103 @@ def test_dense_epilogue_row_scale_and_in_place_addend(built):
     o1, o2 = torch.empty(256, device=dev), torch.empty(256, device=dev)
     dense.colsum(a, out=o1, out2=o2)
     assert torch.equal(o1, o2) and _relerr(o1.cpu(), a.double().sum(0).float().cpu()) < 1e-5
+
+
+def _gat_case(H, Fo, seed, with_halo=True):
+    """A partition-like graph on the device + the per-entry lists a torch reference needs."""
+    from bns_gcn_b200 import ops
+    from bns_gcn_b200.graph import PartitionGraph
+    dev = torch.device("cuda:0")
+    gen = torch.Generator().manual_seed(seed)
+    n_in, n_halo, n_slab = 300, 260, 70
+    ip_in, ix_in = _rand_csr(n_in, n_in, 9, seed=seed, heavy=1, empty_frac=0.05)
+    a_in = ops.DeviceGraph.from_csr(ip_in.to(dev), ix_in.int().to(dev), n_in, 64)
+    a_out = None
+    ip_out = ix_out = None
+    if with_halo:
+        ip_out, ix_out = _rand_csr(n_in, n_halo, 12, seed=seed + 1, heavy=1, empty_frac=0.2)
+        a_out = ops.DeviceGraph.from_csr(ip_out.to(dev), ix_out.int().to(dev), n_halo, 64)
+    g = PartitionGraph(n_in, n_halo if with_halo else 0, a_in, a_out, dev)
+    g.want_positions = True
+    n_u = n_in
+    slot = None
+    if with_halo:
+        slot = torch.full((n_halo,), -1, dtype=torch.int32)
+        chosen = torch.randperm(n_halo, generator=gen)[:n_slab]
+        slot[chosen] = torch.randperm(n_slab, generator=gen).int()
+        g.slot.copy_(slot.to(dev))
+        g.refresh_compaction()
+        n_u = n_in + n_slab
+    rows_in = torch.repeat_interleave(torch.arange(n_in), ip_in[1:] - ip_in[:-1])
+    u = [ix_in]
+    v = [rows_in]
+    if with_halo:
+        rows_out = torch.repeat_interleave(torch.arange(n_in), ip_out[1:] - ip_out[:-1])
+        x = slot[ix_out].long()
+        keep = x >= 0
+        u.append(n_in + x[keep])
+        v.append(rows_out[keep])
+    return g, n_in, n_u, torch.cat(u), torch.cat(v), gen
+
+
+@pytest.mark.parametrize("H,Fo,with_halo", [(1, 64, True), (2, 8, True), (4, 16, False), (1, 256, True)])
+def test_fused_gat_attention_matches_the_per_entry_reference(built, H, Fo, with_halo):
+    """graph.GatAttention == the u_add_v / leaky_relu / edge_softmax / u_mul_e+sum algebra of dgl.nn.GATConv written with
+    torch ops on explicit entry lists (what module/gat.py's op-by-op path and oracle.GATConvRef do), forward and the
+    gradients with respect to ft, el and er; attention dropout off."""
+    from bns_gcn_b200.graph import GatAttention
+    dev = torch.device("cuda:0")
+    g, n_in, n_u, u, v, gen = _gat_case(H, Fo, 100 + H + Fo, with_halo)
+    ft = torch.randn(n_u, H * Fo, generator=gen)
+    el = torch.randn(n_u, H, generator=gen)
+    er = torch.randn(n_in, H, generator=gen)
+    d = torch.randn(n_in, H * Fo, generator=gen)
+    # reference (f64 on the CPU)
+    ftr, elr, err = (t.double().clone().requires_grad_(True) for t in (ft, el, er))
+    e = torch.nn.functional.leaky_relu(elr[u] + err[v], 0.2)
+    m = torch.full((n_in, H), float("-inf"), dtype=torch.float64).scatter_reduce(0, v.unsqueeze(1).expand(-1, H), e.detach(), "amax")
+    ex = torch.exp(e - m[v])
+    den = torch.zeros(n_in, H, dtype=torch.float64).index_add(0, v, ex)
+    a = ex / den[v]
+    ref = torch.zeros(n_in, H, Fo, dtype=torch.float64).index_add(0, v, a.unsqueeze(-1) * ftr.view(-1, H, Fo)[u]).reshape(n_in, H * Fo)
+    (ref * d.double()).sum().backward()
+    ftg, elg, erg = (t.to(dev).requires_grad_(True) for t in (ft, el, er))
+    out = GatAttention.apply(ftg, elg, erg, g, H, Fo, 0.2, 0.0, 1)
+    (out * d.to(dev)).sum().backward()
+    assert _relerr(out.detach().cpu(), ref.detach().float()) < 2e-5
+    assert _relerr(ftg.grad.cpu(), ftr.grad.float()) < 2e-5
+    assert _relerr(elg.grad.cpu(), elr.grad.float()) < 5e-5
+    assert _relerr(erg.grad.cpu(), err.grad.float()) < 5e-5
+    # rows without any entry produce zeros
+    deg = torch.bincount(v, minlength=n_in)
+    assert torch.all(out.detach().cpu()[deg == 0] == 0)
+
+
+def test_fused_gat_attention_dropout_is_consistent_between_forward_and_backward(built):
+    """With attention dropout the layer is still linear in ft for fixed scores: <rst(ft), d> == <ft, d_ft(d)> holds only
+    if the backward regenerates exactly the forward's Philox mask; the keep rate is 1 - p; a new offset gives a new mask."""
+    from bns_gcn_b200 import ops
+    from bns_gcn_b200.graph import GatAttention
+    dev = torch.device("cuda:0")
+    H, Fo, p = 2, 32, 0.4
+    g, n_in, n_u, u, v, gen = _gat_case(H, Fo, 7, True)
+    ft = torch.randn(n_u, H * Fo, generator=gen).to(dev).requires_grad_(True)
+    el = torch.randn(n_u, H, generator=gen).to(dev)
+    er = torch.randn(n_in, H, generator=gen).to(dev)
+    d = torch.randn(n_in, H * Fo, generator=gen).to(dev)
+    ops.RNG.update(seed=5, offset=11, offset_dev=None)
+    out = GatAttention.apply(ft, el, er, g, H, Fo, 0.2, p, 3)
+    out.backward(d)
+    lhs, rhs = (out.detach() * d).sum().item(), (ft.detach() * ft.grad).sum().item()
+    assert abs(lhs - rhs) <= 1e-4 * max(abs(lhs), 1.0), (lhs, rhs)
+    out2 = GatAttention.apply(ft.detach(), el, er, g, H, Fo, 0.2, p, 3)
+    assert torch.equal(out2, out.detach())
+    ops.RNG.update(offset=12)
+    assert not torch.equal(GatAttention.apply(ft.detach(), el, er, g, H, Fo, 0.2, p, 3), out.detach())
+    # keep rate: compare the total attention mass of every row (sum of a' over its entries ~ 1) via ft = ones
+    ones = torch.ones(n_u, H * Fo, device=dev)
+    mass = GatAttention.apply(ones, el, er, g, H, Fo, 0.2, p, 3)[:, ::Fo]           # [n_in, H]: sum of a'_uv per head
+    deg = torch.bincount(v, minlength=n_in).to(dev)
+    big = deg >= 8
+    assert abs(mass[big].mean().item() - 1.0) < 0.1
+    ops.RNG.update(seed=0, offset=0, offset_dev=None)
