@@ -20,7 +20,8 @@ from . import dense
 
 # the attention (u_add_v, leaky_relu, edge_softmax, attn_drop, u_mul_e + sum of DGL's GATConv) as kernels
 # (graph.GatAttention); False / per-head widths that are not multiples of 4: the op-by-op torch path below
-FUSED_ATTENTION = True
+import os as _os
+FUSED_ATTENTION = _os.environ.get("BNS_GAT_FUSED", "1") != "0"
 
 
 class GATConv(nn.Module):
