@@ -303,15 +303,18 @@ def _aggregate(g: PartitionGraph, x_u: torch.Tensor, rs: torch.Tensor, ready) ->
     return y
 
 
-def _aggregate_t(g: PartitionGraph, dys: torch.Tensor, n_u: int, cs_in=None, cs_halo=None) -> torch.Tensor:
+def _aggregate_t(g: PartitionGraph, dys: torch.Tensor, n_u: int, cs_in=None, cs_halo=None, after_halo=None) -> torch.Tensor:
     """``cs * (A^T dys)`` over the epoch's graph: ``[n_u, F]`` (inner rows, then the sampled halo rows); ``cs``: GCN's
-    per-source scale (1/sqrt(out_deg)), applied as the row scale of the transposed products."""
+    per-source scale (1/sqrt(out_deg)), applied as the row scale of the transposed products.  The halo rows come first;
+    ``after_halo(du)`` is called as soon as they are final (the gradient return trip starts there)."""
     du = torch.empty(n_u, dys.shape[1], dtype=torch.float32, device=dys.device)
     if n_u > g.n_in:
         tail = du[g.n_in:]
         tail.zero_()
         if g.a_out_t is not None:
             ops.spmm(g.a_out_t, dys, tail, row_scale=cs_halo, row_map=g.slot)
+    if after_halo is not None:
+        after_halo(du)
     ops.spmm_auto(g.a_in_t, dys, du[:g.n_in], row_scale=cs_in)
     return du
 
@@ -327,17 +330,28 @@ class SageConvFn(torch.autograd.Function):
     arena and returns d h_u ``[n_u, in_features]``."""
 
     @staticmethod
-    def forward(ctx, h_u, w1, b1, w2, b2, g: PartitionGraph, rs, ready, arena: ParamArena, narrow_first: bool):
+    def forward(ctx, h_u, w1, b1, w2, b2, g: PartitionGraph, rs, ready, arena: ParamArena, narrow_first: bool,
+                exchange=None):
+        """``exchange = (Buffer, layer)`` when ``h_u`` came out of ``Buffer.update``: the backward then hands the halo
+        rows of its gradient to ``Buffer.begin_backward`` as soon as they are final."""
+        ctx.exchange = exchange
         n_in = g.n_in
         h_u = h_u.contiguous()
         W1, W2 = arena.padded(w1), arena.padded(w2)
         h_in = h_u[:n_in]
         if narrow_first:
-            if ready is not None:               # the transform reads every row of h_u, halo rows included
+            # transform, then aggregate; the local rows go first -- their GEMM and the inner-edge pass need nothing from
+            # the peers and hide the exchange -- the halo rows after the exchange's event
+            n_u = h_u.shape[0]
+            t = gather_friendly(n_u, W2.shape[0], h_u.device)                   # [n_u, out_p]
+            dense.tc_mm_tn(h_in, W2, out=t[:n_in])
+            out = dense.tc_mm_tn(h_in, W1, arena.bias_sum(b1, b2))              # linear1(h) + b1 + b2 ...
+            ops.spmm_auto(g.a_in, t[:n_in], out, row_scale=rs, accumulate=True)  # ... + (A_in t) / deg
+            if ready is not None:
                 torch.cuda.current_stream(h_u.device).wait_event(ready)
-            t = dense.tc_mm_tn(h_u, W2, out=gather_friendly(h_u.shape[0], W2.shape[0], h_u.device))   # [n_u, out_p]
-            ah = _aggregate(g, t, rs, None)                                     # [n_in, out_p]
-            out = dense.tc_mm_tn(h_in, W1, arena.bias_sum(b1, b2), addend=ah)   # linear1(h) + b1 + b2 + ah
+            if g.a_out is not None and n_u > n_in:
+                dense.tc_mm_tn(h_u[n_in:], W2, out=t[n_in:])
+                halo_aggregate(g, t[n_in:], out, rs, None)                      # ... + (A_out t_halo) / deg
             ctx.save_for_backward(h_u)
         else:
             ah = _aggregate(g, h_u, rs, ready)                                  # [n_in, in]
@@ -355,83 +369,33 @@ class SageConvFn(torch.autograd.Function):
         n_in = g.n_in
         dout = dout.contiguous()
         dense.colsum(dout, out=a.grad_padded(b1), out2=a.grad_padded(b2))
+        begin = None
+        if ctx.exchange is not None:
+            buf, layer = ctx.exchange
+            begin = lambda du_: buf.begin_backward(layer, du_)      # noqa: E731
         if ctx.narrow:
             (h_u,) = ctx.saved_tensors
             n_u = h_u.shape[0]
-            dense.tc_mm_nt(dout, h_u[:n_in], out=a.grad_padded(w1))
             dys = scale_rows(dout, rs, out=gather_friendly(n_in, dout.shape[1], dout.device))
             dt = _aggregate_t(g, dys, n_u)                                      # [n_u, out_p]
+            du = torch.empty(n_u, h_u.shape[1], dtype=torch.float32, device=dout.device)
+            if n_u > n_in:                                                      # halo rows first: they travel ...
+                dense.tc_mm_tn(dt[n_in:], a.transposed(w2), out=du[n_in:])
+            if begin is not None:
+                begin(du)
+            dense.tc_mm_tn(dt[:n_in], a.transposed(w2), out=du[:n_in])          # ... while the local rows are computed
+            dense.tc_mm_nt(dout, h_u[:n_in], out=a.grad_padded(w1))
             dense.tc_mm_nt(dt, h_u, out=a.grad_padded(w2))
-            du = dense.tc_mm_tn(dt, a.transposed(w2))                           # [n_u, in]
         else:
             h_u, ah = ctx.saved_tensors
             n_u = h_u.shape[0]
+            dys = dense.tc_mm_tn(dout, a.transposed(w2), row_scale=rs)          # (dout W2) / deg
+            du = _aggregate_t(g, dys, n_u, after_halo=begin)
             dense.tc_mm_nt(dout, h_u[:n_in], out=a.grad_padded(w1))
             dense.tc_mm_nt(dout, ah, out=a.grad_padded(w2))
-            dys = dense.tc_mm_tn(dout, a.transposed(w2), row_scale=rs)          # (dout W2) / deg
-            du = _aggregate_t(g, dys, n_u)
         inner = du[:n_in]
         dense.tc_mm_tn(dout, a.transposed(w1), addend=inner, out=inner)         # += dout W1, in place
-        return du, None, None, None, None, None, None, None, None, None
-
-
-class GcnConvFn(torch.autograd.Function):
-    """GCNLayer.forward, training branch (module/layer.py:32-38):
-
-        out = linear( (A (h_u / out_norm_u)) / in_norm )
-
-    with the same aggregate-after-transform rewrite as ``SageConvFn`` where the layer narrows.  ``rs = 1/in_norm``
-    (``[n_in]``), ``cs_u = 1/out_norm`` over the STATIC ``[inner | halo]`` numbering; the halo part rides in the epoch's
-    compaction as per-entry weights (``PartitionGraph.halo_col_scale``)."""
-
-    @staticmethod
-    def forward(ctx, h_u, w, b, g: PartitionGraph, rs, cs_u, ready, arena: ParamArena, narrow_first: bool):
-        n_in = g.n_in
-        h_u = h_u.contiguous()
-        W, bp = arena.padded(w), arena.padded(b)
-        cs_in, cs_halo = cs_u[:n_in], cs_u[n_in:]
-        has_halo = g.a_out is not None and h_u.shape[0] > n_in
-        if narrow_first:
-            if ready is not None:
-                torch.cuda.current_stream(h_u.device).wait_event(ready)
-            t = dense.tc_mm_tn(h_u, W, out=gather_friendly(h_u.shape[0], W.shape[0], h_u.device))     # [n_u, out_p]
-            ts = scale_rows(t[:n_in], cs_in, out=gather_friendly(n_in, W.shape[0], h_u.device))
-            s = ops.spmm_auto(g.a_in, ts)                                                             # raw sums
-            if has_halo:
-                halo_aggregate(g, t[n_in:], s, None, cs_halo)
-            out = scale_rows(s, rs, bias=bp)                                                          # / in_norm + b
-            ctx.save_for_backward(h_u)
-        else:
-            y = ops.spmm_auto(g.a_in, scale_rows(h_u[:n_in], cs_in), row_scale=rs)
-            if ready is not None:
-                torch.cuda.current_stream(h_u.device).wait_event(ready)
-            if has_halo:
-                halo_aggregate(g, h_u[n_in:], y, rs, cs_halo)
-            out = dense.tc_mm_tn(y, W, bp)
-            ctx.save_for_backward(y)
-        ctx.n_u = h_u.shape[0]
-        ctx.g, ctx.rs, ctx.cs, ctx.arena, ctx.narrow, ctx.params = g, rs, (cs_in, cs_halo), arena, narrow_first, (w, b)
-        return out
-
-    @staticmethod
-    def backward(ctx, dout):
-        g, rs, a = ctx.g, ctx.rs, ctx.arena
-        cs_in, cs_halo = ctx.cs
-        w, b = ctx.params
-        dout = dout.contiguous()
-        dense.colsum(dout, out=a.grad_padded(b))
-        if ctx.narrow:
-            (h_u,) = ctx.saved_tensors
-            dys = scale_rows(dout, rs, out=gather_friendly(g.n_in, dout.shape[1], dout.device))
-            dt = _aggregate_t(g, dys, ctx.n_u, cs_in, cs_halo)                  # [n_u, out_p]
-            dense.tc_mm_nt(dt, h_u, out=a.grad_padded(w))
-            du = dense.tc_mm_tn(dt, a.transposed(w))                            # [n_u, in]
-        else:
-            (y,) = ctx.saved_tensors
-            dense.tc_mm_nt(dout, y, out=a.grad_padded(w))
-            dys = dense.tc_mm_tn(dout, a.transposed(w), row_scale=rs)           # (dout W) / in_norm
-            du = _aggregate_t(g, dys, ctx.n_u, cs_in, cs_halo)
-        return du, None, None, None, None, None, None, None, None
+        return du, None, None, None, None, None, None, None, None, None, None
 
 
 def sage_layer_eligible(layer, feat: torch.Tensor) -> bool:

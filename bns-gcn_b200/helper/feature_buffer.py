@@ -309,6 +309,7 @@ class Buffer(object):
         res = _BoundaryExchange.apply(feat, self, layer, overlap)
         if overlap:
             res._bns_ready = self._last_ready
+        res._bns_exchange = (self, layer)          # lets a fused consumer start the gradient return trip early
         return res
 
     def _forward(self, layer, feat, overlap):
@@ -377,17 +378,22 @@ class Buffer(object):
         return h_u
 
     # ---- backward (the grad hook) -------------------------------------------------------------------
-    def _backward(self, layer, grad):
+    def begin_backward(self, layer, grad):
+        """Start the gradient return trip of ``layer`` as soon as the HALO rows ``grad[n_in:]`` are final: the rows go to
+        their owners on the comm stream while the caller still computes ``grad[:n_in]`` (fused.SageConvFn.backward calls
+        this between its two transposed aggregations).  ``_backward`` then only waits and scatter-adds."""
+        if self._size == 1:
+            return
+        self._begun = (layer, grad.data_ptr(), self._exchange_backward(layer, grad))
+
+    def _exchange_backward(self, layer, grad):
+        """Enqueue send + receive of the halo gradient rows; returns ``(done event, recv list or None)``."""
         F = grad.shape[1]
-        if not grad.is_contiguous():
-            grad = grad.contiguous()
-        trace = getattr(self, "trace", None)          # tests only: {name: tensor} of the gradients around the exchange
-        if trace is not None:
-            trace[f"grad_u{layer}"] = grad.detach().clone()
         main, cs = torch.cuda.current_stream(self._device), self._comm_stream
         start, done = torch.cuda.Event(), torch.cuda.Event()
         start.record(main)
         cs.wait_event(start)
+        recv = None
         with torch.cuda.stream(cs):
             with self._timer_ctx(f'backward_{layer}', cs):
                 if self._backend == 'nccl':
@@ -428,6 +434,21 @@ class Buffer(object):
             done.record(cs)
         if not self.graph_mode:
             grad.record_stream(cs)
+        return done, recv
+
+    def _backward(self, layer, grad):
+        F = grad.shape[1]
+        if not grad.is_contiguous():
+            grad = grad.contiguous()
+        trace = getattr(self, "trace", None)          # tests only: {name: tensor} of the gradients around the exchange
+        if trace is not None:
+            trace[f"grad_u{layer}"] = grad.detach().clone()
+        main = torch.cuda.current_stream(self._device)
+        begun, self._begun = getattr(self, "_begun", None), None
+        if begun is not None and begun[0] == layer and begun[1] == grad.data_ptr():
+            done, recv = begun[2]                     # the producer already sent the halo rows (begin_backward)
+        else:
+            done, recv = self._exchange_backward(layer, grad)
         main.wait_event(done)
         inner = grad[:self._num_in]
         if self._backend == 'nccl' or self._maps is None:

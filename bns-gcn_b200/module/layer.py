@@ -132,7 +132,7 @@ class GraphSAGELayer(nn.Module):
             narrow = AGGREGATE_AFTER_TRANSFORM and out_f < in_f
             out = _f.SageConvFn.apply(feat, self.linear1.weight, self.linear1.bias, self.linear2.weight,
                                       self.linear2.bias, graph, graph.recip(in_norm), getattr(feat, '_bns_ready', None),
-                                      arena, narrow)
+                                      arena, narrow, getattr(feat, '_bns_exchange', None))
             holder.value = out                  # [n_in, ceil4(out_features)]
             return out if out.shape[1] == out_f else out[:, :out_f]
         if self.training:
