@@ -398,6 +398,67 @@ class SageConvFn(torch.autograd.Function):
         return du, None, None, None, None, None, None, None, None, None, None
 
 
+class GcnConvFn(torch.autograd.Function):
+    """GCNLayer.forward, training branch (module/layer.py:32-38):
+
+        out = linear( (A (h_u / out_norm_u)) / in_norm )
+
+    with the same aggregate-after-transform rewrite as ``SageConvFn`` where the layer narrows.  ``rs = 1/in_norm``
+    (``[n_in]``), ``cs_u = 1/out_norm`` over the STATIC ``[inner | halo]`` numbering; the halo part rides in the epoch's
+    compaction as per-entry weights (``PartitionGraph.halo_col_scale``)."""
+
+    @staticmethod
+    def forward(ctx, h_u, w, b, g: PartitionGraph, rs, cs_u, ready, arena: ParamArena, narrow_first: bool):
+        n_in = g.n_in
+        h_u = h_u.contiguous()
+        W, bp = arena.padded(w), arena.padded(b)
+        cs_in, cs_halo = cs_u[:n_in], cs_u[n_in:]
+        has_halo = g.a_out is not None and h_u.shape[0] > n_in
+        if narrow_first:
+            t = gather_friendly(h_u.shape[0], W.shape[0], h_u.device)                                 # [n_u, out_p]
+            dense.tc_mm_tn(h_u[:n_in], W, out=t[:n_in])                                               # local rows first
+            ts = scale_rows(t[:n_in], cs_in, out=gather_friendly(n_in, W.shape[0], h_u.device))
+            s = ops.spmm_auto(g.a_in, ts)                                                             # raw sums
+            if ready is not None:
+                torch.cuda.current_stream(h_u.device).wait_event(ready)
+            if has_halo:
+                dense.tc_mm_tn(h_u[n_in:], W, out=t[n_in:])
+                halo_aggregate(g, t[n_in:], s, None, cs_halo)
+            out = scale_rows(s, rs, bias=bp)                                                          # / in_norm + b
+            ctx.save_for_backward(h_u)
+        else:
+            y = ops.spmm_auto(g.a_in, scale_rows(h_u[:n_in], cs_in), row_scale=rs)
+            if ready is not None:
+                torch.cuda.current_stream(h_u.device).wait_event(ready)
+            if has_halo:
+                halo_aggregate(g, h_u[n_in:], y, rs, cs_halo)
+            out = dense.tc_mm_tn(y, W, bp)
+            ctx.save_for_backward(y)
+        ctx.n_u = h_u.shape[0]
+        ctx.g, ctx.rs, ctx.cs, ctx.arena, ctx.narrow, ctx.params = g, rs, (cs_in, cs_halo), arena, narrow_first, (w, b)
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        g, rs, a = ctx.g, ctx.rs, ctx.arena
+        cs_in, cs_halo = ctx.cs
+        w, b = ctx.params
+        dout = dout.contiguous()
+        dense.colsum(dout, out=a.grad_padded(b))
+        if ctx.narrow:
+            (h_u,) = ctx.saved_tensors
+            dys = scale_rows(dout, rs, out=gather_friendly(g.n_in, dout.shape[1], dout.device))
+            dt = _aggregate_t(g, dys, ctx.n_u, cs_in, cs_halo)                  # [n_u, out_p]
+            dense.tc_mm_nt(dt, h_u, out=a.grad_padded(w))
+            du = dense.tc_mm_tn(dt, a.transposed(w))                            # [n_u, in]
+        else:
+            (y,) = ctx.saved_tensors
+            dense.tc_mm_nt(dout, y, out=a.grad_padded(w))
+            dys = dense.tc_mm_tn(dout, a.transposed(w), row_scale=rs)           # (dout W) / in_norm
+            du = _aggregate_t(g, dys, ctx.n_u, cs_in, cs_halo)
+        return du, None, None, None, None, None, None, None, None
+
+
 def sage_layer_eligible(layer, feat: torch.Tensor) -> bool:
     """Shapes the tcgen05 kernels take on every GEMM of the fused layer."""
     lin = layer.linear if layer.use_pp else layer.linear1
