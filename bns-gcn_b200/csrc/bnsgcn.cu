@@ -2,7 +2,7 @@
 //
 // Hot kernels (all HBM/L2-bound f32 gather / scatter work; no tensor-core shaped math here):
 //   spmm_kernel        K1/K1b/K2  nnz-balanced CSR row-sum, one warp per chunk, 16 B/lane gathers
-//                      (rows longer than one chunk: partial sums, combined in chunk order by the last chunk to arrive)
+//   spmm_fixup_kernel  deterministic combine of rows longer than one chunk
 //   gather / scatter   K3/K5      boundary pack and gradient scatter-add
 //   philox_key / take  K6         counter-based exactly-k sampling (with cub radix sort)
 //   p2p_put_rows       K3+C1      pack straight into the peer's receive slab over NVLink + flag
@@ -90,7 +90,6 @@ struct bns_graph {
     int64_t *chunk_start = nullptr; // [n_chunks]
     int32_t *chunk_part = nullptr;  // [n_chunks]  partial-sum slot, -1 when the row is a single chunk
     int32_t *row_chunk = nullptr;   // [n_rows+1]  first chunk of each row (row r owns chunks row_chunk[r] .. row_chunk[r+1])
-    int32_t *chunk_split = nullptr; // [n_chunks]  index of the row in split_row / split_part, -1 when it is a single chunk
     int32_t *split_row = nullptr;   // [n_split]
     int32_t *split_part = nullptr;  // [n_split+1] first partial slot of each split row
     int32_t *perm = nullptr;        // transposes only: [nnz] entry k of this graph is entry perm[k] of its source
@@ -117,8 +116,7 @@ __global__ void fill_chunks_kernel(const int64_t *__restrict__ indptr, int64_t n
                                    const int32_t *__restrict__ chunk_off, const int32_t *__restrict__ part_off,
                                    const int32_t *__restrict__ split_off, int32_t *__restrict__ chunk_row,
                                    int64_t *__restrict__ chunk_start, int32_t *__restrict__ chunk_part,
-                                   int32_t *__restrict__ chunk_split, int32_t *__restrict__ split_row,
-                                   int32_t *__restrict__ split_part) {
+                                   int32_t *__restrict__ split_row, int32_t *__restrict__ split_part) {
     int64_t r = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
     if (r >= n_rows) return;
     int32_t c0 = chunk_off[r], c1 = chunk_off[r + 1];
@@ -129,7 +127,6 @@ __global__ void fill_chunks_kernel(const int64_t *__restrict__ indptr, int64_t n
         chunk_row[c] = (int32_t)r;
         chunk_start[c] = s + (int64_t)(c - c0) * chunk;
         chunk_part[c] = split ? p0 + (c - c0) : -1;
-        chunk_split[c] = split ? split_off[r] : -1;
     }
     if (split) {
         int32_t i = split_off[r];
@@ -213,14 +210,12 @@ int build_chunks(bns_graph *g, cudaStream_t st) {
     BNS_CUDA(cudaMalloc(&g->chunk_row, (g->n_chunks + 1) * sizeof(int32_t)));
     BNS_CUDA(cudaMalloc(&g->chunk_start, (g->n_chunks + 1) * sizeof(int64_t)));
     BNS_CUDA(cudaMalloc(&g->chunk_part, (g->n_chunks + 1) * sizeof(int32_t)));
-    BNS_CUDA(cudaMalloc(&g->chunk_split, (g->n_chunks + 1) * sizeof(int32_t)));
     BNS_CUDA(cudaMalloc(&g->split_row, (g->n_split + 1) * sizeof(int32_t)));
     BNS_CUDA(cudaMalloc(&g->split_part, (g->n_split + 2) * sizeof(int32_t)));
     if (n > 0) {
         fill_chunks_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(g->indptr, n, g->chunk_nnz, chunk_off, part_off,
                                                                        split_off, g->chunk_row, g->chunk_start,
-                                                                       g->chunk_part, g->chunk_split, g->split_row,
-                                                                       g->split_part);
+                                                                       g->chunk_part, g->split_row, g->split_part);
     }
     set_last_kernel<<<1, 32, 0, st>>>(g->split_part, g->n_split, (int32_t)g->n_parts);
     BNS_CUDA(cudaGetLastError());
@@ -256,7 +251,7 @@ extern "C" int bns_device_info(char *name, size_t name_len, int *sms, int64_t *l
 extern "C" int bns_graph_destroy(bns_graph_t *g) {
     if (!g) return BNS_OK;
     cudaFree(g->indptr); cudaFree(g->indices); cudaFree(g->chunk_row); cudaFree(g->chunk_start);
-    cudaFree(g->chunk_part); cudaFree(g->chunk_split); cudaFree(g->split_row); cudaFree(g->split_part); cudaFree(g->perm);
+    cudaFree(g->chunk_part); cudaFree(g->row_chunk); cudaFree(g->split_row); cudaFree(g->split_part); cudaFree(g->perm);
     delete g;
     return BNS_OK;
 }
@@ -394,9 +389,7 @@ struct SpmmArgs {
     const int32_t *chunk_row;
     const int64_t *chunk_start;
     const int32_t *chunk_part;
-    const int32_t *chunk_split;
     const int32_t *chunk_cnt;      // compact mode (bns_graph_compact_cols): live entries of each chunk, NULL otherwise
-    unsigned int *split_cnt;       // [n_tiles][n_split] arrival counters of the split rows (zero between launches)
     const int32_t *split_row;
     const int32_t *split_part;
     int64_t n_chunks, n_split;
@@ -426,7 +419,6 @@ template <> struct Vec<4> {
     __device__ __forceinline__ void zero() { v = make_float4(0.f, 0.f, 0.f, 0.f); }
     __device__ __forceinline__ void load_ro(const float *p) { v = __ldg(reinterpret_cast<const float4 *>(p)); }
     __device__ __forceinline__ void load(const float *p) { v = *reinterpret_cast<const float4 *>(p); }
-    __device__ __forceinline__ void load_cg(const float *p) { v = __ldcg(reinterpret_cast<const float4 *>(p)); }
     __device__ __forceinline__ void store(float *p) const { *reinterpret_cast<float4 *>(p) = v; }
     __device__ __forceinline__ void add(const Vec &o) { v.x += o.v.x; v.y += o.v.y; v.z += o.v.z; v.w += o.v.w; }
     __device__ __forceinline__ void fma(const Vec &o, float s) {
@@ -443,7 +435,6 @@ template <> struct Vec<1> {
     __device__ __forceinline__ void zero() { v = 0.f; }
     __device__ __forceinline__ void load_ro(const float *p) { v = __ldg(p); }
     __device__ __forceinline__ void load(const float *p) { v = *p; }
-    __device__ __forceinline__ void load_cg(const float *p) { v = __ldcg(p); }
     __device__ __forceinline__ void store(float *p) const { *p = v; }
     __device__ __forceinline__ void add(const Vec &o) { v += o.v; }
     __device__ __forceinline__ void fma(const Vec &o, float s) { v = fmaf(o.v, s, v); }
@@ -593,43 +584,12 @@ __global__ void __launch_bounds__(kThreads, (NV <= 1 ? 5 : 4)) spmm_kernel(SpmmA
             if (gi != 0) continue;
         }
         const int32_t part = a.chunk_part[c];
-        bool finish = true;
-        if (part >= 0) {
-            // The row spans several chunks: park the raw partial sum; the LAST chunk of the row to arrive (whichever
-            // warp that is) adds all of them in chunk order -- a fixed order, so the result does not depend on who was
-            // last -- and finishes the row like a single-chunk one.  (Round 1 ran a second kernel for this.)
-            constexpr unsigned kGroupMask = (G >= 32) ? 0xffffffffu : ((1u << G) - 1u);
+        if (part >= 0) {   // the row spans several chunks: park the raw partial sum, combined later
             float *wr = a.ws + (int64_t)part * a.ldws;
 #pragma unroll
             for (int t = 0; t < NV; ++t)
                 if (fok[t]) acc[t].store(wr + fcol[t]);
-            __threadfence();
-            __syncwarp(kGroupMask);            // every lane's slice is fenced before lane 0 announces the chunk
-            const int32_t si = a.chunk_split[c];
-            const int32_t p0 = a.split_part[si], p1 = a.split_part[si + 1];
-            unsigned int *cnt = a.split_cnt + (item / a.n_chunks) * a.n_split + si;
-            int last = 0;
-            if (gl == 0) last = (atomicAdd(cnt, 1u) == (unsigned)(p1 - p0 - 1)) ? 1 : 0;
-            last = __shfl_sync(kGroupMask, last, 0);
-            finish = last != 0;
-            if (finish) {
-                __threadfence();
-                if (gl == 0) *cnt = 0u;                      // re-armed for the next launch
-#pragma unroll
-                for (int t = 0; t < NV; ++t) acc[t].zero();
-                for (int32_t p = p0; p < p1; ++p) {
-                    const float *pr = a.ws + (int64_t)p * a.ldws;
-#pragma unroll
-                    for (int t = 0; t < NV; ++t)
-                        if (fok[t]) {
-                            Vec<W> v;
-                            v.load_cg(pr + fcol[t]);
-                            acc[t].add(v);
-                        }
-                }
-            }
-        }
-        if (finish) {
+        } else {
             const float rs = a.row_scale ? a.row_scale[row] : 1.f;
             float *yr = a.Y + (int64_t)orow * a.ldy;
 #pragma unroll
@@ -644,6 +604,44 @@ __global__ void __launch_bounds__(kThreads, (NV <= 1 ? 5 : 4)) spmm_kernel(SpmmA
                 acc[t].store(yr + fcol[t]);
             }
         }
+    }
+}
+
+// Rows longer than one chunk: add their partial sums in chunk order (deterministic), then finish
+// exactly like the single-chunk epilogue.
+template <int W, int NV, bool GUARD>
+__global__ void __launch_bounds__(kThreads) spmm_fixup_kernel(SpmmArgs a) {
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    const int f0 = blockIdx.y * (32 * W * NV);
+    const int64_t i = (int64_t)blockIdx.x * kWarps + w;
+    if (i >= a.n_split) return;
+    const int32_t row = a.split_row[i];
+    int32_t orow = row;
+    if (a.row_map) {
+        orow = a.row_map[row];
+        if (orow < 0) return;
+    }
+    const int32_t p0 = a.split_part[i], p1 = a.split_part[i + 1];
+    const float rs = a.row_scale ? a.row_scale[row] : 1.f;
+    float *yr = a.Y + (int64_t)orow * a.ldy;
+#pragma unroll
+    for (int t = 0; t < NV; ++t) {
+        const int fc = f0 + (lane + 32 * t) * W;
+        if (GUARD && fc >= a.F) continue;
+        Vec<W> acc;
+        acc.zero();
+        for (int32_t p = p0; p < p1; ++p) {
+            Vec<W> v;
+            v.load(a.ws + (int64_t)p * a.ldws + fc);
+            acc.add(v);
+        }
+        if (a.row_scale) acc.scale(rs);
+        if (a.accumulate) {
+            Vec<W> old;
+            old.load(yr + fc);
+            acc.add(old);
+        }
+        acc.store(yr + fc);
     }
 }
 
@@ -667,7 +665,17 @@ int launch_spmm(SpmmArgs a, cudaStream_t st) {
     int64_t cap = (int64_t)sm_count() * blocks_per_sm;
     unsigned gx = (unsigned)(want < cap ? (want > 0 ? want : 1) : cap);
     spmm_kernel<W, G, NV, MAP, CSCALE, GUARD><<<gx, kThreads, 0, st>>>(a);
-    ++g_launches;
+    g_launches += a.n_split > 0 ? 2 : 1;
+    if (a.n_split > 0) {
+        unsigned fx = (unsigned)((a.n_split + kWarps - 1) / kWarps);
+        if (W == 4) {
+            const int tiles = (a.F + 255) / 256;
+            spmm_fixup_kernel<4, 2, true><<<dim3(fx, tiles), kThreads, 0, st>>>(a);
+        } else {
+            const int tiles = (a.F + 255) / 256;
+            spmm_fixup_kernel<1, 8, true><<<dim3(fx, tiles), kThreads, 0, st>>>(a);
+        }
+    }
     return BNS_OK;
 }
 
@@ -688,10 +696,6 @@ int dispatch_flags(const SpmmArgs &a, cudaStream_t st) {
 }
 
 inline int64_t ws_ld(int64_t F) { return (F + 3) / 4 * 4; }
-// workspace layout: [n_parts x ws_ld(F)] partial sums, then (256-byte aligned) [ceil(F / 32) x n_split] arrival counters
-inline size_t ws_partial_bytes(const bns_graph *g, int64_t F) {
-    return ((size_t)g->n_parts * (size_t)ws_ld(F) * sizeof(float) + 255) / 256 * 256;
-}
 
 int64_t l2_bytes() {
     const int dev = current_device();
@@ -748,8 +752,8 @@ int spmm_dispatch(const SpmmArgs &a, int64_t x_rows, int32_t slab_hint, cudaStre
 }  // namespace
 
 extern "C" size_t bns_spmm_workspace_bytes(const bns_graph_t *g, int64_t F) {
-    if (!g || F <= 0 || g->n_split == 0) return 0;
-    return ws_partial_bytes(g, F) + (size_t)((F + 31) / 32) * (size_t)g->n_split * sizeof(unsigned int);
+    if (!g || F <= 0) return 0;
+    return (size_t)g->n_parts * (size_t)ws_ld(F) * sizeof(float);
 }
 
 extern "C" int bns_spmm_sum_f32(const bns_graph_t *g, const float *X, int64_t ldx, int64_t F, float *Y, int64_t ldy,
@@ -771,8 +775,6 @@ extern "C" int bns_spmm_sum_f32(const bns_graph_t *g, const float *X, int64_t ld
     SpmmArgs a;
     a.indptr = g->indptr; a.indices = g->indices;
     a.chunk_row = g->chunk_row; a.chunk_start = g->chunk_start; a.chunk_part = g->chunk_part; a.chunk_cnt = nullptr;
-    a.chunk_split = g->chunk_split;
-    a.split_cnt = need ? reinterpret_cast<unsigned int *>(reinterpret_cast<char *>(ws) + ws_partial_bytes(g, F)) : nullptr;
     a.split_row = g->split_row; a.split_part = g->split_part;
     a.n_chunks = g->n_chunks; a.n_split = g->n_split; a.chunk_nnz = g->chunk_nnz;
     a.X = X; a.ldx = ldx; a.Y = Y; a.ldy = ldy; a.F = (int32_t)F;
@@ -802,8 +804,6 @@ extern "C" int bns_spmm_compact_f32(const bns_graph_t *g, const int32_t *cidx, c
     SpmmArgs a;
     a.indptr = g->indptr; a.indices = cidx;
     a.chunk_row = g->chunk_row; a.chunk_start = g->chunk_start; a.chunk_part = g->chunk_part; a.chunk_cnt = chunk_cnt;
-    a.chunk_split = g->chunk_split;
-    a.split_cnt = need ? reinterpret_cast<unsigned int *>(reinterpret_cast<char *>(ws) + ws_partial_bytes(g, F)) : nullptr;
     a.split_row = g->split_row; a.split_part = g->split_part;
     a.n_chunks = g->n_chunks; a.n_split = g->n_split; a.chunk_nnz = g->chunk_nnz;
     a.X = X; a.ldx = ldx; a.Y = Y; a.ldy = ldy; a.F = (int32_t)F;

@@ -108,7 +108,7 @@ class DeviceGraph:
             return None
         ws = self._ws.get(F)
         if ws is None or ws.numel() < need:
-            ws = torch.zeros(need, dtype=torch.uint8, device=self.device)      # zeroed once: the arrival counters
+            ws = torch.empty(need, dtype=torch.uint8, device=self.device)
             self._ws[F] = ws
         return ws
 

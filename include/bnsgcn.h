@@ -90,9 +90,7 @@ int bns_graph_copy_csr(const bns_graph_t *g, int64_t *indptr_out, int32_t *indic
  *   X  [*, F] with leading dimension ldx (floats); Y [*, F] with ldy.
  * The 16-byte vector path needs F % 4 == 0, ldx % 4 == 0, ldy % 4 == 0 and 16-byte aligned X, Y;
  * anything else takes the scalar path (same results).
- * ws: scratch of at least bns_spmm_workspace_bytes(g, F) bytes (0 when no row is split), ZEROED ONCE by the caller
- *     before its first use (it holds the arrival counters of the rows that span several chunks; each launch leaves
- *     them at zero again).  One workspace per graph and stream: launches that share it must be stream-ordered.
+ * ws: scratch of at least bns_spmm_workspace_bytes(g, F) bytes (0 when no row is split).
  * L2 blocking: the feature dimension is processed in column slabs (256/128/64/32 floats) picked so that
  * x_rows * slab * 4 bytes stays resident in L2 (override: slab_hint, or env BNS_SPMM_SLAB).
  * ----------------------------------------------------------------------------------------------*/
