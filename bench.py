@@ -117,8 +117,17 @@ def make_args(n_parts: int, backend: str, extra: dict):
     return ns
 
 
+SCALE = 1.0          # --scale: shrinks the per-rank generated shapes (papers100m) in nodes and edges alike
+
+
 def build_partition(shape: str, n_parts: int, rank: int, device):
-    from bns_gcn_b200.data import make_graph, partition_graph
+    from bns_gcn_b200.data import SHAPES, make_graph, make_local_partition, partition_graph
+    if shape == "papers100m":
+        # never built as one graph: every rank generates its own piece on its GPU (data.make_local_partition)
+        part = make_local_partition(shape, rank, n_parts, seed=0, device=device, scale=SCALE)
+        stats = {"n_nodes": int(part.gpb.ranges[-1]), "n_edges": part.graph.num_edges() * n_parts,
+                 "n_feat": SHAPES[shape]["n_feat"]}
+        return part, stats
     fg = make_graph(shape, seed=0, device=device)
     stats = {"n_nodes": fg.n_nodes, "n_edges": fg.n_edges, "n_feat": fg.n_feat}
     part = partition_graph(fg, n_parts, WORKLOAD["partition"], seed=0, ranks=[rank], device=device)[0]
@@ -647,12 +656,15 @@ def main():
     ap.add_argument("--rate", type=float, default=None)
     ap.add_argument("--dropout", type=float, default=None)
     ap.add_argument("--no-probe", action="store_true", help="skip the parity probe")
+    ap.add_argument("--scale", type=float, default=1.0, help="papers100m only: fraction of the 111 M nodes / 1.6 B edges")
     ap.add_argument("--cpu-worker", default="", help=argparse.SUPPRESS)      # internal: one gloo process of the CPU arm
     ap.add_argument("--cpu-rank", type=int, default=0, help=argparse.SUPPRESS)
     a = ap.parse_args()
     if a.cpu_worker:
         cpu_worker(a)
         return
+    global SCALE
+    SCALE = a.scale
     for k, v in (("model", a.model), ("n_layers", a.n_layers), ("n_hidden", a.n_hidden), ("sampling_rate", a.rate),
                  ("dropout", a.dropout), ("shape", a.shape)):
         if v is not None:

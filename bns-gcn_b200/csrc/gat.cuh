@@ -79,6 +79,12 @@ __global__ void __launch_bounds__(kThreads) gat_fwd_kernel(GatArgs a, int64_t nn
     const int64_t warps_total = (int64_t)gridDim.x * kWarps;
     const uint64_t offset = a.offset + (a.offset_dev ? *a.offset_dev : 0ull);
     const int H = a.H, F = a.H * a.Fo;
+    int hd[NV];                                   // head that owns each float4 column group of this lane
+#pragma unroll
+    for (int t = 0; t < NV; ++t) {
+        const int c = (lane + 32 * t) * 4;
+        hd[t] = c < F ? c / a.Fo : 0;
+    }
     for (int64_t v = (int64_t)blockIdx.x * kWarps + w; v < a.g.n_rows; v += warps_total) {
         float erv[kGatMaxHeads], m[kGatMaxHeads], l[kGatMaxHeads];
 #pragma unroll
@@ -87,39 +93,60 @@ __global__ void __launch_bounds__(kThreads) gat_fwd_kernel(GatArgs a, int64_t nn
             m[h] = -INFINITY;
             l[h] = 0.f;
         }
-        // pass 1: the row maximum of the scores, per head
+        // walk 1: per-lane online (max, sum of exp) of the scores, then one cross-lane combine per head
         BNS_GAT_FOR_EACH_ENTRY({
             (void)pos; (void)halo;
 _Pragma("unroll")
             for (int h = 0; h < kGatMaxHeads; ++h)
-                if (h < H) m[h] = fmaxf(m[h], leaky(a.el[(int64_t)u * H + h] + erv[h], a.slope));
+                if (h < H) {
+                    const float sc = leaky(a.el[(int64_t)u * H + h] + erv[h], a.slope);
+                    if (sc > m[h]) { l[h] = l[h] * expf(m[h] - sc) + 1.f; m[h] = sc; }
+                    else l[h] += expf(sc - m[h]);
+                }
         })
 #pragma unroll
-        for (int h = 0; h < kGatMaxHeads; ++h)
+        for (int h = 0; h < kGatMaxHeads; ++h) {
+            float mt = m[h];
 #pragma unroll
-            for (int o = 16; o > 0; o >>= 1) m[h] = fmaxf(m[h], __shfl_xor_sync(0xffffffffu, m[h], o));
-        // pass 2: the normaliser
-        BNS_GAT_FOR_EACH_ENTRY({
-            (void)pos; (void)halo;
-_Pragma("unroll")
-            for (int h = 0; h < kGatMaxHeads; ++h)
-                if (h < H) l[h] += expf(leaky(a.el[(int64_t)u * H + h] + erv[h], a.slope) - m[h]);
-        })
-#pragma unroll
-        for (int h = 0; h < kGatMaxHeads; ++h) l[h] = warp_sum(l[h]);
-        // pass 3: probabilities (stored), dropout, weighted accumulation -- 32 entries at a time through shared memory
+            for (int o = 16; o > 0; o >>= 1) mt = fmaxf(mt, __shfl_xor_sync(0xffffffffu, mt, o));
+            l[h] = warp_sum(m[h] == -INFINITY ? 0.f : l[h] * expf(m[h] - mt));
+            m[h] = mt;
+        }
+        // walk 2: probabilities (stored), dropout, weighted accumulation -- 32 entries at a time through shared memory
         float4 acc[NV];
 #pragma unroll
         for (int t = 0; t < NV; ++t) acc[t] = make_float4(0.f, 0.f, 0.f, 0.f);
+        constexpr int U = NV <= 2 ? 4 : (NV == 4 ? 2 : 1);        // entries whose row gathers are in flight together
         auto consume = [&](int cnt) {
             __syncwarp();
-            for (int jj = 0; jj < cnt; ++jj) {
+            int jj = 0;
+            for (; jj + U <= cnt; jj += U) {
+                float4 x[U][NV];
+#pragma unroll
+                for (int q = 0; q < U; ++q) {
+                    const float *fr = a.ft + (int64_t)s_u[w][jj + q] * a.ldft;
+#pragma unroll
+                    for (int t = 0; t < NV; ++t) {
+                        const int c = (lane + 32 * t) * 4;
+                        x[q][t] = c < F ? __ldg(reinterpret_cast<const float4 *>(fr + c)) : make_float4(0.f, 0.f, 0.f, 0.f);
+                    }
+                }
+#pragma unroll
+                for (int q = 0; q < U; ++q)
+#pragma unroll
+                    for (int t = 0; t < NV; ++t) {
+                        const float wt = s_w[w][jj + q][hd[t]];
+                        acc[t].x = fmaf(x[q][t].x, wt, acc[t].x); acc[t].y = fmaf(x[q][t].y, wt, acc[t].y);
+                        acc[t].z = fmaf(x[q][t].z, wt, acc[t].z); acc[t].w = fmaf(x[q][t].w, wt, acc[t].w);
+                    }
+            }
+            for (; jj < cnt; ++jj) {
                 const float *fr = a.ft + (int64_t)s_u[w][jj] * a.ldft;
 #pragma unroll
                 for (int t = 0; t < NV; ++t) {
                     const int c = (lane + 32 * t) * 4;
                     if (c < F) {
-                        const float wt = s_w[w][jj][c / a.Fo];
+                        const float wt = s_w[w][jj][hd[t]];
                         const float4 x = __ldg(reinterpret_cast<const float4 *>(fr + c));
                         acc[t].x = fmaf(x.x, wt, acc[t].x); acc[t].y = fmaf(x.y, wt, acc[t].y);
                         acc[t].z = fmaf(x.z, wt, acc[t].z); acc[t].w = fmaf(x.w, wt, acc[t].w);
@@ -181,6 +208,12 @@ __global__ void __launch_bounds__(kThreads) gat_bwd_kernel(GatArgs a, int64_t nn
     const int64_t warps_total = (int64_t)gridDim.x * kWarps;
     const uint64_t offset = a.offset + (a.offset_dev ? *a.offset_dev : 0ull);
     const int H = a.H, F = a.H * a.Fo;
+    int hd[NV];
+#pragma unroll
+    for (int t = 0; t < NV; ++t) {
+        const int c = (lane + 32 * t) * 4;
+        hd[t] = c < F ? c / a.Fo : 0;
+    }
     for (int64_t v = (int64_t)blockIdx.x * kWarps + w; v < a.g.n_rows; v += warps_total) {
         float erv[kGatMaxHeads], rowdot[kGatMaxHeads], der[kGatMaxHeads];
 #pragma unroll
@@ -201,29 +234,38 @@ __global__ void __launch_bounds__(kThreads) gat_bwd_kernel(GatArgs a, int64_t nn
             float mine[kGatMaxHeads];
 #pragma unroll
             for (int h = 0; h < kGatMaxHeads; ++h) mine[h] = 0.f;
-            for (int jj = 0; jj < cnt; ++jj) {
-                const float *fr = a.ft + (int64_t)s_u[w][jj] * a.ldft;
-                float part[kGatMaxHeads];
+            constexpr int U = NV <= 2 ? 4 : (NV == 4 ? 2 : 1);
+            for (int j0 = 0; j0 < cnt; j0 += U) {
+                float4 x[U][NV];
 #pragma unroll
-                for (int h = 0; h < kGatMaxHeads; ++h) part[h] = 0.f;
+                for (int q = 0; q < U; ++q) {
+                    const int jj = j0 + q < cnt ? j0 + q : cnt - 1;           // (a repeated last row: its dot is discarded)
+                    const float *fr = a.ft + (int64_t)s_u[w][jj] * a.ldft;
 #pragma unroll
-                for (int t = 0; t < NV; ++t) {
-                    const int c = (lane + 32 * t) * 4;
-                    if (c < F) {
-                        const float4 x = __ldg(reinterpret_cast<const float4 *>(fr + c));
-                        const float d = (dv[t].x * x.x + dv[t].y * x.y) + (dv[t].z * x.z + dv[t].w * x.w);
-                        const int hh = c / a.Fo;
-#pragma unroll
-                        for (int h = 0; h < kGatMaxHeads; ++h)
-                            if (h == hh) part[h] += d;
+                    for (int t = 0; t < NV; ++t) {
+                        const int c = (lane + 32 * t) * 4;
+                        x[q][t] = c < F ? __ldg(reinterpret_cast<const float4 *>(fr + c)) : make_float4(0.f, 0.f, 0.f, 0.f);
                     }
                 }
 #pragma unroll
-                for (int h = 0; h < kGatMaxHeads; ++h)
-                    if (h < H) {
-                        const float tot = warp_sum(part[h]);
-                        if (lane == jj) mine[h] = tot;
+                for (int q = 0; q < U; ++q) {
+                    float part[kGatMaxHeads];
+#pragma unroll
+                    for (int h = 0; h < kGatMaxHeads; ++h) part[h] = 0.f;
+#pragma unroll
+                    for (int t = 0; t < NV; ++t) {
+                        const float d = (dv[t].x * x[q][t].x + dv[t].y * x[q][t].y) + (dv[t].z * x[q][t].z + dv[t].w * x[q][t].w);
+#pragma unroll
+                        for (int h = 0; h < kGatMaxHeads; ++h)
+                            if (h == hd[t]) part[h] += d;
                     }
+#pragma unroll
+                    for (int h = 0; h < kGatMaxHeads; ++h)
+                        if (h < H) {
+                            const float tot = warp_sum(part[h]);
+                            if (lane == j0 + q) mine[h] = tot;
+                        }
+                }
             }
             if (valid) {
                 const float *P = (halo ? a.P_out : a.P_in) + pos * H;

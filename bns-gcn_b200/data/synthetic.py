@@ -65,6 +65,10 @@ SHAPES = {
                           law="powerlaw"),
     # configs[3]: Yelp (multi-label)
     "yelp": dict(n=716_847, e=13_954_819, n_feat=300, n_class=100, train=0.75, multilabel=True, law="powerlaw"),
+    # configs[4]: ogbn-papers100M: 111,059,956 nodes, 1,615,685,872 edges, 128 feats, 172 classes.  Never built as one
+    # graph (57 GB of features): every rank generates ITS piece on its GPU, see make_local_partition
+    "papers100m": dict(n=111_059_956, e=1_615_685_872, n_feat=128, n_class=172, train=0.011, multilabel=False,
+                       law="powerlaw"),
     # small shapes used by tests / smoke
     "tiny": dict(n=600, e=6_000, n_feat=16, n_class=5, train=0.5, multilabel=False, law="powerlaw"),
     "tiny-ml": dict(n=500, e=5_000, n_feat=12, n_class=6, train=0.6, multilabel=True, law="powerlaw"),
@@ -175,3 +179,99 @@ def make_graph(name: str, seed: int = 0, device: Optional[torch.device] = None,
     val_mask[rest[: rest.numel() // 3]] = True
     test_mask = ~(train_mask | val_mask)
     return FullGraph(n, indptr, src, feat, label, train_mask, val_mask, test_mask, n_class)
+
+
+# ---- per-rank generation (graphs that do not fit one host) -------------------------------------------------------
+def _weights_on_device(n: int, avg_deg: float, device) -> torch.Tensor:
+    """``_endpoint_weights(n, "powerlaw", ...)`` computed on ``device`` (f64, sums to 1, descending in the index)."""
+    alpha = 2.0 / 3.0
+    i = torch.arange(1, n + 1, dtype=torch.float64, device=device)
+    lo, hi = 0.0, float(n)
+    for _ in range(40):
+        mid = 0.5 * (lo + hi)
+        w = (i + mid) ** (-alpha)
+        top = avg_deg * n * float(w[0] / w.sum())
+        lo, hi = (mid, hi) if top > 44.0 * avg_deg else (lo, mid)
+    w = (i + hi) ** (-alpha)
+    return w / w.sum()
+
+
+def make_local_partition(name: str, rank: int, world: int, seed: int = 0, device: Optional[torch.device] = None,
+                         scale: float = 1.0):
+    """Rank ``rank``'s partition of shape ``name`` under ``--partition-method random``, generated ON THE DEVICE without
+    ever building the full graph (helper/utils.py:37-140 loads, partitions and re-loads the whole dataset on one host;
+    the papers100M shape does not fit one).  Same contract as ``partition.extract_partition``.
+
+    Model: directed Chung-Lu in-edges.  Rank r owns the contiguous id range ``[N r / P, N (r+1) / P)``; node u's
+    expected degree is ``w[(A u + B) mod N]`` with A coprime to N -- ids are decorrelated from degrees, i.e. a contiguous
+    range is a uniformly random set of nodes (the random partition).  It draws ``E / P`` (destination in its range,
+    source anywhere) pairs, both ends proportional to w, removes duplicates, adds one self loop per node
+    (utils.py:68-69).  ``in_deg`` is exact (every in-edge of an inner node is local); ``out_deg`` is set to ``in_deg``
+    (the graph is symmetric in expectation; the true value would need a global count -- GraphSAGE does not use it).
+    ``scale`` shrinks node and edge counts together (same average degree)."""
+    from .partition import NID, GraphPartitionBook, LocalGraph, Partition
+    spec = dict(SHAPES[name])
+    if device is None:
+        device = torch.device("cuda") if torch.cuda.is_available() else torch.device("cpu")
+    n, e = max(int(spec["n"] * scale), world * 4), max(int(spec["e"] * scale), world * 8)
+    ranges = torch.tensor([(n * i) // world for i in range(world + 1)], dtype=torch.int64)
+    start, end = int(ranges[rank]), int(ranges[rank + 1])
+    n_in = end - start
+    w = _weights_on_device(n, e / n, device)
+    cdf = torch.cumsum(w, 0)
+    cdf[-1] = 1.0
+    # the bijection id -> weight rank, and back
+    import math
+    A = 2_654_435_761 % n
+    while math.gcd(A, n) != 1:
+        A += 1
+    B, A_inv = (7919 * (seed + 1)) % n, pow(A, -1, n)
+    own = torch.arange(start, end, dtype=torch.int64, device=device)
+
+    def to_rank(u):                                   # (A u + B) mod n without overflowing int64: A, u < 2^31 for n < 2^31
+        return (u * A + B) % n
+
+    def from_rank(k):
+        return ((k - B) % n) * A_inv % n
+
+    gen = torch.Generator(device=device).manual_seed(seed * 1_000_003 + rank)
+    cdf_own = torch.cumsum(w[to_rank(own)], 0)
+    total_own = float(cdf_own[-1])
+    m = e // world
+    keys = [own * n + own]                            # the self loops, as (dst, src) keys
+    chunk = 32_000_000
+    done = 0
+    while done < m:
+        c = min(chunk, m - done)
+        r = torch.rand(2, c, generator=gen, dtype=torch.float64, device=device)
+        dst = own[torch.searchsorted(cdf_own, r[0] * total_own).clamp_(max=n_in - 1)]
+        src = from_rank(torch.searchsorted(cdf, r[1]).clamp_(max=n - 1))
+        keys.append(torch.unique(dst * n + src))
+        done += c
+    key = torch.unique(torch.cat(keys))               # sorted by (dst, src)
+    del keys
+    dst, src = key // n, key % n
+    del key
+    indptr = torch.zeros(n_in + 1, dtype=torch.int64, device=device)
+    indptr[1:] = torch.cumsum(torch.bincount(dst - start, minlength=n_in), 0)
+    inner = (src >= start) & (src < end)
+    halo = torch.unique(src[~inner])                  # sorted global ids
+    local = torch.where(inner, src - start, n_in + torch.searchsorted(halo, src))
+    gid = torch.cat([own, halo])
+    part_id = torch.searchsorted(ranges.to(device), gid, right=True) - 1
+    inner_node = torch.zeros(gid.numel(), dtype=torch.bool, device=device)
+    inner_node[:n_in] = True
+    in_deg = indptr[1:] - indptr[:-1]
+    fgen = torch.Generator(device=device).manual_seed(seed * 1_000_003 + 7 + rank)
+    n_feat, n_class = spec["n_feat"], spec["n_class"]
+    feat = torch.randn(n_in, n_feat, generator=fgen, dtype=torch.float32, device=device)
+    if spec["multilabel"]:
+        label = (torch.rand(n_in, n_class, generator=fgen, device=device) < 0.1).float()
+    else:
+        label = torch.randint(0, n_class, (n_in,), generator=fgen, dtype=torch.int64, device=device)
+    train_mask = torch.rand(n_in, generator=fgen, device=device) < spec["train"]
+    nd = {NID: gid, "part_id": part_id, "inner_node": inner_node, "feat": feat, "label": label, "in_deg": in_deg,
+          "out_deg": in_deg.clone(), "train_mask": train_mask}
+    meta = {"n_feat": n_feat, "n_class": n_class, "n_train": max(int(round(spec["train"] * n)), 1)}
+    return Partition(rank, world, LocalGraph(n_in, int(halo.numel()), indptr, local.contiguous()), nd,
+                     GraphPartitionBook(ranges.clone()), meta)

@@ -238,6 +238,50 @@ def precompute(part: PartitionGraph, graph, node_dict, boundary, model, gpb, pos
         raise Exception
 
 
+def precompute_streaming(part: PartitionGraph, node_dict, boundary, model):
+    """``precompute`` for GraphSAGE without ever materialising the full halo feature matrix (train.py:189, :202 fetch the
+    features of ALL boundary nodes at once: ~42 GB per rank on the papers100M shape under a random partition).  The halo
+    columns of ``a_out`` are grouped by owner, so the aggregation is a sum over peers: step i of the reference's ring
+    (helper/utils.py:204-206) receives the rows of ONE peer, multiplies them with that peer's column block of ``a_out``
+    (accumulating), and frees both.  Peak extra memory: one peer's rows + one column block."""
+    rank, size = _rank_size()
+    if model != 'graphsage':
+        raise NotImplementedError("precompute_streaming: GraphSAGE only (GCN needs the out-degrees too, GAT keeps the rows)")
+    feat = node_dict['feat']
+    n_in, n_feat = feat.shape
+    pad = (-n_feat) % 4
+    x_in = F.pad(feat, (0, pad)) if pad else feat
+    c = ctx.comm()
+    with torch.no_grad():
+        acc = ops.spmm_auto(part.a_in, x_in)                                     # raw sums over the inner edges
+        if size > 1 and part.a_out is not None and part.a_out.nnz:
+            counts = _halo_counts(node_dict)
+            first = [0] * size                                                   # first halo column of each owner
+            tot = 0
+            for j in range(size):
+                first[j] = tot
+                tot += 0 if j == rank else counts[j]
+            ip, ix = part.a_out.csr()
+            rows = torch.repeat_interleave(torch.arange(n_in, device=feat.device), ip[1:] - ip[:-1])
+            for i in range(1, size):
+                right, left = (rank + i) % size, (rank - i + size) % size
+                send = [None] * size
+                recv = [None] * size
+                send[right] = x_in[boundary[right]]
+                recv[left] = torch.empty(counts[left], x_in.shape[1], dtype=torch.float32, device=feat.device)
+                c.alltoall(send, recv, tag=TransferTag.FEAT * 1000 + i)
+                m = (ix >= first[left]) & (ix < first[left] + counts[left])
+                ipb = torch.zeros(n_in + 1, dtype=torch.int64, device=feat.device)
+                ipb[1:] = torch.cumsum(torch.bincount(rows[m], minlength=n_in), 0)
+                blk = ops.DeviceGraph.from_csr(ipb, (ix[m] - first[left]).to(torch.int32), counts[left])
+                ops.spmm(blk, recv[left], acc, accumulate=True)
+                torch.cuda.current_stream(feat.device).synchronize()             # the block and the rows die here
+                del blk, recv, send, m, ipb
+        from . import fused
+        mean = fused.scale_rows(acc, 1.0 / node_dict['in_deg'].float())
+    return torch.cat([feat, mean[:, :n_feat]], dim=1)
+
+
 def create_model(layer_size, args):
     """train.py:214-222."""
     if args.model == 'gcn':
@@ -353,7 +397,14 @@ def setup(graph: LocalGraph, node_dict, gpb, args, device=None) -> TrainState:
         ctx.buffer._get().set_maps(maps, n_slot, pos)
     out_deg_all = collect_out_degree(node_dict, boundary)                   # train.py:350
     if args.use_pp:
-        node_dict['feat'] = precompute(part, graph, node_dict, boundary, args.model, gpb, pos, out_deg_all)
+        halo_bytes = graph.n_halo * node_dict['feat'].shape[1] * 4
+        stream = getattr(args, 'streaming_precompute', None)
+        if stream is None:                  # automatic: when all the halo rows together would not fit comfortably
+            stream = args.model == 'graphsage' and halo_bytes > (16 << 30)
+        if stream and args.model == 'graphsage':
+            node_dict['feat'] = precompute_streaming(part, node_dict, boundary, args.model)
+        else:
+            node_dict['feat'] = precompute(part, graph, node_dict, boundary, args.model, gpb, pos, out_deg_all)
     if getattr(args, 'multilabel', False) or args.dataset == 'yelp':
         loss_fcn = torch.nn.BCEWithLogitsLoss(reduction='sum')              # train.py:358-361
     else:

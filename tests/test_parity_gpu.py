@@ -317,3 +317,30 @@ def test_run_with_eval_writes_checkpoints_and_results(built, tmp_path, monkeypat
     load_checkpoint(model, checkpoint_path(args, 3))          # the last periodic checkpoint is the final weights
     sd = torch.load(checkpoint_path(args, 3))
     assert list(sd.keys()) == [k for k, _ in model.named_parameters()]
+
+
+def test_streaming_precompute_equals_the_materialised_one(built):
+    """train.precompute_streaming (one peer's halo rows at a time) == train.precompute (all halo rows at once,
+    train.py:170-211), 3 ranks, and the locally generated partitions of data.make_local_partition train to parity with
+    the oracle like the ones cut from a full graph."""
+    import argparse
+    from tests.harness import make_args, run_oracle, run_product, _compare
+    from bns_gcn_b200.data import make_local_partition
+    P = 3
+    parts = [make_local_partition("papers100m", r, P, seed=1, device=torch.device("cpu"), scale=3e-5) for r in range(P)]
+    for p in parts:                               # a small feature width keeps the oracle quick
+        p.node_dict["feat"] = p.node_dict["feat"][:, :24].contiguous()
+        p.meta["n_feat"] = 24
+    outs = {}
+    for stream in (False, True):
+        args = make_args(dataset="papers100m", model="graphsage", sampling_rate=0.5, n_hidden=16, n_partitions=P,
+                         streaming_precompute=stream)
+        outs[stream] = run_product(parts, args, "cuda:0", 2)
+    for r in range(P):
+        a, b = outs[True][r]["feat0"], outs[False][r]["feat0"]
+        assert ((a - b).norm() / b.norm()).item() < 1e-6
+    sel = [[outs[True][r]["selected"][e] for r in range(P)] for e in range(2)]
+    args = make_args(dataset="papers100m", model="graphsage", sampling_rate=0.5, n_hidden=16, n_partitions=P)
+    orc = run_oracle(parts, args, 2, sel)
+    worst, detail = _compare(outs[True], orc, P)
+    assert worst < TOL, {k: v for k, v in detail.items() if v >= TOL}
