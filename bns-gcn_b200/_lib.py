@@ -101,8 +101,17 @@ SIGNATURES = {
     "bns_gat_colsum_f32": (c_int, [c_void_p, c_void_p, c_int32, c_void_p, c_int64, c_void_p, c_void_p]),
     "bns_spmm_weighted_f32": (c_int, [c_void_p, c_void_p, c_int64, c_int64, c_void_p, c_int64, c_void_p, c_int64, c_int,
                                       c_void_p, c_int64, c_int, c_void_p, c_size_t, c_void_p]),
-    "bns_spmm_compact_f32": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int64, c_void_p, c_int64,
-                                     c_void_p, c_int64, c_int32, c_int, c_void_p, c_size_t, c_void_p]),
+    "bns_spmm_compact_f32": (c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_void_p, c_void_p, c_int64, c_int64, c_void_p,
+                                     c_int64, c_void_p, c_int64, c_int32, c_int, c_void_p, c_size_t, c_void_p]),
+    "bns_gat_proj_f32": (c_int, [c_void_p, c_int64, c_int64, c_int32, c_int32, c_void_p, c_void_p, c_void_p]),
+    "bns_gat_proj_bwd_f32": (c_int, [c_void_p, c_int64, c_int64, c_int32, c_int32, c_void_p, c_void_p, c_void_p, c_int64,
+                                     c_int, c_void_p, c_void_p, c_size_t, c_void_p]),
+    "bns_gat_scores_f32": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int32, c_void_p, c_void_p,
+                                   c_float, c_float, c_uint64, c_uint64, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
+                                   c_void_p, c_void_p]),
+    "bns_gat_softmax_bwd_f32": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int32, c_void_p, c_void_p,
+                                        c_float, c_float, c_uint64, c_uint64, c_void_p, c_void_p, c_void_p, c_void_p,
+                                        c_void_p, c_void_p, c_void_p]),
     "bns_p2p_put_all_f32": (c_int, [c_void_p, POINTER(PutAll), c_int64, c_void_p, c_int64, c_int64, c_void_p, c_int32,
                                     c_int32, c_uint64, c_void_p, c_void_p]),
     "bns_p2p_put_ids_i64": (c_int, [c_void_p, c_int32, POINTER(c_int64), POINTER(c_int32), POINTER(c_uint64), c_void_p,

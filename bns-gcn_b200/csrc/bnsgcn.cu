@@ -790,9 +790,10 @@ extern "C" int bns_spmm_sum_f32(const bns_graph_t *g, const float *X, int64_t ld
 // chunk's live entries come first in its range, `chunk_cnt` says how many; `cw` = per-entry weights gathered at
 // compaction time (GCN's 1/sqrt(out_deg) of the halo sources) or NULL.  Work is proportional to the SAMPLE, not to the
 // halo (the col_map kernel walks every halo edge to use ~10 % of them).
-extern "C" int bns_spmm_compact_f32(const bns_graph_t *g, const int32_t *cidx, const float *cw, const int32_t *chunk_cnt,
-                                    const float *X, int64_t ldx, int64_t F, float *Y, int64_t ldy, const float *row_scale,
-                                    int64_t x_rows, int32_t slab_hint, int accumulate, void *ws, size_t ws_bytes, void *stream) {
+extern "C" int bns_spmm_compact_f32(const bns_graph_t *g, const int32_t *cidx, const float *cw, int64_t cw_ld,
+                                    const int32_t *chunk_cnt, const float *X, int64_t ldx, int64_t F, float *Y, int64_t ldy,
+                                    const float *row_scale, int64_t x_rows, int32_t slab_hint, int accumulate, void *ws,
+                                    size_t ws_bytes, void *stream) {
     BNS_REQUIRE(g && cidx && chunk_cnt, "bns_spmm_compact_f32: NULL argument");
     BNS_REQUIRE(F > 0 && F < (1 << 24), "bns_spmm_compact_f32: bad feature width %lld", (long long)F);
     if (g->n_rows == 0) return BNS_OK;
@@ -808,7 +809,7 @@ extern "C" int bns_spmm_compact_f32(const bns_graph_t *g, const int32_t *cidx, c
     a.n_chunks = g->n_chunks; a.n_split = g->n_split; a.chunk_nnz = g->chunk_nnz;
     a.X = X; a.ldx = ldx; a.Y = Y; a.ldy = ldy; a.F = (int32_t)F;
     a.row_scale = row_scale; a.col_scale = nullptr; a.edge_weight = cw; a.row_map = nullptr; a.col_map = nullptr;
-    a.edge_perm = nullptr; a.edge_ld = 1;
+    a.edge_perm = nullptr; a.edge_ld = cw_ld > 0 ? cw_ld : 1;
     a.n_direct = (int32_t)g->n_cols; a.accumulate = accumulate ? 1 : 0;
     a.ws = reinterpret_cast<float *>(ws); a.ldws = ws_ld(F);
     a.n_tiles = 1;
@@ -865,7 +866,7 @@ struct SddmmArgs {
 };
 
 // one warp per chunk; the lanes keep their slice of A[row] in registers and walk the entries like the SpMM does
-template <int NV>
+template <int NV, int U>
 __global__ void __launch_bounds__(kThreads) sddmm_dot_kernel(SddmmArgs a) {
     __shared__ int32_t s_col[kWarps][32];
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
@@ -896,22 +897,37 @@ __global__ void __launch_bounds__(kThreads) sddmm_dot_kernel(SddmmArgs a) {
             __syncwarp();
             const int cnt = (e - k0) < 32 ? (int)(e - k0) : 32;
             float mine = 0.f;
-            for (int j = 0; j < cnt; ++j) {
-                const int32_t cj = s_col[w][j];
-                float d = 0.f;
-                if (cj >= 0) {
-                    const float *br = a.B + (int64_t)cj * a.ldb;
+            // U gathered rows in flight per lane (the loads of one group are issued before any of its sums)
+            for (int j0 = 0; j0 < cnt; j0 += U) {
+                float4 b[U][NV];
+                int32_t cj[U];
+#pragma unroll
+                for (int q = 0; q < U; ++q) {
+                    cj[q] = (j0 + q < cnt) ? s_col[w][j0 + q] : -1;
 #pragma unroll
                     for (int t = 0; t < NV; ++t) {
                         const int f = (lane + 32 * t) * 4;
-                        if (f < a.F) {
-                            const float4 b = __ldg(reinterpret_cast<const float4 *>(br + f));
-                            d += (av[t].x * b.x + av[t].y * b.y) + (av[t].z * b.z + av[t].w * b.w);
-                        }
+                        b[q][t] = (cj[q] >= 0 && f < a.F)
+                                      ? __ldg(reinterpret_cast<const float4 *>(a.B + (int64_t)cj[q] * a.ldb + f))
+                                      : make_float4(0.f, 0.f, 0.f, 0.f);
                     }
                 }
-                d = warp_sum(d);
-                if (lane == j) mine = d;
+                float d[U];
+#pragma unroll
+                for (int q = 0; q < U; ++q) {
+                    d[q] = 0.f;
+#pragma unroll
+                    for (int t = 0; t < NV; ++t)
+                        d[q] += (av[t].x * b[q][t].x + av[t].y * b[q][t].y) + (av[t].z * b[q][t].z + av[t].w * b[q][t].w);
+                }
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) {
+#pragma unroll
+                    for (int q = 0; q < U; ++q) d[q] += __shfl_xor_sync(0xffffffffu, d[q], o);
+                }
+#pragma unroll
+                for (int q = 0; q < U; ++q)
+                    if (lane == j0 + q) mine = d[q];
             }
             if (k < e) a.out[k * a.ldo] = mine;
             __syncwarp();
@@ -940,10 +956,12 @@ extern "C" int bns_sddmm_dot_f32(const bns_graph_t *g, const float *A, int64_t l
     unsigned gx = (unsigned)(want < cap ? (want > 0 ? want : 1) : cap);
     cudaStream_t st = as_stream(stream);
     const int nv = (int)((F + 127) / 128);
-    if (nv <= 1) sddmm_dot_kernel<1><<<gx, kThreads, 0, st>>>(a);
-    else if (nv == 2) sddmm_dot_kernel<2><<<gx, kThreads, 0, st>>>(a);
-    else if (nv <= 4) sddmm_dot_kernel<4><<<gx, kThreads, 0, st>>>(a);
-    else sddmm_dot_kernel<8><<<gx, kThreads, 0, st>>>(a);
+    // gathered rows in flight per lane, measured on the Yelp shape (profiles/gat_r02.md): F = 256: 8 (3.2 ms) beats 4 (3.9 ms);
+    // F = 100: 4 (1.46 ms) beats 8 (1.76 ms)
+    if (nv <= 1) sddmm_dot_kernel<1, 4><<<gx, kThreads, 0, st>>>(a);
+    else if (nv == 2) sddmm_dot_kernel<2, 8><<<gx, kThreads, 0, st>>>(a);
+    else if (nv <= 4) sddmm_dot_kernel<4, 2><<<gx, kThreads, 0, st>>>(a);
+    else sddmm_dot_kernel<8, 1><<<gx, kThreads, 0, st>>>(a);
     ++g_launches;
     BNS_CUDA(cudaGetLastError());
     return BNS_OK;

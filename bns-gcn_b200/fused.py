@@ -234,6 +234,25 @@ def dropout(x: torch.Tensor, p: float, seed: int) -> torch.Tensor:
     return y
 
 
+class DropoutFn(torch.autograd.Function):
+    """``dropout_p`` as an autograd node on ``bns_dropout_f32``: the backward regenerates the Philox mask of the forward
+    (same seed, same epoch offset) instead of storing it."""
+
+    @staticmethod
+    def forward(ctx, x, p: float, seed: int):
+        ctx.p, ctx.seed = p, seed
+        ctx.rng = (ops.RNG["seed"], ops.RNG["offset"], ops.RNG["offset_dev"])
+        return dropout(x, p, seed)
+
+    @staticmethod
+    def backward(ctx, dy):
+        keep = ops.RNG["seed"], ops.RNG["offset"], ops.RNG["offset_dev"]
+        ops.RNG.update(seed=ctx.rng[0], offset=ctx.rng[1], offset_dev=ctx.rng[2])
+        dx = dropout(dy, ctx.p, ctx.seed)
+        ops.RNG.update(seed=keep[0], offset=keep[1], offset_dev=keep[2])
+        return dx, None, None
+
+
 def gather_friendly(rows: int, width: int, device) -> torch.Tensor:
     """An uninitialised ``[rows, width]`` f32 matrix whose row stride is a multiple of 64 bytes: a narrow row that the
     SpMM gathers (44 padded class scores = 176 bytes) then always spans the minimum number of 128-byte lines (2), where

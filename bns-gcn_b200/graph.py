@@ -12,6 +12,8 @@ from __future__ import annotations
 
 from typing import Dict, Optional
 
+import os
+
 import torch
 
 from . import ops
@@ -176,14 +178,69 @@ class WeightedAggregate(torch.autograd.Function):
         return d_ft, d_w_in, d_w_out, None
 
 
+_PROJ_WS = {}
+
+
+class GatProjection(torch.autograd.Function):
+    """``el = <ft_src, attn_l>``, ``er = <ft_dst, attn_r>`` per head (the two ``(feat * attn).sum(-1)`` of
+    ``dgl.nn.GATConv``) on ``bns_gat_proj_f32``; the backward (``bns_gat_proj_bwd_f32``) makes ``d ft = s (x) attn`` and
+    the deterministic ``d attn = sum_r s_r ft_r`` in one pass over ``ft`` each."""
+
+    @staticmethod
+    def forward(ctx, ft_src, ft_dst, attn_l, attn_r, H: int, Fo: int):
+        from ._lib import check, lib
+        ft_src, ft_dst = ft_src.contiguous(), ft_dst.contiguous()
+        al, ar = attn_l.reshape(-1).contiguous(), attn_r.reshape(-1).contiguous()
+        dev = ft_src.device
+        el = torch.empty(ft_src.shape[0], H, dtype=torch.float32, device=dev)
+        er = torch.empty(ft_dst.shape[0], H, dtype=torch.float32, device=dev)
+        st = torch.cuda.current_stream(dev).cuda_stream
+        with torch.cuda.device(dev):
+            check(lib.bns_gat_proj_f32(ft_src.data_ptr(), ft_src.stride(0), ft_src.shape[0], H, Fo, al.data_ptr(), el.data_ptr(),
+                                       st), "bns_gat_proj_f32")
+            check(lib.bns_gat_proj_f32(ft_dst.data_ptr(), ft_dst.stride(0), ft_dst.shape[0], H, Fo, ar.data_ptr(), er.data_ptr(),
+                                       st), "bns_gat_proj_f32")
+        ctx.save_for_backward(ft_src, ft_dst, al, ar)
+        ctx.cfg = (H, Fo, attn_l.shape)
+        return el, er
+
+    @staticmethod
+    def backward(ctx, d_el, d_er):
+        from ._lib import check, lib
+        ft_src, ft_dst, al, ar = ctx.saved_tensors
+        H, Fo, shape = ctx.cfg
+        dev = ft_src.device
+        st = torch.cuda.current_stream(dev).cuda_stream
+        key = (dev, H * Fo, st)
+        ws = _PROJ_WS.get(key)
+        if ws is None:
+            ws = _PROJ_WS[key] = torch.empty(lib.bns_colsum_workspace_bytes(H * Fo), dtype=torch.uint8, device=dev)
+        outs = []
+        with torch.cuda.device(dev):
+            for ft, a, s in ((ft_src, al, d_el), (ft_dst, ar, d_er)):
+                s = s.contiguous()
+                d_ft = torch.empty_like(ft)
+                d_a = torch.empty_like(a)
+                check(lib.bns_gat_proj_bwd_f32(ft.data_ptr(), ft.stride(0), ft.shape[0], H, Fo, a.data_ptr(), s.data_ptr(),
+                                               d_ft.data_ptr(), d_ft.stride(0), 0, d_a.data_ptr(), ws.data_ptr(), ws.numel(),
+                                               st), "bns_gat_proj_bwd_f32")
+                outs.append((d_ft, d_a.view(shape)))
+        return outs[0][0], outs[1][0], outs[0][1], outs[1][1], None, None
+
+
 class GatAttention(torch.autograd.Function):
-    """The attention of ``dgl.nn.GATConv`` for all heads (``bns_gat_forward_f32`` / ``bns_gat_backward_f32`` /
-    ``bns_gat_colsum_f32`` / ``bns_spmm_weighted_f32``):
+    """The attention of ``dgl.nn.GATConv`` for all heads:
 
         rst_v = sum_u attn_drop(edge_softmax(leaky_relu(el_u + er_v)))_uv * ft_u
 
     over the inner entries and this epoch's sampled halo entries (the partition graph's compaction with positions).
-    ``ft [n_u, H * Fo]``, ``el [n_u, H]``, ``er [n_in, H]`` -> ``[n_in, H * Fo]``; gradients for all three."""
+    ``ft [n_u, H * Fo]``, ``el [n_u, H]``, ``er [n_in, H]`` -> ``[n_in, H * Fo]``; gradients for all three.
+
+    Stages (include/bnsgcn.h): ``bns_gat_scores_f32`` (scalars: probabilities + dropped attention per entry) ->
+    ``bns_spmm_weighted_f32`` / ``bns_spmm_compact_f32`` per head; backward ``bns_sddmm_dot_f32`` ->
+    ``bns_gat_softmax_bwd_f32`` -> ``bns_gat_colsum_f32`` -> ``bns_spmm_weighted_f32`` on the transposes.  The one-launch
+    row walks ``bns_gat_forward_f32`` / ``bns_gat_backward_f32`` compute the same thing (``BNS_GAT_ROWWALK=1``; the
+    tests run both) but are a latency chain per row on low-degree graphs: profiles/gat_r02.md."""
 
     @staticmethod
     def forward(ctx, ft, el, er, g: PartitionGraph, H: int, Fo: int, slope: float, p: float, seed: int):
@@ -197,15 +254,36 @@ class GatAttention(torch.autograd.Function):
         p_in = torch.empty(max(g.a_in.nnz, 1), H, dtype=torch.float32, device=dev)
         p_out = torch.empty(max(g.a_out.nnz, 1), H, dtype=torch.float32, device=dev) if c is not None else None
         off, off_dev = ops.RNG["offset"], ops.RNG["offset_dev"]
-        args = (g.a_in._h, None if c is None else g.a_out._h, None if c is None else c.cidx.data_ptr(),
-                None if c is None else c.chunk_cnt.data_ptr(), None if c is None else c.cpos.data_ptr(), n_in,
-                ft.data_ptr(), ft.stride(0), H, Fo, el.data_ptr(), er.data_ptr(), float(slope), float(p),
-                seed & (2 ** 64 - 1), off & (2 ** 64 - 1), ops._ptr(off_dev))
-        with torch.cuda.device(dev):
-            check(lib.bns_gat_forward_f32(*args, rst.data_ptr(), rst.stride(0), p_in.data_ptr(), ops._ptr(p_out),
-                                          torch.cuda.current_stream(dev).cuda_stream), "bns_gat_forward_f32")
-        ctx.g, ctx.c, ctx.args, ctx.cfg = g, c, args, (H, Fo, float(p))
-        ctx.save_for_backward(ft, el, er, p_in, *(() if p_out is None else (p_out,)))
+        head = (g.a_in._h, None if c is None else g.a_out._h, None if c is None else c.cidx.data_ptr(),
+                None if c is None else c.chunk_cnt.data_ptr(), None if c is None else c.cpos.data_ptr(), n_in)
+        tail = (H, el.data_ptr(), er.data_ptr(), float(slope), float(p), seed & (2 ** 64 - 1), off & (2 ** 64 - 1),
+                ops._ptr(off_dev))
+        rowwalk = os.environ.get("BNS_GAT_ROWWALK", "0") == "1"
+        st = torch.cuda.current_stream(dev).cuda_stream
+        w_in = w_out = None
+        if rowwalk:
+            with torch.cuda.device(dev):
+                check(lib.bns_gat_forward_f32(*head, ft.data_ptr(), ft.stride(0), H, Fo, *tail[1:], rst.data_ptr(),
+                                              rst.stride(0), p_in.data_ptr(), ops._ptr(p_out), st), "bns_gat_forward_f32")
+        else:
+            if p > 0:
+                w_in = torch.empty_like(p_in)
+                w_out = torch.empty_like(p_out) if p_out is not None else None
+            wc = torch.empty_like(p_out) if p_out is not None else None          # halo attention, compacted positions
+            with torch.cuda.device(dev):
+                check(lib.bns_gat_scores_f32(*head, *tail, p_in.data_ptr(), ops._ptr(p_out), ops._ptr(w_in), ops._ptr(w_out),
+                                             ops._ptr(wc), st), "bns_gat_scores_f32")
+            for h in range(H):
+                cols = slice(h * Fo, (h + 1) * Fo)
+                ops.spmm_weighted(g.a_in, ft[:n_in, cols], rst[:, cols], p_in if w_in is None else w_in, h)
+                if c is not None:
+                    ops.spmm_compact(c, ft[n_in:, cols], rst[:, cols], accumulate=True, weights=wc, head=h)
+        ctx.g, ctx.c, ctx.head, ctx.tail, ctx.cfg, ctx.rowwalk = g, c, head, tail, (H, Fo, float(p)), rowwalk
+        saved = [ft, el, er, p_in] + ([p_out] if p_out is not None else [])
+        if w_in is not None:
+            saved += [w_in] + ([w_out] if w_out is not None else [])
+        ctx.n_w = 0 if w_in is None else (2 if w_out is not None else 1)
+        ctx.save_for_backward(*saved)
         return rst
 
     @staticmethod
@@ -214,26 +292,42 @@ class GatAttention(torch.autograd.Function):
         g, c = ctx.g, ctx.c
         H, Fo, p = ctx.cfg
         ft, el, er, p_in, *rest = ctx.saved_tensors
-        p_out = rest[0] if rest else None
+        p_out = rest.pop(0) if c is not None else None
         d_rst = d_rst.contiguous()
         dev, n_in, n_u = ft.device, g.n_in, ft.shape[0]
         de_in = torch.empty_like(p_in)
         de_out = torch.empty_like(p_out) if p_out is not None else None
-        a_in = torch.empty_like(p_in) if p > 0 else None
-        a_out = torch.empty_like(p_out) if (p > 0 and p_out is not None) else None
         d_er = torch.empty(n_in, H, dtype=torch.float32, device=dev)
         st = torch.cuda.current_stream(dev).cuda_stream
+        if ctx.rowwalk:
+            a_in = torch.empty_like(p_in) if p > 0 else None
+            a_out = torch.empty_like(p_out) if (p > 0 and p_out is not None) else None
+            with torch.cuda.device(dev):
+                check(lib.bns_gat_backward_f32(*ctx.head, ft.data_ptr(), ft.stride(0), H, Fo, *ctx.tail[1:], d_rst.data_ptr(),
+                                               d_rst.stride(0), p_in.data_ptr(), ops._ptr(p_out), de_in.data_ptr(),
+                                               ops._ptr(de_out), ops._ptr(a_in), ops._ptr(a_out), d_er.data_ptr(), st),
+                      "bns_gat_backward_f32")
+            w_in, w_out = (a_in, a_out) if p > 0 else (p_in, p_out)
+        else:
+            w_in, w_out = p_in, p_out
+            if ctx.n_w:
+                w_in = rest.pop(0)
+                w_out = rest.pop(0) if ctx.n_w == 2 else None
+            for h in range(H):                                 # d a'_uv = <d rst_v, ft_u> (0 for an unsampled halo node)
+                cols = slice(h * Fo, (h + 1) * Fo)
+                ops.sddmm_dot(g.a_in, d_rst[:, cols], ft[:n_in, cols], out=de_in[:, h])
+                if c is not None:
+                    ops.sddmm_dot(g.a_out, d_rst[:, cols], ft[n_in:, cols], col_map=g.slot, n_direct=0, out=de_out[:, h])
+            with torch.cuda.device(dev):
+                check(lib.bns_gat_softmax_bwd_f32(*ctx.head, *ctx.tail, p_in.data_ptr(), ops._ptr(p_out), de_in.data_ptr(),
+                                                  ops._ptr(de_out), d_er.data_ptr(), st), "bns_gat_softmax_bwd_f32")
         with torch.cuda.device(dev):
-            check(lib.bns_gat_backward_f32(*ctx.args, d_rst.data_ptr(), d_rst.stride(0), p_in.data_ptr(), ops._ptr(p_out),
-                                           de_in.data_ptr(), ops._ptr(de_out), ops._ptr(a_in), ops._ptr(a_out),
-                                           d_er.data_ptr(), st), "bns_gat_backward_f32")
             d_el = torch.empty(n_u, H, dtype=torch.float32, device=dev)
             check(lib.bns_gat_colsum_f32(g.a_in_t._h, de_in.data_ptr(), H, None, 0, d_el.data_ptr(), st),
                   "bns_gat_colsum_f32")
             if c is not None:
                 check(lib.bns_gat_colsum_f32(g.a_out_t._h, de_out.data_ptr(), H, g.slot.data_ptr(), n_in, d_el.data_ptr(),
                                              st), "bns_gat_colsum_f32")
-        w_in, w_out = (a_in, a_out) if p > 0 else (p_in, p_out)
         d_ft = torch.empty(n_u, H * Fo, dtype=torch.float32, device=dev)
         for h in range(H):
             cols = slice(h * Fo, (h + 1) * Fo)

@@ -6,15 +6,17 @@ call the reference makes -- ``layer(g, (h_src, h_dst))`` on the bipartite ``_U -
     ft = fc(feat_drop(h))            el = <ft_src, attn_l>      er = <ft_dst, attn_r>
     e_uv = leaky_relu(el_u + er_v)   a = attn_drop(edge_softmax(e))     rst_v = sum_u a_uv ft_u + bias
 
-The per-entry score / softmax algebra runs as torch ops on ``[nnz, heads]`` vectors over the STATIC entry lists of
-the partition graph (an unsampled halo entry gets e = -inf, i.e. weight 0); the F-wide work is libbnsgcn.so:
-weighted SpMM, its transpose, and the SDDMM-dot of the attention gradient (``graph.WeightedAggregate``)."""
+Everything after ``fc`` runs as kernels of libbnsgcn.so (``graph.GatProjection``, ``graph.GatAttention``; feature
+dropout on the Philox kernel).  The op-by-op fallback (``BNS_GAT_FUSED=0`` or a per-head width that is not a multiple
+of 4) writes the per-entry score / softmax algebra as torch ops on ``[nnz, heads]`` vectors over the STATIC entry lists
+of the partition graph (an unsampled halo entry gets e = -inf, i.e. weight 0) around the weighted SpMM, its transpose
+and the SDDMM-dot of the attention gradient (``graph.WeightedAggregate``)."""
 import torch
 import torch.nn.functional as F
 from torch import nn
 
-from .. import ops
-from ..graph import GatAttention, PartitionGraph, WeightedAggregate, gat_entries
+from .. import fused, ops
+from ..graph import GatAttention, GatProjection, PartitionGraph, WeightedAggregate, gat_entries
 from . import dense
 
 
@@ -57,20 +59,28 @@ class GATConv(nn.Module):
         ready = getattr(feat[0], '_bns_ready', None)
         if ready is not None:          # every row of h_src is read below: wait for the overlapped exchange
             torch.cuda.current_stream(feat[0].device).wait_event(ready)
-        h_src, h_dst = self.feat_drop(feat[0]), self.feat_drop(feat[1])
+        kernels = FUSED_ATTENTION and Fo % 4 == 0 and H <= 8 and H * Fo <= 1024 and \
+            (graph.a_out is None or (graph.compact is not None and graph.compact.cpos is not None))
+        salt = ops.RNG["seed"] + 15485863 * (1 + getattr(self, "_layer_index", 0))
+        pf = self.feat_drop.p if self.training else 0.0
+        if kernels and pf > 0 and fused.dropout_supported(feat[0]) and fused.dropout_supported(feat[1]):
+            # two independent masks, as DGL draws them (feat_drop is applied to the source and the destination rows)
+            h_src, h_dst = fused.DropoutFn.apply(feat[0], pf, salt + 1), fused.DropoutFn.apply(feat[1], pf, salt + 2)
+        else:
+            h_src, h_dst = self.feat_drop(feat[0]), self.feat_drop(feat[1])
         ft_src = dense.linear(h_src, self.fc.weight).view(-1, H, Fo)
         ft_dst = dense.linear(h_dst, self.fc.weight).view(-1, H, Fo)
+        if kernels:
+            # el / er, score -> edge softmax -> dropout -> weighted aggregation (and their backward) as kernels
+            ft2 = ft_src.reshape(-1, H * Fo)
+            el, er = GatProjection.apply(ft2, ft_dst.reshape(-1, H * Fo), self.attn_l, self.attn_r, H, Fo)
+            p = self.attn_drop.p if self.training else 0.0
+            rst = GatAttention.apply(ft2, el, er, graph, H, Fo, self.negative_slope, p, salt)
+            if self.bias is not None:
+                rst += self.bias                                    # in place: the attention saved nothing of it
+            return rst.view(-1, H, Fo)
         el = (ft_src * self.attn_l).sum(dim=-1)                     # [n_U, H]
         er = (ft_dst * self.attn_r).sum(dim=-1)                     # [n_in, H]
-        if FUSED_ATTENTION and Fo % 4 == 0 and H <= 8 and H * Fo <= 1024 and \
-                (graph.a_out is None or (graph.compact is not None and graph.compact.cpos is not None)):
-            # score -> edge softmax -> dropout -> weighted aggregation (and their backward) as kernels, all heads at once
-            p = self.attn_drop.p if self.training else 0.0
-            rst = GatAttention.apply(ft_src.reshape(-1, H * Fo), el, er, graph, H, Fo, self.negative_slope, p,
-                                     ops.RNG["seed"] + 15485863 * (1 + getattr(self, "_layer_index", 0))).view(-1, H, Fo)
-            if self.bias is not None:
-                rst = rst + self.bias.view(1, H, Fo)
-            return rst
         rin, cin, rout, cout = gat_entries(graph)
         e_in = F.leaky_relu(el[cin] + er[rin], self.negative_slope)                                  # [nnz_in, H]
         n_u = ft_src.shape[0]

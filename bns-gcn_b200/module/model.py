@@ -53,13 +53,13 @@ class GNNBase(nn.Module):
                 if nm is not None:
                     self.norm.append(nm)
 
-    def _between(self, i, h, may_fuse):
+    def _between(self, i, h, may_fuse, with_dropout=True):
         """norm -> activation after layer ``i``.  Returns ``(h, dropped)``: with ``may_fuse`` and LayerNorm + ReLU the
-        fused kernel also applies the NEXT layer's input dropout."""
+        fused kernel also applies the NEXT layer's input dropout (``with_dropout``; GAT drops inside its layers)."""
         nm = self.norm[i] if self.use_norm else None
         if (may_fuse and FUSE_NORM_ACT_DROPOUT and isinstance(nm, nn.LayerNorm) and self.activation is F.relu
                 and nm.elementwise_affine and ops.ln_relu_dropout_supported(h, h.shape[1])):
-            p = self.dropout.p if self.training else 0.0
+            p = self.dropout.p if (self.training and with_dropout) else 0.0
             slots = out = None
             if self._arena is not None and self.training:
                 slots = (self._arena.grad_padded(nm.weight), self._arena.grad_padded(nm.bias))
@@ -149,7 +149,8 @@ class GAT(GNNBase):
                     src, dst = h, h[0:g.num_nodes('_V')]                # :120-121: layer 0 holds the stored halo rows
                 else:
                     src, dst = ctx.buffer.update(i, h, overlap=True), h  # :117-118
-                h = layer(g, (src, dst)).mean(1)
+                h = layer(g, (src, dst))
+                h = h.view(h.shape[0], -1) if h.shape[1] == 1 else h.mean(1)   # the mean over one head is the head
             if i < self.n_layers - 1:
-                h, _ = self._between(i, h, False)
+                h, _ = self._between(i, h, h.is_cuda, with_dropout=False)
         return h

@@ -259,8 +259,10 @@ class CompactedCols:
 
 
 def spmm_compact(c: CompactedCols, x: torch.Tensor, out: torch.Tensor, *, row_scale: Optional[torch.Tensor] = None,
-                 accumulate: bool = False, slab: int = 0, live_nnz: Optional[int] = None) -> torch.Tensor:
-    """``bns_spmm_compact_f32``: the SpMM over the compacted (sampled) entries only."""
+                 accumulate: bool = False, slab: int = 0, live_nnz: Optional[int] = None,
+                 weights: Optional[torch.Tensor] = None, head: int = 0) -> torch.Tensor:
+    """``bns_spmm_compact_f32``: the SpMM over the compacted (sampled) entries only.  ``weights`` ``[nnz, heads]`` at
+    the COMPACTED positions (GAT's dropped attention, column ``head``) replaces the compaction's own per-entry weights."""
     g = c.g
     _req(x, torch.float32, "x")
     _req(out, torch.float32, "out")
@@ -273,7 +275,8 @@ def spmm_compact(c: CompactedCols, x: torch.Tensor, out: torch.Tensor, *, row_sc
         ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         ev0.record(torch.cuda.current_stream(x.device))
     with torch.cuda.device(x.device):
-        check(lib.bns_spmm_compact_f32(g._h, c.cidx.data_ptr(), _ptr(c.cw), c.chunk_cnt.data_ptr(), x.data_ptr(), x.stride(0),
+        cw_ptr, cw_ld = (_ptr(c.cw), 1) if weights is None else (weights.data_ptr() + 4 * head, weights.stride(0))
+        check(lib.bns_spmm_compact_f32(g._h, c.cidx.data_ptr(), cw_ptr, cw_ld, c.chunk_cnt.data_ptr(), x.data_ptr(), x.stride(0),
                                        F, out.data_ptr(), out.stride(0), _ptr(row_scale), x.shape[0], slab,
                                        1 if accumulate else 0, _ptr(ws), 0 if ws is None else ws.numel(), _stream_ptr()),
               "bns_spmm_compact_f32")

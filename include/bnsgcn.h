@@ -304,9 +304,11 @@ int bns_graph_compact_cols(const bns_graph_t *g, const int32_t *col_map, int64_t
                            int32_t *cpos /*device [nnz] or NULL: position of each live entry in the CSR (GAT keeps its
                                            per-entry attention at those positions)*/,
                            int32_t *chunk_cnt /*device [n_chunks]*/, void *stream);
-int bns_spmm_compact_f32(const bns_graph_t *g, const int32_t *cidx, const float *cw, const int32_t *chunk_cnt,
-                         const float *X, int64_t ldx, int64_t F, float *Y, int64_t ldy, const float *row_scale,
-                         int64_t x_rows, int32_t slab_hint, int accumulate, void *ws, size_t ws_bytes, void *stream);
+int bns_spmm_compact_f32(const bns_graph_t *g, const int32_t *cidx, const float *cw /*per compacted entry, or NULL*/,
+                         int64_t cw_ld /*stride of cw in floats (1; heads for GAT's [nnz, heads] attention)*/,
+                         const int32_t *chunk_cnt, const float *X, int64_t ldx, int64_t F, float *Y, int64_t ldy,
+                         const float *row_scale, int64_t x_rows, int32_t slab_hint, int accumulate, void *ws, size_t ws_bytes,
+                         void *stream);
 
 /* ------------------------------------------------------------------------------------------------
  * K10 fused: the attention of dgl.nn.GATConv (module/model.py:96-132; DGL 0.9 python/dgl/nn/pytorch/conv/gatconv.py):
@@ -333,6 +335,27 @@ int bns_gat_backward_f32(const bns_graph_t *a_in, const bns_graph_t *a_out, cons
                          int32_t out_feats, const float *el, const float *er, float negative_slope, float p_drop, uint64_t seed,
                          uint64_t offset, const uint64_t *offset_dev, const float *d_rst, int64_t ldd, const float *P_in,
                          const float *P_out, float *dE_in, float *dE_out, float *A_in, float *A_out, float *d_er, void *stream);
+/* The same algebra decomposed (what graph.GatAttention runs: each stage has thousands of independent gathers in flight,
+ * where one fused row walk is a latency chain per row): bns_gat_scores_f32 -- scalars only: probabilities P and dropped
+ * attention W at the original positions, W_out_compact at the compacted positions -- then bns_spmm_weighted_f32 /
+ * bns_spmm_compact_f32 per head; backward: bns_sddmm_dot_f32 into dE, bns_gat_softmax_bwd_f32 (dE: d a' -> d e in
+ * place, d er), bns_gat_colsum_f32, bns_spmm_weighted_f32 through the permutation. */
+int bns_gat_scores_f32(const bns_graph_t *a_in, const bns_graph_t *a_out, const int32_t *cidx, const int32_t *chunk_cnt,
+                       const int32_t *cpos, int64_t x_halo_base, int32_t heads, const float *el, const float *er,
+                       float negative_slope, float p_drop, uint64_t seed, uint64_t offset, const uint64_t *offset_dev,
+                       float *P_in, float *P_out, float *W_in /*NULL when p_drop == 0*/, float *W_out, float *W_out_compact,
+                       void *stream);
+int bns_gat_softmax_bwd_f32(const bns_graph_t *a_in, const bns_graph_t *a_out, const int32_t *cidx, const int32_t *chunk_cnt,
+                            const int32_t *cpos, int64_t x_halo_base, int32_t heads, const float *el, const float *er,
+                            float negative_slope, float p_drop, uint64_t seed, uint64_t offset, const uint64_t *offset_dev,
+                            const float *P_in, const float *P_out, float *dE_in, float *dE_out, float *d_er, void *stream);
+/* el / er of GATConv: out[r, h] = <X[r, h*Fo:(h+1)*Fo], attn[h, :]>, and its backward: dX[r, h, :] (+)= s[r, h] * attn[h, :],
+ * d_attn[h, :] = sum_r s[r, h] * X[r, h, :] (deterministic).  ws: bns_colsum_workspace_bytes(heads * Fo). */
+int bns_gat_proj_f32(const float *X, int64_t ldx, int64_t rows, int32_t heads, int32_t Fo, const float *attn, float *out,
+                     void *stream);
+int bns_gat_proj_bwd_f32(const float *X, int64_t ldx, int64_t rows, int32_t heads, int32_t Fo, const float *attn,
+                         const float *s, float *dX, int64_t lddx, int accumulate, float *d_attn, void *ws, size_t ws_bytes,
+                         void *stream);
 int bns_gat_colsum_f32(const bns_graph_t *gT, const float *dE, int32_t heads, const int32_t *row_map, int64_t out_base,
                        float *d_el, void *stream);
 int bns_spmm_weighted_f32(const bns_graph_t *g, const float *X, int64_t ldx, int64_t F, float *Y, int64_t ldy,

@@ -699,12 +699,14 @@ def _gat_case(H, Fo, seed, with_halo=True):
     return g, n_in, n_u, torch.cat(u), torch.cat(v), gen
 
 
-@pytest.mark.parametrize("H,Fo,with_halo", [(1, 64, True), (2, 8, True), (4, 16, False), (1, 256, True)])
-def test_fused_gat_attention_matches_the_per_entry_reference(built, H, Fo, with_halo):
+@pytest.mark.parametrize("rowwalk", ["0", "1"], ids=["stages", "row-walk"])
+@pytest.mark.parametrize("H,Fo,with_halo", [(1, 64, True), (2, 8, True), (4, 16, False), (1, 256, True), (1, 100, True)])
+def test_fused_gat_attention_matches_the_per_entry_reference(built, monkeypatch, H, Fo, with_halo, rowwalk):
     """graph.GatAttention == the u_add_v / leaky_relu / edge_softmax / u_mul_e+sum algebra of dgl.nn.GATConv written with
     torch ops on explicit entry lists (what module/gat.py's op-by-op path and oracle.GATConvRef do), forward and the
     gradients with respect to ft, el and er; attention dropout off."""
     from bns_gcn_b200.graph import GatAttention
+    monkeypatch.setenv("BNS_GAT_ROWWALK", rowwalk)
     dev = torch.device("cuda:0")
     g, n_in, n_u, u, v, gen = _gat_case(H, Fo, 100 + H + Fo, with_halo)
     ft = torch.randn(n_u, H * Fo, generator=gen)
@@ -732,11 +734,13 @@ def test_fused_gat_attention_matches_the_per_entry_reference(built, H, Fo, with_
     assert torch.all(out.detach().cpu()[deg == 0] == 0)
 
 
-def test_fused_gat_attention_dropout_is_consistent_between_forward_and_backward(built):
+@pytest.mark.parametrize("rowwalk", ["0", "1"], ids=["stages", "row-walk"])
+def test_fused_gat_attention_dropout_is_consistent_between_forward_and_backward(built, monkeypatch, rowwalk):
     """With attention dropout the layer is still linear in ft for fixed scores: <rst(ft), d> == <ft, d_ft(d)> holds only
     if the backward regenerates exactly the forward's Philox mask; the keep rate is 1 - p; a new offset gives a new mask."""
     from bns_gcn_b200 import ops
     from bns_gcn_b200.graph import GatAttention
+    monkeypatch.setenv("BNS_GAT_ROWWALK", rowwalk)
     dev = torch.device("cuda:0")
     H, Fo, p = 2, 32, 0.4
     g, n_in, n_u, u, v, gen = _gat_case(H, Fo, 7, True)
@@ -751,6 +755,11 @@ def test_fused_gat_attention_dropout_is_consistent_between_forward_and_backward(
     assert abs(lhs - rhs) <= 1e-4 * max(abs(lhs), 1.0), (lhs, rhs)
     out2 = GatAttention.apply(ft.detach(), el, er, g, H, Fo, 0.2, p, 3)
     assert torch.equal(out2, out.detach())
+    # the staged kernels and the one-launch row walk draw the SAME mask (Philox keyed by entry position and head)
+    monkeypatch.setenv("BNS_GAT_ROWWALK", "1" if rowwalk == "0" else "0")
+    other = GatAttention.apply(ft.detach().clone().requires_grad_(True), el, er, g, H, Fo, 0.2, p, 3)
+    assert _relerr(other.detach().cpu(), out.detach().cpu()) < 1e-5
+    monkeypatch.setenv("BNS_GAT_ROWWALK", rowwalk)
     ops.RNG.update(offset=12)
     assert not torch.equal(GatAttention.apply(ft.detach(), el, er, g, H, Fo, 0.2, p, 3), out.detach())
     # keep rate: compare the total attention mass of every row (sum of a' over its entries ~ 1) via ft = ones
@@ -760,3 +769,33 @@ def test_fused_gat_attention_dropout_is_consistent_between_forward_and_backward(
     big = deg >= 8
     assert abs(mass[big].mean().item() - 1.0) < 0.1
     ops.RNG.update(seed=0, offset=0, offset_dev=None)
+
+
+@pytest.mark.parametrize("H,Fo,n_src,n_dst", [(1, 256, 3001, 2000), (2, 8, 777, 700), (8, 128, 300, 300), (1, 100, 513, 1), (3, 4, 50, 0)])
+def test_gat_projection_matches_torch(built, H, Fo, n_src, n_dst):
+    """graph.GatProjection (el / er of GATConv and their backward) == (ft.view(n, H, Fo) * attn).sum(-1) under autograd."""
+    from bns_gcn_b200.graph import GatProjection
+    dev = torch.device("cuda:0")
+    gen = torch.Generator().manual_seed(H * 1000 + Fo)
+    fs, fd = torch.randn(n_src, H * Fo, generator=gen), torch.randn(n_dst, H * Fo, generator=gen)
+    al, ar = torch.randn(1, H, Fo, generator=gen), torch.randn(1, H, Fo, generator=gen)
+    g1, g2 = torch.randn(n_src, H, generator=gen), torch.randn(n_dst, H, generator=gen)
+    ref_in = [t.double().clone().requires_grad_(True) for t in (fs, fd, al, ar)]
+    rel = (ref_in[0].view(-1, H, Fo) * ref_in[2]).sum(-1)
+    rer = (ref_in[1].view(-1, H, Fo) * ref_in[3]).sum(-1)
+    ((rel * g1.double()).sum() + (rer * g2.double()).sum()).backward()
+    got_in = [t.to(dev).requires_grad_(True) for t in (fs, fd, al, ar)]
+    el, er = GatProjection.apply(*got_in, H, Fo)
+    ((el * g1.to(dev)).sum() + (er * g2.to(dev)).sum()).backward()
+    assert _relerr(el.detach().cpu(), rel.detach().float()) < 1e-5
+    if n_dst:
+        assert _relerr(er.detach().cpu(), rer.detach().float()) < 1e-5
+    for got, ref in zip(got_in, ref_in):
+        assert got.grad.shape == ref.grad.shape
+        if ref.grad.numel():
+            assert _relerr(got.grad.cpu(), ref.grad.float()) < 2e-5
+    # deterministic
+    got2 = [t.to(dev).requires_grad_(True) for t in (fs, fd, al, ar)]
+    e2, r2 = GatProjection.apply(*got2, H, Fo)
+    ((e2 * g1.to(dev)).sum() + (r2 * g2.to(dev)).sum()).backward()
+    assert torch.equal(got2[2].grad, got_in[2].grad) and torch.equal(got2[0].grad, got_in[0].grad)
