@@ -463,9 +463,12 @@ def inprocess_probe_loss(shape: str, world: int, dev) -> float:
     from bns_gcn_b200 import train
     from bns_gcn_b200.data import make_graph, partition_graph
     from bns_gcn_b200.helper.comm import run_threads
-    fg = make_graph(shape, seed=0, device=dev)
-    parts = partition_graph(fg, world, WORKLOAD["partition"], seed=0, device=dev)
-    del fg
+    if shape == "papers100m":
+        parts = [build_partition(shape, world, r, dev)[0] for r in range(world)]     # per-rank generator (never one graph)
+    else:
+        fg = make_graph(shape, seed=0, device=dev)
+        parts = partition_graph(fg, world, WORKLOAD["partition"], seed=0, device=dev)
+        del fg
 
     def fn(comm, r):
         p = parts[r]
@@ -647,6 +650,9 @@ def main():
     ap.add_argument("--mode", default="graph", choices=["graph", "eager"],
                     help="graph: the epoch is captured once into a CUDA graph and replayed (default); eager: launched op by op")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--watchdog", type=int, default=int(os.environ.get("BNS_BENCH_WATCHDOG", "0")),
+                    help="seconds after which every rank dumps the Python stacks of all its threads to stderr and exits "
+                         "(post-mortem of a hang on a box nobody can attach to); 0 = off")
     ap.add_argument("--strict", action="store_true", help="fail instead of falling back to eager when capture fails")
     ap.add_argument("--profile", default="", help="write a torch.profiler kernel table of 3 epochs (rank 0) to this file")
     # non-default workloads (the other BASELINE.json configs); the driver's contract run uses the defaults above
@@ -660,6 +666,9 @@ def main():
     ap.add_argument("--cpu-worker", default="", help=argparse.SUPPRESS)      # internal: one gloo process of the CPU arm
     ap.add_argument("--cpu-rank", type=int, default=0, help=argparse.SUPPRESS)
     a = ap.parse_args()
+    if a.watchdog > 0:
+        import faulthandler
+        faulthandler.dump_traceback_later(a.watchdog, exit=True)
     if a.cpu_worker:
         cpu_worker(a)
         return
