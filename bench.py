@@ -153,8 +153,6 @@ def run_ours(a):
             raise SystemExit(f"--gpus {a.gpus} needs torchrun (one rank per GPU); WORLD_SIZE is 1")
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
-    if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
-        os.environ["NCCL_DEBUG"] = "WARN"        # NCCL prints its version banner on STDOUT: keep that for the JSON line
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
     K, W = a.steps, max(a.warmup, 3)
@@ -442,7 +440,7 @@ def run_ours(a):
             probe["ok"] = bool(probe["rel_err"] < 1e-4)
     if probe is not None:
         out["parity_probe"] = probe
-    print(json.dumps(out), file=sys.__stdout__, flush=True)
+    emit(out)
     _leave(world)
 
 
@@ -585,9 +583,12 @@ def cpu_epochs_per_sec(shape: str, n_parts: int, steps: int, warmup: int, budget
             with open(os.path.join(d, "job.json"), "w") as f:
                 json.dump({"world": n_parts, "per_rank": per_rank, "steps": steps, "warmup": warmup, "budget_s": budget_s,
                            "probe": probe, "port": port, "workload": WORKLOAD}, f)
+            # the workers form their OWN gloo group: nothing of the launcher's rendezvous may leak into them (with
+            # TORCHELASTIC_USE_AGENT_STORE set, a tcp:// init makes every rank a store CLIENT and nobody serves)
             env = {k: v for k, v in os.environ.items()
-                   if k not in ("RANK", "LOCAL_RANK", "WORLD_SIZE", "MASTER_ADDR", "MASTER_PORT", "TORCHELASTIC_RUN_ID",
-                                "OMP_NUM_THREADS", "GROUP_RANK", "ROLE_RANK", "LOCAL_WORLD_SIZE")}
+                   if k not in ("RANK", "LOCAL_RANK", "WORLD_SIZE", "MASTER_ADDR", "MASTER_PORT", "OMP_NUM_THREADS",
+                                "GROUP_RANK", "ROLE_RANK", "LOCAL_WORLD_SIZE", "GROUP_WORLD_SIZE", "ROLE_WORLD_SIZE",
+                                "ROLE_NAME") and not k.startswith(("TORCHELASTIC_", "TORCH_NCCL_"))}
             env["OMP_NUM_THREADS"] = str(per_rank)
             env["CUDA_VISIBLE_DEVICES"] = ""             # the CPU arm never touches a GPU
             procs = [subprocess.Popen([sys.executable, os.path.abspath(__file__), "--cpu-worker", d, "--cpu-rank", str(r)],
@@ -635,7 +636,28 @@ def run_reference(a):
                               "same workload); steps_requested = --steps"},
            "cpu_baseline": res,
            "e2e": {"value": res["value"], "unit": "epochs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
-    print(json.dumps(out))
+    emit(out)
+
+
+_JSON_FD = None
+
+
+def protect_stdout() -> None:
+    """The contract is ONE JSON line on stdout.  C libraries write to file descriptor 1 behind Python's back (NCCL prints
+    its version banner there at NCCL_DEBUG=VERSION / WARN), so keep a private duplicate of the real stdout for `emit`
+    and point descriptor 1 at stderr for everything else -- in this process and every child it starts."""
+    global _JSON_FD
+    if _JSON_FD is None:
+        sys.stdout.flush()
+        _JSON_FD = os.dup(1)
+        os.dup2(2, 1)
+
+
+def emit(out: dict) -> None:
+    data = (json.dumps(out) + "\n").encode()
+    fd = 1 if _JSON_FD is None else _JSON_FD
+    while data:
+        data = data[os.write(fd, data):]
 
 
 def main():
@@ -672,6 +694,7 @@ def main():
     if a.cpu_worker:
         cpu_worker(a)
         return
+    protect_stdout()
     global SCALE
     SCALE = a.scale
     for k, v in (("model", a.model), ("n_layers", a.n_layers), ("n_hidden", a.n_hidden), ("sampling_rate", a.rate),

@@ -144,6 +144,60 @@ def test_exchange_metadata_gloo(tmp_path, world, use_store):
         assert r[me]["out_deg"].numel() == r[me]["nid"].numel()
 
 
+def _local_generator_worker(rank, world, port, out_dir):
+    os.environ["MASTER_ADDR"], os.environ["MASTER_PORT"] = "127.0.0.1", str(port)
+    sys.path.insert(0, ROOT)
+    import torch.distributed as dist
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    import bns_gcn_b200  # noqa: F401
+    from bns_gcn_b200 import train
+    from bns_gcn_b200.data import make_local_partition
+    from bns_gcn_b200.helper.utils import get_boundary
+    p = make_local_partition("papers100m", rank, world, seed=0, device=torch.device("cpu"), scale=0.0002)
+    boundary = get_boundary(p.node_dict, p.gpb)
+    send_size, _ = train.get_send_size(boundary, 0.1)
+    recv_size = train.get_recv_size(p.node_dict, 0.1)
+    out_deg = train.collect_out_degree(p.node_dict, boundary)
+    ip, ix = p.graph.indptr, p.graph.indices
+    torch.save({"boundary": boundary, "send": send_size, "recv": recv_size, "nid": p.node_dict["_ID"], "n_in": p.graph.n_in,
+                "n_halo": p.graph.n_halo, "ranges": p.gpb.ranges, "part_id": p.node_dict["part_id"], "indptr": ip,
+                "indices": ix, "in_deg": p.node_dict["in_deg"], "out_deg_all": out_deg, "meta": p.meta},
+               os.path.join(out_dir, f"r{rank}.pt"))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_per_rank_generator_partitions_agree_gloo(tmp_path):
+    """data.make_local_partition (the papers100M-shape path: every rank generates its own piece, the graph never exists
+    as a whole): the pieces of 2 ranks form ONE consistent partitioned graph -- contiguous ownership, halo ids owned by
+    the peer and sorted, boundary lists that mirror the peer's halo, matching send / receive sizes, exact in-degrees,
+    one self loop per node, no duplicate entries."""
+    import torch.multiprocessing as mp
+    world = 2
+    mp.spawn(_local_generator_worker, args=(world, 29671, str(tmp_path)), nprocs=world, join=True)
+    r = [torch.load(os.path.join(tmp_path, f"r{i}.pt")) for i in range(world)]
+    assert torch.equal(r[0]["ranges"], r[1]["ranges"]) and r[0]["meta"] == r[1]["meta"]
+    for me in range(world):
+        a, other = r[me], 1 - me
+        b = r[other]
+        n_in, lo, hi = a["n_in"], int(a["ranges"][me]), int(a["ranges"][me + 1])
+        assert n_in == hi - lo and torch.equal(a["nid"][:n_in], torch.arange(lo, hi))
+        halo = a["nid"][n_in:]
+        assert halo.numel() == a["n_halo"] and torch.all(halo[1:] > halo[:-1])             # sorted, unique
+        assert torch.all((halo < lo) | (halo >= hi)) and torch.all(a["part_id"][n_in:] == other)
+        # what the peer may be asked to send me is exactly my halo, in the peer's local numbering
+        assert torch.equal(b["boundary"][me] + int(a["ranges"][other]), halo)
+        assert a["recv"][other] == b["send"][me] == int(0.1 * halo.numel())
+        ip, ix = a["indptr"], a["indices"].long()
+        assert torch.equal(ip[1:] - ip[:-1], a["in_deg"]) and int(ip[-1]) == ix.numel()
+        rows = torch.repeat_interleave(torch.arange(n_in), ip[1:] - ip[:-1])
+        key = rows * (n_in + a["n_halo"]) + ix
+        assert key.unique().numel() == key.numel()                                          # no duplicate entries
+        assert int(((ix == rows).long()).sum()) == n_in                                     # one self loop per node
+        assert torch.unique(ix[ix >= n_in]).numel() == a["n_halo"]                          # every halo node is used
+        assert a["out_deg_all"].numel() == n_in + a["n_halo"]
+
+
 def test_dense_split_k_plan_is_sane_without_a_gpu(built):
     """``bns_dense_nt_workspace_bytes`` is pure host arithmetic (SM count falls back to 148 without a device): the
     weight-gradient contraction is cut into slices of at most 48 k-blocks of 32 rows (accumulation-chain bound,
