@@ -29,7 +29,7 @@ def main():
         unit = launches[0]["dram__bytes_read.sum"][1]
         scale = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}.get(unit, 1.0)
         res[str(world)] = {"dram_bytes_per_launch": dram * scale, "kernel_launches_summed": len(launches),
-                           "source": f"ncu --metrics dram__bytes_*.sum --clock-control none, gpurun_out/{name} "
+                           "source": f"ncu --metrics dram__bytes_*.sum --clock-control none, profiles/{name} "
                                      "(tools/ncu_spmm_traffic.sh, round 2)"}
         lines.append(f"## world {world}: {len(launches)} kernel launch(es) per logical SpMM")
         for k in launches:
