@@ -349,7 +349,7 @@ int bns_gat_softmax_bwd_f32(const bns_graph_t *a_in, const bns_graph_t *a_out, c
                             const int32_t *cpos, int64_t x_halo_base, int32_t heads, const float *el, const float *er,
                             float negative_slope, float p_drop, uint64_t seed, uint64_t offset, const uint64_t *offset_dev,
                             const float *P_in, const float *P_out, float *dE_in, float *dE_out, float *d_er, void *stream);
-/* el / er of GATConv: out[r, h] = <X[r, h*Fo:(h+1)*Fo], attn[h, :]>, and its backward: dX[r, h, :] (+)= s[r, h] * attn[h, :],
+/* el / er of GATConv (module/model.py:102; DGL 0.9 gatconv.py: el = (feat_src * attn_l).sum(-1), er likewise): out[r, h] = <X[r, h*Fo:(h+1)*Fo], attn[h, :]>, and its backward: dX[r, h, :] (+)= s[r, h] * attn[h, :],
  * d_attn[h, :] = sum_r s[r, h] * X[r, h, :] (deterministic).  ws: bns_colsum_workspace_bytes(heads * Fo). */
 int bns_gat_proj_f32(const float *X, int64_t ldx, int64_t rows, int32_t heads, int32_t Fo, const float *attn, float *out,
                      void *stream);
