@@ -1,12 +1,24 @@
 // gat.cuh -- GATConv's attention as kernels (included by bnsgcn.cu).  Reference: module/model.py:96-132 builds
 // dgl.nn.GATConv(in, out, heads, dropout, dropout); per layer DGL runs  e = leaky_relu(el_u + er_v)  (u_add_v),
 // a = edge_softmax(e), a = attn_drop(a), rst_v = sum_u a_uv ft_u  (u_mul_e + sum) and their autograd.  Round 1 did the
-// per-entry algebra with ~25 ATen launches over [nnz, heads] temporaries and one SpMM launch per head.  Here:
+// per-entry algebra with ~25 ATen launches over [nnz, heads] temporaries and one SpMM launch per head.  Here, two forms
+// of the same algebra (same Philox mask, tests compare them):
 //
+// (A) staged -- what graph.GatAttention runs (profiles/gat_r02.md: 2-3x faster on low-degree graphs)
+//   gat_proj_kernel / gat_proj_bwd_kernel   el = <ft, attn_l>, er = <ft, attn_r> per head and their backward
+//   gat_scores_kernel        one warp per destination row, scalars only: score -> online max / sum -> probability P and
+//                            dropped attention a' per entry (a' of the halo entries also at their compacted positions)
+//   (rst = A' ft is the weighted SpMM per head: bns_spmm_weighted_f32 + bns_spmm_compact_f32;
+//    d a' = <d rst_v, ft_u> is bns_sddmm_dot_f32)
+//   gat_softmax_bwd_kernel   one warp per destination row, scalars only: d a' -> d e per entry (in place), d er_v
+//
+// (B) one launch per direction (BNS_GAT_ROWWALK=1)
 //   gat_fwd_kernel     one warp per destination row, all heads: score -> max -> sum -> probability (stored per entry for
 //                      the backward) -> Philox dropout -> weighted accumulation of the gathered ft rows
 //   gat_bwd_kernel     one warp per destination row: d a = <d rst_v, ft_u> (SDDMM) -> softmax / leaky-relu backward ->
 //                      d e per entry, d er_v; writes the dropped attention a' for the transposed SpMM
+//
+// both:
 //   gat_colsum_kernel  d el_u = sum over the entries of column u of d e (walks the static transposes through their
 //                      entry permutation: deterministic, no atomics)
 //   (d ft = A'^T d rst is the weighted transposed SpMM: spmm_kernel with per-entry weights looked up through the
