@@ -258,3 +258,28 @@ def test_metis_standin_finds_planted_structure(objective):
     start = assign_parts(fg, 4, "random", 1)
     better = refine_label_propagation(fg, start, 4, objective)
     assert partition_quality(fg, better, 4)[objective] <= partition_quality(fg, start, 4)[objective]
+
+
+def test_integration_md_examples_have_the_abi_arity(built):
+    """Every `_L.bns_*(...)` call shown in INTEGRATION.md passes as many arguments as include/bnsgcn.h declares (the
+    reference-side stubs a maintainer would paste must at least bind)."""
+    from bns_gcn_b200 import _lib
+    txt = open(os.path.join(ROOT, "INTEGRATION.md")).read()
+    seen = 0
+    for m in re.finditer(r"_L\.(bns_[a-z0-9_]+)\(", txt):
+        name, i, depth, commas = m.group(1), m.end(), 1, 0
+        while depth > 0 and i < len(txt):
+            ch = txt[i]
+            if ch in "([{":
+                depth += 1
+            elif ch in ")]}":
+                depth -= 1
+            elif ch == "," and depth == 1:
+                commas += 1
+            i += 1
+        body = txt[m.end():i - 1].strip()
+        n_args = 0 if not body else commas + 1
+        assert name in _lib.SIGNATURES, name
+        assert n_args == len(_lib.SIGNATURES[name][1]), (name, n_args, len(_lib.SIGNATURES[name][1]))
+        seen += 1
+    assert seen >= 30
