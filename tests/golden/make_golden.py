@@ -42,6 +42,11 @@ CONFIGS = {
     "gcn_small": dict(shape="small", n_parts=4, model="gcn", n_layers=3, n_hidden=32, rate=0.1, epochs=2, slim=True),
     "graphsage_nlin_induc": dict(shape="tiny", n_parts=3, model="graphsage", n_layers=3, n_hidden=16, rate=0.5, epochs=3,
                                  n_linear=1, inductive=True, slim=True),
+    # GAT, 2 heads: the reference's GAT model / precompute / construct_feat / epoch loop (module/model.py:96-132,
+    # train.py:208-209, :284-297, :401-402) run as they are; the layer they instantiate, dgl.nn.GATConv, comes from the
+    # stand-in below (GATConvStandIn: DGL 0.9's published forward as a DENSE masked softmax -- a different formulation
+    # from the oracle's and the product's entry-list one, so this pins the wiring AND cross-checks the op)
+    "gat": dict(shape="tiny", n_parts=2, model="gat", n_layers=3, n_hidden=16, rate=0.5, epochs=3, heads=2),
 }
 
 
@@ -157,6 +162,55 @@ class FakeHetero:
                 v.data.update(saved[k])
 
 
+class GATConvStandIn(torch.nn.Module):
+    """dgl.nn.GATConv (DGL 0.9, python/dgl/nn/pytorch/conv/gatconv.py) for the call the reference makes --
+    ``GATConv(in, out, heads, feat_drop, attn_drop)`` applied as ``layer(g, (h_src, h_dst))`` on the bipartite graph:
+
+        ft = fc(feat_drop(h)).view(-1, H, F);  el = (ft_src * attn_l).sum(-1);  er = (ft_dst * attn_r).sum(-1)
+        e_uv = leaky_relu(el_u + er_v, 0.2);   a = attn_drop(edge_softmax(g, e));   rst_v = sum_u a_uv ft_u + bias
+
+    Same constructor order / parameter names / initialisation as DGL (fc, attn_l, attn_r, bias; xavier-normal with the
+    ReLU gain, zero bias).  The attention is written DENSE here: an [n_v, n_u, H] score tensor, -inf where there is no
+    edge, softmax over the source axis."""
+
+    def __init__(self, in_feats, out_feats, num_heads, feat_drop=0., attn_drop=0., negative_slope=0.2, residual=False,
+                 activation=None, allow_zero_in_degree=False, bias=True):
+        super().__init__()
+        assert not residual and activation is None
+        nn = torch.nn
+        self._num_heads, self._out_feats = num_heads, out_feats
+        self.fc = nn.Linear(in_feats, out_feats * num_heads, bias=False)
+        self.attn_l = nn.Parameter(torch.FloatTensor(size=(1, num_heads, out_feats)))
+        self.attn_r = nn.Parameter(torch.FloatTensor(size=(1, num_heads, out_feats)))
+        self.feat_drop, self.attn_drop = nn.Dropout(feat_drop), nn.Dropout(attn_drop)
+        self.leaky_relu = nn.LeakyReLU(negative_slope)
+        self.bias = nn.Parameter(torch.FloatTensor(size=(num_heads * out_feats,)))
+        gain = nn.init.calculate_gain('relu')
+        nn.init.xavier_normal_(self.fc.weight, gain=gain)
+        nn.init.xavier_normal_(self.attn_l, gain=gain)
+        nn.init.xavier_normal_(self.attn_r, gain=gain)
+        nn.init.constant_(self.bias, 0)
+
+    def forward(self, graph, feat):
+        H, F = self._num_heads, self._out_feats
+        h_src, h_dst = self.feat_drop(feat[0]), self.feat_drop(feat[1])
+        ft_src = self.fc(h_src).view(-1, H, F)
+        ft_dst = self.fc(h_dst).view(-1, H, F)
+        n_u, n_v = ft_src.shape[0], ft_dst.shape[0]
+        assert int(graph.u.max()) < n_u and int(graph.v.max()) < n_v
+        if (torch.bincount(graph.v, minlength=n_v) == 0).any():
+            raise RuntimeError("There are 0-in-degree nodes in the graph")       # DGLError in DGL
+        el = (ft_src * self.attn_l).sum(dim=-1)                                  # [n_u, H]
+        er = (ft_dst * self.attn_r).sum(dim=-1)                                  # [n_v, H]
+        score = self.leaky_relu(el.unsqueeze(0) + er.unsqueeze(1))               # [n_v, n_u, H]
+        adj = torch.zeros(n_v, n_u, dtype=torch.bool)
+        adj[graph.v, graph.u] = True
+        score = score.masked_fill(~adj.unsqueeze(-1), float('-inf'))
+        a = self.attn_drop(torch.softmax(score, dim=1))
+        rst = torch.einsum('vuh,uhf->vhf', a, ft_src)
+        return rst + self.bias.view(1, H, F)
+
+
 def _node_subgraph(g, mask):
     keep = torch.nonzero(mask, as_tuple=True)[0]
     new = torch.full((g.n,), -1, dtype=torch.long)
@@ -180,7 +234,7 @@ def install_dgl_shim():
     dist_m = types.ModuleType("dgl.distributed")
     dist_m.partition_graph = None
     nn_m = types.ModuleType("dgl.nn")
-    nn_m.GATConv = object
+    nn_m.GATConv = GATConvStandIn
     dgl.data, dgl.distributed, dgl.nn = data, dist_m, nn_m
     ogb = types.ModuleType("ogb")
     ogbn = types.ModuleType("ogb.nodeproppred")
@@ -269,7 +323,7 @@ def worker(rank, world, cfg, port, out_dir):
             return torch.arange(int(part.gpb.ranges[i]), int(part.gpb.ranges[i + 1]))
 
     args = argparse.Namespace(dataset="synthetic", model=cfg["model"], dropout=0.0, lr=1e-2, sampling_rate=cfg["rate"],
-                              heads=1, n_epochs=cfg["epochs"], n_partitions=world, n_hidden=cfg["n_hidden"],
+                              heads=cfg.get("heads", 1), n_epochs=cfg["epochs"], n_partitions=world, n_hidden=cfg["n_hidden"],
                               n_layers=cfg["n_layers"], log_every=1, weight_decay=0.0, norm=cfg.get("norm", "layer"),
                               n_linear=cfg.get("n_linear", 0), use_pp=True, inductive=cfg.get("inductive", False), seed=0, backend="gloo", eval=False,
                               graph_name="golden", n_feat=part.meta["n_feat"], n_class=part.meta["n_class"],

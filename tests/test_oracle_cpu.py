@@ -26,14 +26,14 @@ def _oracle_run(cfg, selected_per_epoch):
     def fn(comm, r):
         rk = O.OracleRank(O.RankInput.from_partition(parts[r]), comm, model=cfg["model"], n_layers=cfg["n_layers"],
                           n_hidden=cfg["n_hidden"], sampling_rate=cfg["rate"], dropout=0.0, seed=0,
-                          norm=cfg.get("norm", "layer"), n_linear=cfg.get("n_linear", 0))
+                          norm=cfg.get("norm", "layer"), n_linear=cfg.get("n_linear", 0), heads=cfg.get("heads", 1))
         for e in range(cfg["epochs"]):
             rk.epoch(selected=selected_per_epoch[e][r], trace=True)
         return rk
     return O.run_threads(cfg["n_parts"], fn)
 
 
-@pytest.mark.parametrize("name", ["graphsage", "gcn", "graphsage_bn"])
+@pytest.mark.parametrize("name", ["graphsage", "gcn", "graphsage_bn", "gat"])
 def test_oracle_reproduces_reference_golden(name):
     """The oracle, fed the index sets the reference drew, reproduces what the reference computed:
     boundary sets exactly; precomputed features, layer outputs, logits, reduced grads, updated weights to 1e-5."""
@@ -55,6 +55,8 @@ def test_oracle_reproduces_reference_golden(name):
         for i, lo in enumerate(g["layer_out"][-1]):
             if bn and i < last:
                 continue
+            if lo.dim() == 3:                      # GATConv returns [n, heads, F]; the model (and the trace) averages heads
+                lo = lo.mean(1)
             assert _rel(rk.trace[f"layer{i}"], lo) < 1e-5, (r, i)
         assert _rel(rk.trace["logits"], g["logits"][-1]) < 1e-5
         for k, (p, gp, gg) in enumerate(zip(rk.net.parameters(), g["params"], g["grads"])):
