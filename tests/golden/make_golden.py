@@ -47,6 +47,9 @@ CONFIGS = {
     # stand-in below (GATConvStandIn: DGL 0.9's published forward as a DENSE masked softmax -- a different formulation
     # from the oracle's and the product's entry-list one, so this pins the wiring AND cross-checks the op)
     "gat": dict(shape="tiny", n_parts=2, model="gat", n_layers=3, n_hidden=16, rate=0.5, epochs=3, heads=2),
+    # --sampling-rate 0 (BNS-GCN's p = 0 end of the sweep): no boundary node is ever sampled, send sizes and ratios are 0
+    "graphsage_rate0": dict(shape="tiny", n_parts=2, model="graphsage", n_layers=3, n_hidden=16, rate=0.0, epochs=2,
+                            slim=True),
 }
 
 

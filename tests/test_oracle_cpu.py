@@ -139,12 +139,12 @@ def test_philox_sampler_properties():
     assert np.array_equal(s[0], sample_boundary(b, k, seed=7, offset=3)[0])
 
 
-@pytest.mark.parametrize("fixture", ["graphsage_small_p8", "gcn_small_p4", "graphsage_nlin_induc_p3"])
+@pytest.mark.parametrize("fixture", ["graphsage_small_p8", "gcn_small_p4", "graphsage_nlin_induc_p3", "graphsage_rate0_p2"])
 def test_oracle_reproduces_reference_golden_slim(fixture):
     """The same pin on wider configurations (slim fixtures: every rank's index sets, rank 0's tensors): 8 partitions
     (7 peers per rank, 6000-node graph); GCN over 4 ranks at sampling rate 0.1; GraphSAGE with a trailing nn.Linear
-    (--n-linear 1) on the inductive graph over 3 ranks.  The reference's own train.run on gloo vs the oracle fed the
-    index sets the reference drew."""
+    (--n-linear 1) on the inductive graph over 3 ranks; --sampling-rate 0 (nothing is ever exchanged, ratio 0).  The
+    reference's own train.run on gloo vs the oracle fed the index sets the reference drew."""
     gold = torch.load(os.path.join(GOLD, f"ref_{fixture}.pt"))
     cfg, ranks = gold["config"], gold["ranks"]
     sel = [[ranks[r]["selected"][e] for r in range(cfg["n_parts"])] for e in range(cfg["epochs"])]
