@@ -48,6 +48,10 @@ CONFIGS = {
     # from the oracle's and the product's entry-list one, so this pins the wiring AND cross-checks the op)
     "gat": dict(shape="tiny", n_parts=2, model="gat", n_layers=3, n_hidden=16, rate=0.5, epochs=3, heads=2),
     # --sampling-rate 0 (BNS-GCN's p = 0 end of the sweep): no boundary node is ever sampled, send sizes and ratios are 0
+    # BASELINE configs[3] in miniature: multi-label targets, --dataset yelp selects BCEWithLogitsLoss(reduction='sum')
+    # (train.py:358-361), 2-layer GAT, 1 head
+    "gat_yelp": dict(shape="tiny-ml", n_parts=2, model="gat", n_layers=2, n_hidden=16, rate=0.5, epochs=3, heads=1,
+                     dataset="yelp"),
     "graphsage_rate0": dict(shape="tiny", n_parts=2, model="graphsage", n_layers=3, n_hidden=16, rate=0.0, epochs=2,
                             slim=True),
 }
@@ -325,7 +329,7 @@ def worker(rank, world, cfg, port, out_dir):
         def partid2nids(self, i):
             return torch.arange(int(part.gpb.ranges[i]), int(part.gpb.ranges[i + 1]))
 
-    args = argparse.Namespace(dataset="synthetic", model=cfg["model"], dropout=0.0, lr=1e-2, sampling_rate=cfg["rate"],
+    args = argparse.Namespace(dataset=cfg.get("dataset", "synthetic"), model=cfg["model"], dropout=0.0, lr=1e-2, sampling_rate=cfg["rate"],
                               heads=cfg.get("heads", 1), n_epochs=cfg["epochs"], n_partitions=world, n_hidden=cfg["n_hidden"],
                               n_layers=cfg["n_layers"], log_every=1, weight_decay=0.0, norm=cfg.get("norm", "layer"),
                               n_linear=cfg.get("n_linear", 0), use_pp=True, inductive=cfg.get("inductive", False), seed=0, backend="gloo", eval=False,

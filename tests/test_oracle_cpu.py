@@ -26,14 +26,15 @@ def _oracle_run(cfg, selected_per_epoch):
     def fn(comm, r):
         rk = O.OracleRank(O.RankInput.from_partition(parts[r]), comm, model=cfg["model"], n_layers=cfg["n_layers"],
                           n_hidden=cfg["n_hidden"], sampling_rate=cfg["rate"], dropout=0.0, seed=0,
-                          norm=cfg.get("norm", "layer"), n_linear=cfg.get("n_linear", 0), heads=cfg.get("heads", 1))
+                          norm=cfg.get("norm", "layer"), n_linear=cfg.get("n_linear", 0), heads=cfg.get("heads", 1),
+                          multilabel=(cfg.get("dataset") == "yelp"))
         for e in range(cfg["epochs"]):
             rk.epoch(selected=selected_per_epoch[e][r], trace=True)
         return rk
     return O.run_threads(cfg["n_parts"], fn)
 
 
-@pytest.mark.parametrize("name", ["graphsage", "gcn", "graphsage_bn", "gat"])
+@pytest.mark.parametrize("name", ["graphsage", "gcn", "graphsage_bn", "gat", "gat_yelp"])
 def test_oracle_reproduces_reference_golden(name):
     """The oracle, fed the index sets the reference drew, reproduces what the reference computed:
     boundary sets exactly; precomputed features, layer outputs, logits, reduced grads, updated weights to 1e-5."""
