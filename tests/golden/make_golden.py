@@ -31,6 +31,11 @@ ROOT = os.path.dirname(os.path.dirname(HERE))
 CONFIGS = {
     "graphsage": dict(shape="tiny", n_parts=2, model="graphsage", n_layers=3, n_hidden=16, rate=0.5, epochs=3),
     "gcn": dict(shape="tiny", n_parts=2, model="gcn", n_layers=3, n_hidden=16, rate=0.5, epochs=3),
+    # the same two runs, plus the reference's evaluation forward on the whole graph with the trained weights
+    "graphsage_eval": dict(shape="tiny", n_parts=2, model="graphsage", n_layers=3, n_hidden=16, rate=0.5, epochs=2,
+                           eval_logits=True, slim=True),
+    "gcn_eval": dict(shape="tiny", n_parts=2, model="gcn", n_layers=3, n_hidden=16, rate=0.5, epochs=2,
+                     eval_logits=True, slim=True),
     "graphsage_bn": dict(shape="tiny", n_parts=2, model="graphsage", n_layers=3, n_hidden=16, rate=0.5, epochs=3,
                          norm="batch", graph_override={"train": 1.0}),   # whole_size == #nodes, as under --inductive
     # 8 gloo processes, 7 peers per rank; "slim": keep every rank's index sets but only rank 0's tensors (the reduced
@@ -121,6 +126,23 @@ class FakeGraph:
         keep = torch.ones(self.u.numel(), dtype=torch.bool)
         keep[eids] = False
         self.u, self.v = self.u[keep], self.v[keep]
+
+    # the evaluation branch of the layers (module/layer.py:39-45, 93-102) works on the homogeneous graph directly
+    @contextlib.contextmanager
+    def local_scope(self):
+        saved = dict(self.ndata)
+        try:
+            yield
+        finally:
+            self.ndata.clear()
+            self.ndata.update(saved)
+
+    def update_all(self, msg, red):
+        h = self.ndata[msg[1]]
+        out = torch.zeros(self.n, *h.shape[1:], dtype=h.dtype).index_add_(0, self.v, h[self.u])
+        if red[0] == "mean":
+            out = out / self.in_degrees().clamp(min=1).to(h.dtype).view(-1, *([1] * (h.dim() - 1)))
+        self.ndata[red[2]] = out
 
 
 class _EdgeType:
@@ -392,6 +414,15 @@ def worker(rank, world, cfg, port, out_dir):
     ref_train.run(subg, node_dict, GPB(), args)        # <- the reference's own driver, unmodified
 
     m = holder["model"]
+    if cfg.get("eval_logits") and rank == 0:
+        # the reference's evaluation forward (train.py:44-49: model.eval(); model(g, feat)) on the WHOLE graph with the
+        # trained weights: the layers' evaluation branches (degrees taken from the graph, module/layer.py:39-45, 93-102)
+        full = FakeGraph(fg.src.clone(), fg.dst().clone(), fg.n_nodes)
+        was_training = m.training
+        m.eval()
+        with torch.no_grad():
+            rec["eval_logits"] = m(full, fg.feat.clone()).detach().clone()
+        m.train(was_training)
     rec["params"] = [p.detach().clone() for p in m.parameters()]
     rec["grads"] = [p.grad.detach().clone() for p in m.parameters()]
     rec["param_names"] = [n for n, _ in m.named_parameters()]
@@ -412,7 +443,7 @@ def main():
             mp.spawn(worker, args=(cfg["n_parts"], cfg, 29600 + i, d), nprocs=cfg["n_parts"], join=True)
             ranks = [torch.load(os.path.join(d, f"rank{r}.pt")) for r in range(cfg["n_parts"])]
         if cfg.get("slim"):
-            keep0 = ("selected", "boundary", "param_names", "logits", "layer_out", "params", "grads")
+            keep0 = ("selected", "boundary", "param_names", "logits", "layer_out", "params", "grads", "eval_logits")
             ranks = [{k: ([v[-1]] if k in ("logits", "layer_out") else v) for k, v in rk.items()
                       if k in (keep0 if r == 0 else ("selected", "boundary", "param_names"))} for r, rk in enumerate(ranks)]
         out = os.path.join(HERE, f"ref_{name}_p{cfg['n_parts']}.pt")

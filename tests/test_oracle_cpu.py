@@ -164,6 +164,30 @@ def test_oracle_reproduces_reference_golden_slim(fixture):
             assert _rel(p.grad, gg) < 1e-5, (r, nm)
 
 
+@pytest.mark.parametrize("model", ["graphsage", "gcn"])
+def test_oracle_evaluation_forward_reproduces_the_references(model):
+    """tests/golden/ref_<model>_eval_p2.pt: after two training epochs make_golden.py runs the reference's evaluation
+    forward (train.py:44-49: model.eval(); model(g, feat)) on the whole graph.  The oracle, trained on the same index
+    sets, evaluated the same way (layers' evaluation branches, module/layer.py:39-45, 93-102: degrees from the graph,
+    layer 0 concatenates [feat | mean] itself) gives the same logits."""
+    import bns_gcn_b200  # noqa: F401
+    from bns_gcn_b200.data import make_graph
+    from oracle import bns_oracle as O
+    gold = torch.load(os.path.join(GOLD, f"ref_{model}_eval_p2.pt"))
+    cfg, ranks = gold["config"], gold["ranks"]
+    sel = [[ranks[r]["selected"][e] for r in range(cfg["n_parts"])] for e in range(cfg["epochs"])]
+    out = _oracle_run(cfg, sel)
+    fg = make_graph(cfg["shape"], seed=0, device=torch.device("cpu"))
+    net = out[0].net
+    net.eval()
+    out[0].trace = None
+    with torch.no_grad():
+        logits = net(O.EdgeList(fg.src, fg.dst(), fg.n_nodes, fg.n_nodes), fg.feat)
+    want = ranks[0]["eval_logits"]
+    assert logits.shape == want.shape == (fg.n_nodes, fg.n_class)
+    assert _rel(logits, want) < 1e-5
+
+
 def test_oracle_active_set_override():
     """``OracleRank.epoch(relu_masks=...)`` (the kink-aware leg of tests/harness.py): prescribing the oracle's OWN
     active sets changes nothing; flipping the entry closest to the kink is counted, its distance from zero reported,
