@@ -283,3 +283,36 @@ def test_integration_md_examples_have_the_abi_arity(built):
         assert n_args == len(_lib.SIGNATURES[name][1]), (name, n_args, len(_lib.SIGNATURES[name][1]))
         seen += 1
     assert seen >= 30
+
+
+def test_header_is_plain_c_and_links(built, tmp_path):
+    """include/bnsgcn.h is the drop-in boundary: a C (not C++) translation unit that includes nothing but that header
+    compiles with -Wall -Werror -pedantic, links against libbnsgcn.so and can call the entry points that need no GPU."""
+    import shutil
+    import subprocess
+    if shutil.which("gcc") is None:
+        pytest.skip("no gcc")
+    src = tmp_path / "abi_probe.c"
+    src.write_text(
+        '#include "bnsgcn.h"\n'
+        '#include <stdio.h>\n'
+        '#include <string.h>\n'
+        'int main(void) {\n'
+        '    struct bns_epoch_maps m; struct bns_put_all p; struct bns_derive_entry d;\n'
+        '    memset(&m, 0, sizeof m); memset(&p, 0, sizeof p); memset(&d, 0, sizeof d);\n'
+        '    if (bns_abi_version() != BNS_ABI_VERSION) return 2;\n'
+        '    if (bns_spmm_workspace_bytes(NULL, 16) != 0) return 3;\n'
+        '    if (bns_spmm_sum_f32(NULL, NULL, 0, 0, NULL, 0, NULL, NULL, NULL, NULL, NULL, 0, 0, 0, 0, NULL, 0, NULL) >= 0) return 4;\n'
+        '    if (strlen(bns_last_error()) == 0) return 5;\n'
+        '    printf("abi %d peers %d\\n", bns_abi_version(), BNS_MAX_PEERS);\n'
+        '    return 0;\n'
+        '}\n')
+    lib_dir = os.path.join(ROOT, "bns-gcn_b200", "csrc")
+    exe = tmp_path / "abi_probe"
+    cc = subprocess.run(["gcc", "-std=c11", "-Wall", "-Werror", "-pedantic", "-I", os.path.join(ROOT, "include"), str(src),
+                         "-o", str(exe), "-L", lib_dir, "-lbnsgcn", f"-Wl,-rpath,{lib_dir}"],
+                        capture_output=True, text=True)
+    assert cc.returncode == 0, cc.stderr
+    run = subprocess.run([str(exe)], capture_output=True, text=True)
+    assert run.returncode == 0, (run.returncode, run.stdout, run.stderr)
+    assert run.stdout.startswith("abi ")
